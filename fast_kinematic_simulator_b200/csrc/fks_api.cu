@@ -1,0 +1,725 @@
+// C ABI of libfksgpu.so (include/fksgpu.h): uploads, launch plumbing, statistics.
+// The computation itself is in fks_kernels.cu; the environment builder in host/environment_builder.cpp.
+// There is NO CPU fallback: every compute entry point fails with FKS_ERR_NO_DEVICE / FKS_ERR_CUDA when
+// the device path cannot run.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "fks_device_types.h"
+
+using namespace fksdev;
+
+namespace fks_host {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace fks_host
+
+namespace {
+
+int fail(int code, const std::string& msg) {
+    fks_host::set_last_error(msg);
+    return code;
+}
+int cuda_fail(cudaError_t err, const char* what) {
+    return fail(FKS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err));
+}
+#define FKS_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int upload(T** dst, const T* src, size_t n) {
+    *dst = nullptr;
+    if (n == 0) n = 1;
+    FKS_CUDA(cudaMalloc((void**)dst, n * sizeof(T)));
+    if (src) FKS_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return FKS_OK;
+}
+
+template <typename T>
+int ensure(T** ptr, size_t* cap, size_t need) {
+    if (need <= *cap) return FKS_OK;
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    const size_t want = need + need / 4;
+    FKS_CUDA(cudaMalloc((void**)ptr, want * sizeof(T)));
+    *cap = want;
+    return FKS_OK;
+}
+
+}  // namespace
+
+struct fks_env {
+    int device;
+    DevEnv dev;
+    float* d_sdf;
+    unsigned long long* d_keys;
+    uint2* d_vals;
+    double* d_entries;
+    size_t sdf_bytes;
+    size_t l2_window_bytes;
+};
+
+struct fks_robot {
+    int device;
+    DevRobot host;
+    DevRobot* d_robot;
+    double *d_px, *d_py, *d_pz;
+    int* d_plink;
+    int stride;
+};
+
+struct fks_sim {
+    int device;
+    const fks_env* env;
+    const fks_robot* robot;
+    DevSolver sp;
+    uint64_t seed;
+    int32_t debug_level;
+    cudaStream_t stream;
+    int grid_max;
+    size_t dyn_smem;
+    KernelInfo kinfo;
+    ScratchLayout sl;
+    char* d_scratch;
+    unsigned long long* d_stats;
+    unsigned int* d_counter;
+    // staging for the host-buffer entry point (grown on demand)
+    double *d_starts, *d_targets, *d_tape;
+    unsigned long long* d_tape_off;
+    char* d_results;
+    size_t cap_starts, cap_targets, cap_tape, cap_tape_off, cap_results;
+    uint64_t launches;
+    std::string info;
+};
+
+extern "C" {
+
+int fks_abi_version(void) { return FKS_ABI_VERSION; }
+
+const char* fks_last_error_string(void) { return fks_host::g_last_error.c_str(); }
+
+int fks_device_count(int* count) {
+    if (!count) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_device_count: null argument");
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess) {
+        *count = 0;
+        return fail(FKS_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(err));
+    }
+    *count = n;
+    return FKS_OK;
+}
+
+void fks_default_solver_params(fks_solver_params* out) {
+    if (!out) return;
+    out->forward_simulation_time = 1.0;
+    out->simulation_shortcut_distance = 0.0;
+    out->environment_collision_check_tolerance = 0.001;
+    out->resolve_correction_step_scaling_decay_rate = 0.5;
+    out->resolve_correction_initial_step_size = 1.0;
+    out->resolve_correction_min_step_scaling = 0.03125;
+    out->max_resolver_iterations = 25;
+    out->resolve_correction_step_scaling_decay_iterations = 5;
+    out->failed_resolves_end_motion = 1;
+    out->_pad = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// environment
+// ---------------------------------------------------------------------------------------------
+int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
+    if (!desc || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: null argument");
+    *out = nullptr;
+    if (!desc->sdf || desc->nx <= 0 || desc->ny <= 0 || desc->nz <= 0 || desc->nx > 65535 || desc->ny > 65535 ||
+        desc->nz > 65535 || !(desc->sdf_resolution > 0.0) || !(desc->map_resolution > 0.0))
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: bad grid description");
+    if (desc->n_normal_cells < 0 || (desc->n_normal_cells > 0 && (!desc->normal_cell_index || !desc->normal_cell_start || !desc->normal_entries)))
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: bad surface-normal table");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FKS_ERR_NO_DEVICE, "fks_env_create: no CUDA device");
+    if (device < 0 || device >= ndev) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: bad device index");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_env_create: cudaSetDevice failed");
+
+    fks_env* env = new (std::nothrow) fks_env();
+    if (!env) return fail(FKS_ERR_OUT_OF_MEMORY, "fks_env_create: out of host memory");
+    std::memset(env, 0, sizeof(*env));
+    env->device = device;
+    const size_t ncells = (size_t)desc->nx * (size_t)desc->ny * (size_t)desc->nz;
+    env->sdf_bytes = ncells * sizeof(float);
+    int rc = upload(&env->d_sdf, desc->sdf, ncells);
+    if (rc != FKS_OK) { fks_env_destroy(env); return rc; }
+
+    // surface normals: open-addressing hash, load factor <= 0.5, linear probing
+    const size_t ncell_n = (size_t)desc->n_normal_cells;
+    size_t cap = 2;
+    while (cap < 2 * ncell_n) cap <<= 1;
+    std::vector<unsigned long long> keys(cap, 0ull);
+    std::vector<uint2> vals(cap, make_uint2(0u, 0u));
+    const size_t nentries = ncell_n ? (size_t)desc->normal_cell_start[ncell_n] : 0;
+    for (size_t i = 0; i < ncell_n; i++) {
+        const int64_t li = desc->normal_cell_index[i];
+        if (li < 0 || (size_t)li >= ncells || desc->normal_cell_start[i + 1] < desc->normal_cell_start[i]) {
+            fks_env_destroy(env);
+            return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: surface-normal cell out of range");
+        }
+        size_t h = (size_t)(normal_hash((unsigned long long)li) & (cap - 1));
+        while (keys[h] != 0ull) {
+            if (keys[h] == (unsigned long long)li + 1ull) {
+                fks_env_destroy(env);
+                return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: duplicate surface-normal cell");
+            }
+            h = (h + 1) & (cap - 1);
+        }
+        keys[h] = (unsigned long long)li + 1ull;
+        vals[h] = make_uint2(desc->normal_cell_start[i], desc->normal_cell_start[i + 1] - desc->normal_cell_start[i]);
+    }
+    std::vector<double> entries(std::max<size_t>(nentries, 1) * 6, 0.0);
+    for (size_t en = 0; en < nentries; en++) {
+        const double* src = desc->normal_entries + 7 * en;  // entry direction xyzw (w == 0), normal xyz
+        entries[6 * en + 0] = src[0];
+        entries[6 * en + 1] = src[1];
+        entries[6 * en + 2] = src[2];
+        entries[6 * en + 3] = src[4];
+        entries[6 * en + 4] = src[5];
+        entries[6 * en + 5] = src[6];
+    }
+    rc = upload(&env->d_keys, keys.data(), cap);
+    if (rc == FKS_OK) rc = upload(&env->d_vals, vals.data(), cap);
+    if (rc == FKS_OK) rc = upload(&env->d_entries, entries.data(), entries.size());
+    if (rc != FKS_OK) { fks_env_destroy(env); return rc; }
+
+    DevEnv& d = env->dev;
+    std::memcpy(d.origin, desc->origin, sizeof(d.origin));
+    std::memcpy(d.inv_origin, desc->inverse_origin, sizeof(d.inv_origin));
+    d.map_res = desc->map_resolution;
+    d.sdf_res = desc->sdf_resolution;
+    d.inv_sdf_res = 1.0 / desc->sdf_resolution;
+    d.inv_twice_res = 1.0 / (2.0 * desc->sdf_resolution);
+    d.nx = (int)desc->nx;
+    d.ny = (int)desc->ny;
+    d.nz = (int)desc->nz;
+    d.oob = desc->oob_value;
+    d.sdf = env->d_sdf;
+    d.nh_keys = env->d_keys;
+    d.nh_vals = env->d_vals;
+    d.nh_mask = (unsigned long long)(cap - 1);
+    d.normal_entries = env->d_entries;
+
+    // keep the SDF resident in L2 when it fits the persisting carve-out
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        const size_t want = std::min<size_t>(env->sdf_bytes, (size_t)prop.persistingL2CacheMaxSize);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess && env->sdf_bytes <= (size_t)prop.persistingL2CacheMaxSize)
+            env->l2_window_bytes = std::min<size_t>(env->sdf_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    }
+    cudaGetLastError();
+    *out = env;
+    return FKS_OK;
+}
+
+void fks_env_destroy(fks_env* env) {
+    if (!env) return;
+    DeviceGuard guard(env->device);
+    cudaFree(env->d_sdf);
+    cudaFree(env->d_keys);
+    cudaFree(env->d_vals);
+    cudaFree(env->d_entries);
+    delete env;
+}
+
+// ---------------------------------------------------------------------------------------------
+// robot
+// ---------------------------------------------------------------------------------------------
+int fks_robot_create(int device, const fks_robot_desc* r, fks_robot** out) {
+    if (!r || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: null argument");
+    *out = nullptr;
+    if (r->kind != FKS_ROBOT_SE2 && r->kind != FKS_ROBOT_SE3 && r->kind != FKS_ROBOT_LINKED)
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: unknown robot kind");
+    if (r->n_points <= 0 || r->n_points > (1 << 20) || !r->points_xyz || !r->point_link || !r->axes)
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: bad point/axis arrays");
+    const int L = r->n_links, J = r->n_joints, D = r->n_dof;
+    if (L < 1 || L > kMaxLinks || J < 0 || J > kMaxJoints || D < 1 || D > kMaxDof)
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: link/joint/dof count out of range");
+    if (r->kind == FKS_ROBOT_SE2 && (L != 1 || D != 3)) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: SE2 needs 1 link, 3 dof");
+    if (r->kind == FKS_ROBOT_SE3 && (L != 1 || D != 6)) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: SE3 needs 1 link, 6 dof");
+    if (r->kind == FKS_ROBOT_LINKED && (J < 1 || !r->joints)) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: linked robot needs joints");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FKS_ERR_NO_DEVICE, "fks_robot_create: no CUDA device");
+    if (device < 0 || device >= ndev) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: bad device index");
+
+    fks_robot* rob = new (std::nothrow) fks_robot();
+    if (!rob) return fail(FKS_ERR_OUT_OF_MEMORY, "fks_robot_create: out of host memory");
+    std::memset(rob, 0, sizeof(*rob));
+    rob->device = device;
+    DevRobot& h = rob->host;
+    h.kind = r->kind;
+    h.L = L;
+    h.J = (r->kind == FKS_ROBOT_LINKED) ? J : 0;
+    h.D = D;
+    h.P = (int)r->n_points;
+    std::memcpy(h.base, r->base_transform, sizeof(h.base));
+    h.pos_w = r->position_distance_weight;
+    h.rot_w = r->rotation_distance_weight;
+    for (int i = 0; i < D; i++) {
+        const fks_axis_params& a = r->axes[i];
+        DevAxis& d = h.axes[i];
+        d.kp = std::fabs(a.kp);  // pid.hpp:104-113
+        d.ki = std::fabs(a.ki);
+        d.kd = std::fabs(a.kd);
+        d.iclamp = std::fabs(a.integral_clamp);
+        d.vlim = std::fabs(a.velocity_limit);          // unc.hpp:61
+        d.pnoise = std::fabs(a.proportional_noise);
+        d.mnoise = std::fabs(a.minimum_noise);
+        d.sigma = a.noise_sigma;
+    }
+    // points: link-major, point-minor
+    std::vector<double> px((size_t)h.P), py((size_t)h.P), pz((size_t)h.P);
+    std::vector<int> plink((size_t)h.P);
+    for (int l = 0; l <= L; l++) h.link_begin[l] = 0;
+    for (int i = 0; i < h.P; i++) {
+        const int l = r->point_link[i];
+        if (l < 0 || l >= L || (i > 0 && l < r->point_link[i - 1])) {
+            delete rob;
+            return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: point_link must be non-decreasing and < n_links");
+        }
+        px[(size_t)i] = r->points_xyz[3 * i];
+        py[(size_t)i] = r->points_xyz[3 * i + 1];
+        pz[(size_t)i] = r->points_xyz[3 * i + 2];
+        plink[(size_t)i] = l;
+        h.link_begin[l + 1]++;
+    }
+    for (int l = 0; l < L; l++) h.link_begin[l + 1] += h.link_begin[l];
+    // joints (kinematic order: a joint's parent link must already have a transform)
+    int link_parent_joint[kMaxLinks];
+    for (int l = 0; l < L; l++) link_parent_joint[l] = -1;
+    int active = 0;
+    for (int j = 0; j < h.J; j++) {
+        const fks_joint_desc& jd = r->joints[j];
+        if (jd.parent_link < 0 || jd.parent_link >= L || jd.child_link <= 0 || jd.child_link >= L || jd.type < 0 || jd.type > 3 ||
+            (jd.parent_link != 0 && link_parent_joint[jd.parent_link] < 0) || link_parent_joint[jd.child_link] >= 0) {
+            delete rob;
+            return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: joints must form a tree rooted at link 0, in kinematic order");
+        }
+        DevJoint& d = h.joints[j];
+        d.parent = jd.parent_link;
+        d.child = jd.child_link;
+        d.type = jd.type;
+        d.active = (jd.type == FKS_JOINT_FIXED) ? -1 : active++;
+        std::memcpy(d.T, jd.transform, sizeof(d.T));
+        std::memcpy(d.axis, jd.axis, sizeof(d.axis));
+        d.lo = jd.lower_limit;
+        d.hi = jd.upper_limit;
+        d.weight = jd.distance_weight;
+        if (d.active >= 0 && d.active < kMaxDof) h.active_joint[d.active] = j;
+        link_parent_joint[jd.child_link] = j;
+    }
+    if (r->kind == FKS_ROBOT_LINKED && active != D) {  // tnuva.hpp:503-516 throws std::invalid_argument
+        delete rob;
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: number of axis parameter sets != number of active joints");
+    }
+    for (int l = 0; l < L; l++) {
+        unsigned anc = 0u;
+        int j = link_parent_joint[l];
+        while (j >= 0) {
+            anc |= 1u << j;
+            j = link_parent_joint[h.joints[j].parent];
+        }
+        h.link_ancestors[l] = anc;
+    }
+    // self-collision table
+    h.n_pairs = 0;
+    for (int a = 0; a < L; a++) h.disallowed[a] = 0u;
+    if (L > 1 && r->allowed_self_collision) {
+        for (int a = 0; a < L; a++)
+            for (int b = a + 1; b < L; b++) {
+                const bool ab = r->allowed_self_collision[a * L + b] != 0, ba = r->allowed_self_collision[b * L + a] != 0;
+                if (ab != ba) {
+                    delete rob;
+                    return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: allowed_self_collision must be symmetric");
+                }
+                if (!ab) {
+                    h.disallowed[a] |= 1u << b;
+                    h.disallowed[b] |= 1u << a;
+                    h.pair_a[h.n_pairs] = (unsigned char)a;
+                    h.pair_b[h.n_pairs] = (unsigned char)b;
+                    h.n_pairs++;
+                }
+            }
+    }
+    // bounding spheres (slightly inflated) and cumulative masses (spcs.hpp:1244-1255)
+    double acc = 0.0;
+    for (int l = L - 1; l >= 0; l--) {
+        const double m = (double)(h.link_begin[l + 1] - h.link_begin[l]);
+        h.link_mass[l] = m + acc;
+        acc += m;
+    }
+    for (int l = 0; l < L; l++) {
+        double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int p = h.link_begin[l]; p < h.link_begin[l + 1]; p++) {
+            const double v[3] = {px[(size_t)p], py[(size_t)p], pz[(size_t)p]};
+            for (int k = 0; k < 3; k++) {
+                if (p == h.link_begin[l] || v[k] < lo[k]) lo[k] = v[k];
+                if (p == h.link_begin[l] || v[k] > hi[k]) hi[k] = v[k];
+            }
+        }
+        double rad = 0.0;
+        for (int k = 0; k < 3; k++) h.link_center[l][k] = 0.5 * (lo[k] + hi[k]);
+        for (int p = h.link_begin[l]; p < h.link_begin[l + 1]; p++) {
+            const double dx = px[(size_t)p] - h.link_center[l][0], dy = py[(size_t)p] - h.link_center[l][1], dz = pz[(size_t)p] - h.link_center[l][2];
+            rad = std::max(rad, std::sqrt(dx * dx + dy * dy + dz * dz));
+        }
+        h.link_radius[l] = rad * (1.0 + 1e-9) + 1e-12;
+    }
+    rob->stride = (r->kind == FKS_ROBOT_SE2) ? 3 : (r->kind == FKS_ROBOT_SE3 ? 12 : D);
+
+    DeviceGuard guard(device);
+    if (!guard.ok) { delete rob; return fail(FKS_ERR_CUDA, "fks_robot_create: cudaSetDevice failed"); }
+    int rc = upload(&rob->d_robot, &rob->host, 1);
+    if (rc == FKS_OK) rc = upload(&rob->d_px, px.data(), px.size());
+    if (rc == FKS_OK) rc = upload(&rob->d_py, py.data(), py.size());
+    if (rc == FKS_OK) rc = upload(&rob->d_pz, pz.data(), pz.size());
+    if (rc == FKS_OK) rc = upload(&rob->d_plink, plink.data(), plink.size());
+    if (rc != FKS_OK) { fks_robot_destroy(rob); return rc; }
+    *out = rob;
+    return FKS_OK;
+}
+
+void fks_robot_destroy(fks_robot* robot) {
+    if (!robot) return;
+    DeviceGuard guard(robot->device);
+    cudaFree(robot->d_robot);
+    cudaFree(robot->d_px);
+    cudaFree(robot->d_py);
+    cudaFree(robot->d_pz);
+    cudaFree(robot->d_plink);
+    delete robot;
+}
+
+int fks_robot_config_stride(const fks_robot* robot) { return robot ? robot->stride : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// simulator
+// ---------------------------------------------------------------------------------------------
+int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_params* params,
+                   double simulation_controller_frequency, uint64_t prng_seed, int32_t debug_level, fks_sim** out) {
+    if (!env || !robot || !params || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_create: null argument");
+    *out = nullptr;
+    if (env->device != robot->device) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_create: environment and robot live on different devices");
+    if (simulation_controller_frequency == 0.0 || std::isnan(simulation_controller_frequency))
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_create: controller frequency must be non-zero");
+    if (params->resolve_correction_step_scaling_decay_iterations == 0)
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_create: decay iterations must be > 0");
+    DeviceGuard guard(env->device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_sim_create: cudaSetDevice failed");
+    fks_sim* s = new (std::nothrow) fks_sim();
+    if (!s) return fail(FKS_ERR_OUT_OF_MEMORY, "fks_sim_create: out of host memory");
+    s->device = env->device;
+    s->env = env;
+    s->robot = robot;
+    s->seed = prng_seed;
+    s->debug_level = debug_level;
+    s->stream = nullptr;
+    s->d_scratch = nullptr;
+    s->d_stats = nullptr;
+    s->d_counter = nullptr;
+    s->d_starts = s->d_targets = s->d_tape = nullptr;
+    s->d_tape_off = nullptr;
+    s->d_results = nullptr;
+    s->cap_starts = s->cap_targets = s->cap_tape = s->cap_tape_off = s->cap_results = 0;
+    s->launches = 0;
+    const double freq = std::fabs(simulation_controller_frequency);  // spcs.hpp:426
+    s->sp.interval = 1.0 / simulation_controller_frequency;          // spcs.hpp:427 (sign kept)
+    s->sp.shortcut_distance = params->simulation_shortcut_distance;
+    s->sp.check_tolerance = params->environment_collision_check_tolerance;
+    s->sp.decay_rate = params->resolve_correction_step_scaling_decay_rate;
+    s->sp.initial_step = params->resolve_correction_initial_step_size;
+    s->sp.min_scaling = params->resolve_correction_min_step_scaling;
+    s->sp.max_iters = params->max_resolver_iterations;
+    s->sp.decay_iters = params->resolve_correction_step_scaling_decay_iterations;
+    s->sp.n_steps = std::max((uint32_t)(params->forward_simulation_time * freq), 1u);  // spcs.hpp:856
+    s->sp.failed_ends_motion = params->failed_resolves_end_motion ? 1 : 0;
+
+    const DevRobot& h = robot->host;
+    s->dyn_smem = simulate_dyn_smem(h.kind, h.L, h.J, h.D, h.P, robot->stride);
+    int rc = simulate_kernel_info(h.kind, s->dyn_smem, &s->kinfo);
+    if (rc != 0) { delete s; return cuda_fail((cudaError_t)rc, "fks_sim_create: kernel attributes"); }
+    if (s->kinfo.max_blocks_per_sm < 1) { delete s; return fail(FKS_ERR_UNSUPPORTED, "fks_sim_create: robot does not fit one CTA's shared memory"); }
+    cudaDeviceProp prop;
+    cudaError_t err = cudaGetDeviceProperties(&prop, s->device);
+    if (err != cudaSuccess) { delete s; return cuda_fail(err, "cudaGetDeviceProperties"); }
+    s->grid_max = prop.multiProcessorCount * s->kinfo.max_blocks_per_sm;
+    s->sl = make_scratch_layout(h.D, h.P);
+    const size_t scratch_bytes = (size_t)s->grid_max * kWarpsPerBlock * s->sl.total;
+    if ((err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_scratch, scratch_bytes)) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_stats, FKS_NUM_STATS * sizeof(unsigned long long))) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_counter, sizeof(unsigned int))) != cudaSuccess ||
+        (err = cudaMemset(s->d_stats, 0, FKS_NUM_STATS * sizeof(unsigned long long))) != cudaSuccess) {
+        fks_sim_destroy(s);
+        return cuda_fail(err, "fks_sim_create: allocation");
+    }
+    char buf[512];
+    std::snprintf(buf, sizeof(buf),
+                  "simulate_kernel<kind=%d>: %d regs/thread, %zu B dynamic smem/CTA, %d B local/thread, %d threads/CTA, "
+                  "%d CTAs/SM x %d SMs (persistent grid %d), scratch %llu B/warp, L2 window %zu B",
+                  h.kind, s->kinfo.regs, s->dyn_smem, s->kinfo.local_bytes, kThreadsPerBlock, s->kinfo.max_blocks_per_sm,
+                  prop.multiProcessorCount, s->grid_max, (unsigned long long)s->sl.total, env->l2_window_bytes);
+    s->info = buf;
+    *out = s;
+    return FKS_OK;
+}
+
+void fks_sim_destroy(fks_sim* s) {
+    if (!s) return;
+    DeviceGuard guard(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_scratch);
+    cudaFree(s->d_stats);
+    cudaFree(s->d_counter);
+    cudaFree(s->d_starts);
+    cudaFree(s->d_targets);
+    cudaFree(s->d_tape);
+    cudaFree(s->d_tape_off);
+    cudaFree(s->d_results);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+size_t fks_sim_result_stride(const fks_sim* sim) {
+    return sim ? (size_t)sim->robot->stride * 8 + sizeof(fks_result_tail) : 0;
+}
+
+static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* d_targets, size_t n, size_t n_targets,
+                              int allow_contacts, int noise_mode, const double* d_tape, const uint64_t* d_tape_off,
+                              uint64_t first_particle_id, void* d_results, cudaStream_t stream) {
+    if (n == 0) return FKS_OK;
+    if (n > 0xFFFFFF00ull) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate: too many particles for one call");
+    LaunchArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.robot = s->robot->d_robot;
+    a.px = s->robot->d_px;
+    a.py = s->robot->d_py;
+    a.pz = s->robot->d_pz;
+    a.plink = s->robot->d_plink;
+    a.env = s->env->dev;
+    a.sp = s->sp;
+    a.starts = d_starts;
+    a.targets = d_targets;
+    a.n_particles = n;
+    a.n_targets = n_targets;
+    a.allow_contacts = allow_contacts ? 1 : 0;
+    a.noise_mode = noise_mode;
+    a.tape = d_tape;
+    a.tape_off = (const unsigned long long*)d_tape_off;
+    a.seed = s->seed;
+    a.first_id = first_particle_id;
+    a.results = (char*)d_results;
+    a.cfg_stride = s->robot->stride;
+    a.rec_stride = (int)fks_sim_result_stride(s);
+    a.stats = s->d_stats;
+    a.counter = s->d_counter;
+    a.scratch = s->d_scratch;
+    a.scratch_bytes_per_warp = s->sl.total;
+    a.ldj = s->sl.ldj;
+    const size_t blocks_needed = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int grid = (int)std::min<size_t>((size_t)s->grid_max, blocks_needed);
+    FKS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
+    const int rc = launch_simulate(s->robot->host.kind, a, grid, s->dyn_smem, stream, s->env->l2_window_bytes ? s->env->d_sdf : nullptr,
+                                   s->env->l2_window_bytes);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "simulate kernel launch");
+    s->launches++;
+    return FKS_OK;
+}
+
+static int check_batch(const fks_sim* sim, const void* starts, const void* targets, size_t n, size_t n_targets, int noise_mode,
+                       const void* tape_draws, const void* tape_off, const void* results) {
+    if (!sim) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate: null simulator");
+    if (n == 0) return FKS_OK;
+    if (!starts || !targets || !results) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate: null buffer");
+    // assert((target_positions.size() == 1) || (target_positions.size() == start_positions.size())) spcs.hpp:790-793
+    if (!(n_targets == 1 || n_targets == n)) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate: need 1 target or one per start");
+    if (noise_mode != FKS_NOISE_PHILOX && noise_mode != FKS_NOISE_INJECTED && noise_mode != FKS_NOISE_NONE)
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate: unknown noise mode");
+    if (noise_mode == FKS_NOISE_INJECTED && (!tape_draws || !tape_off))
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate: injected noise needs a tape");
+    return FKS_OK;
+}
+
+int fks_forward_simulate(fks_sim* s, const double* starts, const double* targets, size_t n, size_t n_targets,
+                         int allow_contacts, int noise_mode, const fks_noise_tape* tape, uint64_t first_particle_id,
+                         void* results) {
+    int rc = check_batch(s, starts, targets, n, n_targets, noise_mode, tape ? tape->draws : nullptr, tape ? tape->offsets : nullptr, results);
+    if (rc != FKS_OK || n == 0) return rc;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_forward_simulate: cudaSetDevice failed");
+    const size_t stride = (size_t)s->robot->stride;
+    const size_t rec = fks_sim_result_stride(s);
+    size_t n_draws = 0;
+    if (noise_mode == FKS_NOISE_INJECTED) n_draws = (size_t)tape->offsets[n];
+    if ((rc = ensure(&s->d_starts, &s->cap_starts, n * stride)) != FKS_OK) return rc;
+    if ((rc = ensure(&s->d_targets, &s->cap_targets, n_targets * stride)) != FKS_OK) return rc;
+    if ((rc = ensure(&s->d_results, &s->cap_results, n * rec)) != FKS_OK) return rc;
+    if (noise_mode == FKS_NOISE_INJECTED) {
+        if ((rc = ensure(&s->d_tape, &s->cap_tape, std::max<size_t>(n_draws, 1))) != FKS_OK) return rc;
+        if ((rc = ensure(&s->d_tape_off, &s->cap_tape_off, n + 1)) != FKS_OK) return rc;
+    }
+    FKS_CUDA(cudaMemcpyAsync(s->d_starts, starts, n * stride * 8, cudaMemcpyHostToDevice, s->stream));
+    FKS_CUDA(cudaMemcpyAsync(s->d_targets, targets, n_targets * stride * 8, cudaMemcpyHostToDevice, s->stream));
+    if (noise_mode == FKS_NOISE_INJECTED) {
+        if (n_draws) FKS_CUDA(cudaMemcpyAsync(s->d_tape, tape->draws, n_draws * 8, cudaMemcpyHostToDevice, s->stream));
+        FKS_CUDA(cudaMemcpyAsync(s->d_tape_off, tape->offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    }
+    rc = simulate_on_stream(s, s->d_starts, s->d_targets, n, n_targets, allow_contacts, noise_mode, s->d_tape,
+                            (const uint64_t*)s->d_tape_off, first_particle_id, s->d_results, s->stream);
+    if (rc != FKS_OK) return rc;
+    FKS_CUDA(cudaMemcpyAsync(results, s->d_results, n * rec, cudaMemcpyDeviceToHost, s->stream));
+    FKS_CUDA(cudaStreamSynchronize(s->stream));
+    return FKS_OK;
+}
+
+int fks_reverse_simulate(fks_sim* s, const double* starts, const double* targets, size_t n, size_t n_targets,
+                         int allow_contacts, int noise_mode, const fks_noise_tape* tape, uint64_t first_particle_id,
+                         void* results) {
+    // ReverseSimulateMutableRobot forwards to ForwardSimulateMutableRobot (spcs.hpp:838-841)
+    return fks_forward_simulate(s, starts, targets, n, n_targets, allow_contacts, noise_mode, tape, first_particle_id, results);
+}
+
+int fks_forward_simulate_device(fks_sim* s, const double* d_starts, const double* d_targets, size_t n, size_t n_targets,
+                                int allow_contacts, int noise_mode, const double* d_tape_draws,
+                                const uint64_t* d_tape_offsets, uint64_t first_particle_id, void* d_results,
+                                void* cuda_stream) {
+    int rc = check_batch(s, d_starts, d_targets, n, n_targets, noise_mode, d_tape_draws, d_tape_offsets, d_results);
+    if (rc != FKS_OK || n == 0) return rc;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_forward_simulate_device: cudaSetDevice failed");
+    return simulate_on_stream(s, d_starts, d_targets, n, n_targets, allow_contacts, noise_mode, d_tape_draws, d_tape_offsets,
+                              first_particle_id, d_results, (cudaStream_t)cuda_stream);
+}
+
+int fks_get_statistics(fks_sim* s, uint64_t* out) {
+    if (!s || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_get_statistics: null argument");
+    DeviceGuard guard(s->device);
+    FKS_CUDA(cudaDeviceSynchronize());
+    FKS_CUDA(cudaMemcpy(out, s->d_stats, FKS_NUM_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return FKS_OK;
+}
+
+int fks_reset_statistics(fks_sim* s) {
+    if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_reset_statistics: null argument");
+    DeviceGuard guard(s->device);
+    FKS_CUDA(cudaDeviceSynchronize());
+    FKS_CUDA(cudaMemset(s->d_stats, 0, FKS_NUM_STATS * sizeof(uint64_t)));
+    return FKS_OK;
+}
+
+uint64_t fks_sim_launch_count(const fks_sim* s) { return s ? s->launches : 0; }
+
+const char* fks_sim_kernel_info(fks_sim* s) { return s ? s->info.c_str() : ""; }
+
+// ---------------------------------------------------------------------------------------------
+// roofline micro-benchmarks
+// ---------------------------------------------------------------------------------------------
+int fks_measure_fp64_peak(int device, double* flops_per_s) {
+    if (!flops_per_s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_measure_fp64_peak: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FKS_ERR_NO_DEVICE, "no CUDA device");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    FKS_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* d_out = nullptr;
+    FKS_CUDA(cudaMalloc((void**)&d_out, 8));
+    const int grid = prop.multiProcessorCount * 8, iters = 1 << 16;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, 0);
+        int rc = launch_fp64_peak(d_out, grid, iters, nullptr);
+        cudaEventRecord(e1, 0);
+        cudaError_t err = cudaEventSynchronize(e1);
+        if (rc != 0 || err != cudaSuccess) {
+            cudaFree(d_out);
+            return cuda_fail(rc ? (cudaError_t)rc : err, "fp64 peak kernel");
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *flops_per_s = best;
+    return FKS_OK;
+}
+
+int fks_measure_gather_rate(int device, size_t bytes, double* gathers_per_s) {
+    if (!gathers_per_s || bytes < 4096) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_measure_gather_rate: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FKS_ERR_NO_DEVICE, "no CUDA device");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    FKS_CUDA(cudaGetDeviceProperties(&prop, device));
+    size_t n = 1;
+    while (n * 2 * 4 <= bytes) n <<= 1;  // power-of-two element count
+    float *d_data = nullptr, *d_out = nullptr;
+    FKS_CUDA(cudaMalloc((void**)&d_data, n * 4));
+    FKS_CUDA(cudaMalloc((void**)&d_out, 4));
+    FKS_CUDA(cudaMemset(d_data, 0, n * 4));
+    const int grid = prop.multiProcessorCount * 8, iters = 2048;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, 0);
+        int rc = launch_gather(d_data, (unsigned long long)(n - 1), d_out, grid, iters, nullptr);
+        cudaEventRecord(e1, 0);
+        cudaError_t err = cudaEventSynchronize(e1);
+        if (rc != 0 || err != cudaSuccess) {
+            cudaFree(d_data);
+            cudaFree(d_out);
+            return cuda_fail(rc ? (cudaError_t)rc : err, "gather kernel");
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double gathers = 4.0 * (double)iters * 256.0 * (double)grid;
+        if (rep > 0) best = std::max(best, gathers / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_data);
+    cudaFree(d_out);
+    *gathers_per_s = best;
+    return FKS_OK;
+}
+
+}  // extern "C"

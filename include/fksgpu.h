@@ -1,0 +1,291 @@
+/*
+ * fksgpu.h -- C ABI of the B200-native batched particle contact simulator.
+ *
+ * This is the drop-in boundary for ONE path of calderpg/fast_kinematic_simulator:
+ * the batched forward simulation of uncertain "particles"
+ *   SimpleParticleContactSimulator::ForwardSimulateRobots
+ *     (include/fast_kinematic_simulator/simple_particle_contact_simulator.hpp:788-804,
+ *      alias ReverseSimulateRobots :806-822)
+ * and everything it calls per particle (:824-919 step loop, :1546-1816 microstep +
+ * resolver loop, :921-981 env check, :983-1275 self collision, :1818-1939 corrections,
+ * :1990-1998 stacked-Jacobian solve; robots tnuva_robot_models.hpp, actuator noise
+ * simple_uncertainty_models.hpp:48-90, PID simple_pid_controller.hpp:98-135).
+ *
+ * The reference has no FFI; its boundary is the C++ virtual interface
+ * simple_simulator_interface::SimulatorInterface (spcs.hpp:372) created by the factories in
+ * fast_kinematic_simulator.hpp:18-22.  A C++ adapter (csrc/host/gpu_particle_contact_simulator.hpp)
+ * implements that interface on top of the functions below; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain C, opaque handles, int status return (0 = FKS_OK), no exceptions cross the boundary;
+ *  - rigid transforms are 12 doubles, row-major 3x4 [R | t];
+ *  - configurations are flat doubles: SE2 (x,y,theta) = 3, SE3 = 12 (row-major 3x4 [R|t],
+ *    never quaternions), linked = one value per ACTIVE joint in joint order;
+ *  - all arithmetic on the device is FP64 except SDF storage (float) and cell indices (int64).
+ */
+#ifndef FKSGPU_H
+#define FKSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FKS_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------ */
+enum {
+    FKS_OK = 0,
+    FKS_ERR_INVALID_ARGUMENT = 1,
+    FKS_ERR_CUDA = 2,
+    FKS_ERR_NO_DEVICE = 3,
+    FKS_ERR_UNSUPPORTED = 4,
+    FKS_ERR_OUT_OF_MEMORY = 5
+};
+
+/* ---- robot kinds (tnuva_robot_models.hpp:26,201,415) -------------------------------------- */
+enum { FKS_ROBOT_SE2 = 0, FKS_ROBOT_SE3 = 1, FKS_ROBOT_LINKED = 2 };
+
+/* ---- joint types (arc_utilities SimpleJointModel; call sites tnuva.hpp:544-559) ----------- */
+enum { FKS_JOINT_PRISMATIC = 0, FKS_JOINT_REVOLUTE = 1, FKS_JOINT_CONTINUOUS = 2, FKS_JOINT_FIXED = 3 };
+
+/* ---- noise source ------------------------------------------------------------------------- */
+enum {
+    FKS_NOISE_PHILOX = 0,   /* counter-based Philox4x32-10 keyed by (seed, particle, step, microstep, dof) */
+    FKS_NOISE_INJECTED = 1, /* consume a caller-provided tape of truncated-normal draws (parity mode)      */
+    FKS_NOISE_NONE = 2      /* all draws are 0.0 (deterministic debugging)                                  */
+};
+
+/* ---- per-particle result flags (bit field in fks_result_tail.flags) ----------------------- */
+enum {
+    FKS_FLAG_DID_CONTACT        = 1u << 0, /* SimulationResult::did_contact (spcs.hpp:879,918)          */
+    FKS_FLAG_RESOLVE_FAILED     = 1u << 1, /* some ResolveForwardSimulation returned failed (:1745)      */
+    FKS_FLAG_ENDED_BY_FAILURE   = 1u << 2, /* failed_resolves_end_motion break (:884-887)                */
+    FKS_FLAG_ENDED_BY_NOCONTACT = 1u << 3, /* allow_contacts==false stop (:904-909)                      */
+    FKS_FLAG_ENDED_BY_SHORTCUT  = 1u << 4, /* simulation_shortcut_distance break (:898-902)              */
+    /* conditions on which the reference would abort() (asserts are live, CMakeLists.txt:66);
+       the device path records them and keeps going with the documented behaviour instead. */
+    FKS_FLAG_WOULD_ASSERT_MICROSTEP = 1u << 8,  /* microstep motion > resolution (:1570-1575)           */
+    FKS_FLAG_WOULD_ASSERT_NORMAL    = 1u << 9,  /* zero motion / OOB in normal lookup (:91-92,:1882)     */
+    FKS_FLAG_WOULD_ASSERT_NAN       = 1u << 10, /* NaN/Inf control input (unc.hpp:72-73)                 */
+    FKS_FLAG_EMPTY_JACOBIAN         = 1u << 11, /* resolver entered with no correcting point             */
+    FKS_FLAG_TAPE_EXHAUSTED         = 1u << 12, /* injected tape shorter than the draws consumed         */
+    FKS_FLAG_NEAR_RANK_CUT          = 1u << 13, /* a QR pivot came within 1e3x of Eigen's rank threshold
+                                                   (result is round-off determined in the reference)    */
+    FKS_FLAG_J_SPILLED              = 1u << 14  /* stacked Jacobian exceeded the shared-memory tile     */
+};
+
+/* spcs.hpp:345-369 (same field order, defaults :357-368) */
+typedef struct fks_solver_params {
+    double forward_simulation_time;
+    double simulation_shortcut_distance;
+    double environment_collision_check_tolerance;
+    double resolve_correction_step_scaling_decay_rate;
+    double resolve_correction_initial_step_size;
+    double resolve_correction_min_step_scaling;
+    uint32_t max_resolver_iterations;
+    uint32_t resolve_correction_step_scaling_decay_iterations;
+    int32_t failed_resolves_end_motion;
+    int32_t _pad;
+} fks_solver_params;
+
+/* Environment: what SimpleParticleContactSimulator copies at construction (spcs.hpp:420):
+ * collision-map METADATA (cells are never read on the hot path), the SDF floats and the
+ * SurfaceNormalGrid (spcs.hpp:44-343) flattened to a sparse CSR-like table. */
+typedef struct fks_env_desc {
+    double origin[12];          /* grid origin transform (VoxelGrid), world <- grid              */
+    double inverse_origin[12];  /* grid <- world (GetInverseOriginTransform, spcs.hpp:1176)       */
+    double map_resolution;      /* environment_.GetResolution() (spcs.hpp:524-527,1560,1219)      */
+    double sdf_resolution;      /* environment_sdf_.GetResolution() (spcs.hpp:923,957)            */
+    int64_t nx, ny, nz;         /* cells; linear index = (x*ny + y)*nz + z                        */
+    const float* sdf;           /* nx*ny*nz raw SDF cell values (GetImmutable4d, spcs.hpp:941)    */
+    float oob_value;            /* value returned out of bounds (+inf, envb.cpp:473)              */
+    int32_t _pad;
+    /* surface normals: only non-empty cells are listed, sorted by ascending linear index */
+    int64_t n_normal_cells;
+    const int64_t* normal_cell_index;  /* [n_normal_cells]                                       */
+    const uint32_t* normal_cell_start; /* [n_normal_cells+1] offsets into normal_entries         */
+    const double* normal_entries;      /* 7 doubles each: entry_direction xyzw, normal xyz
+                                          (StoredSurfaceNormal, spcs.hpp:48-83; already SafeNormal'd) */
+} fks_env_desc;
+
+/* One actuated axis: SimplePIDController (pid.hpp:53-136) + TruncatedNormalUncertainVelocityActuator
+ * (unc.hpp:48-121).  SE2: 3 axes (x,y,zr); SE3: 6 (x,y,z,xr,yr,zr); linked: one per active joint. */
+typedef struct fks_axis_params {
+    double kp, ki, kd, integral_clamp;
+    double velocity_limit;
+    double proportional_noise;  /* max_actuator_proportional_noise */
+    double minimum_noise;       /* max_actuator_minimum_noise      */
+    double noise_sigma;         /* percent_variance, 0.5 in every tnuva ctor (tnuva.hpp:128,318,469) */
+} fks_axis_params;
+
+/* arc_utilities RobotJoint (call sites tnuva.hpp:487-500,544-559) */
+typedef struct fks_joint_desc {
+    int32_t parent_link;
+    int32_t child_link;
+    int32_t type;          /* FKS_JOINT_* */
+    int32_t _pad;
+    double transform[12];  /* parent link -> joint frame */
+    double axis[3];
+    double lower_limit, upper_limit;
+    double distance_weight;
+} fks_joint_desc;
+
+typedef struct fks_robot_desc {
+    int32_t kind;        /* FKS_ROBOT_* */
+    int32_t n_links;     /* 1 for SE2/SE3 */
+    int32_t n_joints;    /* 0 for SE2/SE3 */
+    int32_t n_dof;       /* 3 / 6 / active joints */
+    int64_t n_points;    /* total collision points, stored link-major, point-minor (spcs.hpp:925-936) */
+    const double* points_xyz;    /* [n_points*3] link-relative */
+    const int32_t* point_link;   /* [n_points] non-decreasing */
+    const fks_axis_params* axes; /* [n_dof] */
+    /* linked only */
+    double base_transform[12];
+    const fks_joint_desc* joints;           /* [n_joints], kinematic order */
+    const uint8_t* allowed_self_collision;  /* [n_links*n_links], 1 = allowed (CheckIfSelfCollisionAllowed) */
+    /* configuration distance weights (ComputeConfigurationDistanceTo, spcs.hpp:898) */
+    double position_distance_weight;
+    double rotation_distance_weight;
+} fks_robot_desc;
+
+/* Injected noise: the truncated-normal outputs of noise_distribution_(rng) (unc.hpp:86) in the
+ * order the reference draws them, [particle][step][microstep][dof]. */
+typedef struct fks_noise_tape {
+    const double* draws;       /* flat */
+    const uint64_t* offsets;   /* [n_particles+1] start of each particle's draws */
+} fks_noise_tape;
+
+/* Tail of every result record; record = cfg_stride doubles followed by this struct. */
+typedef struct fks_result_tail {
+    uint32_t flags;            /* FKS_FLAG_* */
+    uint32_t n_microsteps;     /* executed iterations of the loop at spcs.hpp:1590 */
+    uint32_t n_resolver_iters; /* executed iterations of the loop at spcs.hpp:1625 */
+    uint32_t n_steps;          /* controller steps executed (spcs.hpp:863)         */
+} fks_result_tail;
+
+/* keys of GetStatistics (spcs.hpp:488-500), in this order, then two extra totals */
+enum {
+    FKS_STAT_SUCCESSFUL_RESOLVES = 0,
+    FKS_STAT_UNSUCCESSFUL_RESOLVES = 1,
+    FKS_STAT_FREE_RESOLVES = 2,
+    FKS_STAT_COLLISION_RESOLVES = 3,
+    FKS_STAT_FALLBACK_RESOLVES = 4,
+    FKS_STAT_UNSUCCESSFUL_SELF_COLLISION_RESOLVES = 5,
+    FKS_STAT_UNSUCCESSFUL_ENV_COLLISION_RESOLVES = 6,
+    FKS_STAT_RECOVERED_UNSUCCESSFUL_RESOLVES = 7,
+    FKS_STAT_TOTAL_MICROSTEPS = 8,
+    FKS_STAT_TOTAL_RESOLVER_ITERATIONS = 9,
+    FKS_NUM_STATS = 10
+};
+
+typedef struct fks_env fks_env;
+typedef struct fks_robot fks_robot;
+typedef struct fks_sim fks_sim;
+
+/* -------------------------------------------------------------------------------------------
+ * Library
+ * ----------------------------------------------------------------------------------------- */
+int fks_abi_version(void);
+/* message of the last failing call on this thread */
+const char* fks_last_error_string(void);
+int fks_device_count(int* count);
+
+/* defaults of SimulatorSolverParameters() (spcs.hpp:357-368); replaces GetDefaultSolverParameters (fks.hpp:13-16) */
+void fks_default_solver_params(fks_solver_params* out);
+
+/* -------------------------------------------------------------------------------------------
+ * Environment (replaces the by-value copies of grid / SDF / SurfaceNormalGrid, spcs.hpp:420)
+ * Uploads to `device`, builds the device normal table, requests an L2 persistence window.
+ * ----------------------------------------------------------------------------------------- */
+int fks_env_create(int device, const fks_env_desc* desc, fks_env** out);
+void fks_env_destroy(fks_env* env);
+
+/* -------------------------------------------------------------------------------------------
+ * Robot (replaces the immutable_robot argument of ForwardSimulateRobots, spcs.hpp:788)
+ * ----------------------------------------------------------------------------------------- */
+int fks_robot_create(int device, const fks_robot_desc* desc, fks_robot** out);
+void fks_robot_destroy(fks_robot* robot);
+/* doubles per flattened configuration: 3 / 12 / n_dof */
+int fks_robot_config_stride(const fks_robot* robot);
+
+/* -------------------------------------------------------------------------------------------
+ * Simulator (replaces Make{SE2,SE3,Linked}Simulator, fks.hpp:18-22 / fks.cpp:4-71, and the
+ * SimpleParticleContactSimulator ctor, spcs.hpp:420-444)
+ * ----------------------------------------------------------------------------------------- */
+int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_params* params,
+                   double simulation_controller_frequency, uint64_t prng_seed, int32_t debug_level,
+                   fks_sim** out);
+void fks_sim_destroy(fks_sim* sim);
+/* bytes per result record = 8*cfg_stride + sizeof(fks_result_tail) */
+size_t fks_sim_result_stride(const fks_sim* sim);
+
+/* ForwardSimulateRobots (spcs.hpp:788-804) with HOST buffers.
+ *  starts:  n_particles * cfg_stride doubles; targets: n_targets (1 or n_particles) * cfg_stride
+ *  noise_mode FKS_NOISE_INJECTED requires `tape`; FKS_NOISE_PHILOX uses (prng_seed, first_particle_id + i)
+ *  results: n_particles records of fks_sim_result_stride() bytes
+ * Host->device copies of starts/targets(/tape), the kernel, and the device->host copy of results
+ * all happen inside the call; it returns after the results are on the host. */
+int fks_forward_simulate(fks_sim* sim, const double* starts, const double* targets,
+                         size_t n_particles, size_t n_targets, int allow_contacts,
+                         int noise_mode, const fks_noise_tape* tape, uint64_t first_particle_id,
+                         void* results);
+
+/* ReverseSimulateRobots (spcs.hpp:806-822, :838-841): identical computation */
+int fks_reverse_simulate(fks_sim* sim, const double* starts, const double* targets,
+                         size_t n_particles, size_t n_targets, int allow_contacts,
+                         int noise_mode, const fks_noise_tape* tape, uint64_t first_particle_id,
+                         void* results);
+
+/* Same with DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream).
+ * d_tape_draws / d_tape_offsets may be NULL unless noise_mode == FKS_NOISE_INJECTED. */
+int fks_forward_simulate_device(fks_sim* sim, const double* d_starts, const double* d_targets,
+                                size_t n_particles, size_t n_targets, int allow_contacts,
+                                int noise_mode, const double* d_tape_draws,
+                                const uint64_t* d_tape_offsets, uint64_t first_particle_id,
+                                void* d_results, void* cuda_stream);
+
+/* GetStatistics / ResetStatistics (spcs.hpp:488-512); out has FKS_NUM_STATS entries.
+ * Synchronises the simulator's stream. */
+int fks_get_statistics(fks_sim* sim, uint64_t* out);
+int fks_reset_statistics(fks_sim* sim);
+
+/* number of kernel launches issued by this simulator so far (bench "gpu_launches") */
+uint64_t fks_sim_launch_count(const fks_sim* sim);
+/* kernel attributes of the simulate kernel for this robot kind (regs, smem, occupancy) as a
+ * short human-readable string owned by the sim */
+const char* fks_sim_kernel_info(fks_sim* sim);
+
+/* -------------------------------------------------------------------------------------------
+ * Environment builder (host C++; replaces simulator_environment_builder::BuildCompleteEnvironment,
+ * simulator_environment_builder.cpp:470-476).  Obstacles are cuboids (OBSTACLE_CONFIG,
+ * simulator_environment_builder.hpp:25-49).  The result owns its arrays; `desc` points into it.
+ * ----------------------------------------------------------------------------------------- */
+typedef struct fks_obstacle {
+    double pose[12];
+    double extents[3]; /* half extents */
+    uint32_t object_id;
+    uint32_t _pad;
+} fks_obstacle;
+
+typedef struct fks_built_env fks_built_env;
+int fks_build_environment(const fks_obstacle* obstacles, size_t n_obstacles, double resolution,
+                          fks_built_env** out);
+const fks_env_desc* fks_built_env_desc(const fks_built_env* env);
+/* occupancy of the collision map (1 byte per cell, 1 = filled); not used on the hot path */
+const uint8_t* fks_built_env_occupancy(const fks_built_env* env);
+void fks_built_env_destroy(fks_built_env* env);
+
+/* -------------------------------------------------------------------------------------------
+ * Device micro-benchmarks used for the roofline denominators: dependent-free DFMA
+ * throughput (FLOP/s) and random 4-byte gather rate (gathers/s) over a `bytes`-sized array.
+ * ----------------------------------------------------------------------------------------- */
+int fks_measure_fp64_peak(int device, double* flops_per_s);
+int fks_measure_gather_rate(int device, size_t bytes, double* gathers_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FKSGPU_H */

@@ -1,0 +1,168 @@
+"""TEST INFRASTRUCTURE -- ctypes binding of oracle/libfks_oracle.so (the CPU restatement of the
+reference's forward-simulate path).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module; the product never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfks_oracle.so")
+PID_REF = os.path.join(_HERE, "_ref", "pid_ref")
+
+ORACLE_NOISE_MT19937 = 3
+SENS_NAMES = ("cell_boundary", "est_threshold", "est_zero", "rank_cut", "pivot_tie", "nmicro", "normal_tie",
+              "angle_wrap", "self_collision", "raw_threshold", "step_fraction")
+SENS_SELF_COLLISION = 1 << 8
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    lib.oracle_create.restype = C.c_void_p
+    lib.oracle_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint64, C.c_int]
+    lib.oracle_destroy.argtypes = [C.c_void_p]
+    lib.oracle_destroy.restype = None
+    lib.oracle_num_threads.argtypes = [C.c_void_p]
+    lib.oracle_config_stride.argtypes = [C.c_void_p]
+    lib.oracle_forward_simulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    lib.oracle_tape_total.argtypes = [C.c_void_p]
+    lib.oracle_tape_total.restype = C.c_uint64
+    lib.oracle_copy_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_copy_tape.restype = None
+    lib.oracle_copy_sensitivity.argtypes = [C.c_void_p, C.c_void_p]
+    lib.oracle_copy_sensitivity.restype = None
+    lib.oracle_get_statistics.argtypes = [C.c_void_p, C.c_void_p]
+    lib.oracle_get_statistics.restype = None
+    lib.oracle_reset_statistics.argtypes = [C.c_void_p]
+    lib.oracle_reset_statistics.restype = None
+    lib.oracle_colpiv_qr_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oracle_colpiv_qr_solve.restype = None
+    lib.oracle_pid_run.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.oracle_pid_run.restype = None
+    lib.oracle_exp_twist.argtypes = [C.c_void_p, C.c_void_p]
+    lib.oracle_exp_twist.restype = None
+    lib.oracle_twist_between.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_twist_between.restype = None
+    lib.oracle_wrap_angle.argtypes = [C.c_double]
+    lib.oracle_wrap_angle.restype = C.c_double
+    lib.oracle_truncated_normal.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_void_p]
+    lib.oracle_truncated_normal.restype = None
+    lib.oracle_philox_truncated_normal.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
+    lib.oracle_philox_truncated_normal.restype = C.c_double
+    lib.oracle_env_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_robot_kinematics.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load()
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class OracleSimulator:
+    """CPU oracle of SimpleParticleContactSimulator::ForwardSimulateRobots.  `env_desc` / `robot_desc` are
+    the same ctypes structures (include/fksgpu.h) the product consumes."""
+
+    def __init__(self, env_desc, robot_desc, solver_params, frequency=25.0, seed=42, num_threads=0):
+        self._keep = (env_desc, robot_desc, solver_params)
+        self._h = lib().oracle_create(C.addressof(env_desc), C.addressof(robot_desc), C.addressof(solver_params),
+                                      float(frequency), int(seed), int(num_threads))
+        if not self._h:
+            raise ValueError("oracle_create rejected the robot description")
+        self.stride = lib().oracle_config_stride(self._h)
+        self.num_threads = lib().oracle_num_threads(self._h)
+        self.dtype = np.dtype([("cfg", np.float64, (self.stride,)), ("flags", np.uint32), ("n_microsteps", np.uint32),
+                               ("n_resolver_iters", np.uint32), ("n_steps", np.uint32)])
+
+    def forward_simulate(self, starts, targets, allow_contacts=True, noise_mode=ORACLE_NOISE_MT19937, tape=None,
+                         first_particle_id=0, record_tape=False):
+        starts = _f64(starts).reshape(-1, self.stride)
+        targets = _f64(targets).reshape(-1, self.stride)
+        n = starts.shape[0]
+        out = np.empty(n, dtype=self.dtype)
+        ctape = None
+        keep = None
+        if tape is not None:
+            draws = _f64(tape[0])
+            offs = np.ascontiguousarray(tape[1], dtype=np.uint64)
+            if draws.size == 0:
+                draws = np.zeros(1)
+
+            class T(C.Structure):
+                _fields_ = [("draws", C.c_void_p), ("offsets", C.c_void_p)]
+
+            ctape = T(draws.ctypes.data, offs.ctypes.data)
+            keep = (draws, offs)
+        rc = lib().oracle_forward_simulate(self._h, starts.ctypes.data, targets.ctypes.data, n, targets.shape[0],
+                                           int(bool(allow_contacts)), int(noise_mode),
+                                           C.addressof(ctape) if ctape is not None else None, int(first_particle_id),
+                                           int(bool(record_tape)), out.ctypes.data)
+        del keep
+        if rc != 0:
+            raise ValueError("oracle_forward_simulate failed with code %d" % rc)
+        return out
+
+    def statistics(self):
+        out = np.zeros(10, dtype=np.uint64)
+        lib().oracle_get_statistics(self._h, out.ctypes.data)
+        return out
+
+    def reset_statistics(self):
+        lib().oracle_reset_statistics(self._h)
+
+    def close(self):
+        if self._h:
+            lib().oracle_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_with_tape(oracle, starts, targets, allow_contacts=True, noise_mode=ORACLE_NOISE_MT19937, first_particle_id=0):
+    """Run the oracle recording its truncated-normal draws; returns (records, (draws, offsets), sensitivity)."""
+    starts = _f64(starts).reshape(-1, oracle.stride)
+    n = starts.shape[0]
+    rec = oracle.forward_simulate(starts, targets, allow_contacts, noise_mode, None, first_particle_id, record_tape=True)
+    total = int(lib().oracle_tape_total(oracle._h))
+    draws = np.zeros(max(total, 1))
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    lib().oracle_copy_tape(oracle._h, draws.ctypes.data, offs.ctypes.data)
+    sens = np.zeros(n, dtype=np.uint32)
+    lib().oracle_copy_sensitivity(oracle._h, sens.ctypes.data)
+    return rec, (draws[:total], offs), sens
+
+
+def sensitivity_of_last_call(oracle, n):
+    sens = np.zeros(n, dtype=np.uint32)
+    lib().oracle_copy_sensitivity(oracle._h, sens.ctypes.data)
+    return sens
+
+
+def pid_reference(kp, ki, kd, iclamp, errors, timesteps):
+    """Run the REFERENCE's own simple_pid_controller.hpp (oracle/_ref/pid_ref)."""
+    lines = ["%r %r %r %r %d" % (float(kp), float(ki), float(kd), float(iclamp), len(errors))]
+    lines += ["%r %r" % (float(e), float(t)) for e, t in zip(errors, timesteps)]
+    out = subprocess.run([PID_REF], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout
+    return np.array([float(x) for x in out.split()])
