@@ -39,7 +39,7 @@ FLAG_EMPTY_JACOBIAN = 1 << 11
 FLAG_TAPE_EXHAUSTED = 1 << 12
 FLAG_NEAR_RANK_CUT = 1 << 13
 FLAG_J_SPILLED = 1 << 14
-NUM_STATS = 10
+NUM_STATS = 11
 STAT_NAMES = (
     "successful_resolves",
     "unsuccessful_resolves",
@@ -51,6 +51,7 @@ STAT_NAMES = (
     "recovered_unsuccessful_resolves",
     "total_microsteps",
     "total_resolver_iterations",
+    "total_corrected_points",
 )
 
 

@@ -1240,6 +1240,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) simulate_kernel(const __grid
                     double scaling = sp.initial_step;
                     while (in_collision) {
                         const int rows = collect_corrections<KIND>(c, e, Tprev, Tcur, has_self);  // spcs:1627
+                        st.v[FKS_STAT_TOTAL_CORRECTED_POINTS] += (unsigned long long)(rows / 3);
                         if (rows == 0) {
                             // Eigen would return an empty vector and ApplyControlInput would assert; documented
                             // device behaviour: zero correction step

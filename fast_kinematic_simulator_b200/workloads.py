@@ -256,12 +256,28 @@ def arm_selfcollision(n_particles=256, seed=1003):
                     target.reshape(1, 7), "7-DoF arm folding onto itself (self-collision resolver path)")
 
 
+def arm_elbow(n_particles=256, seed=1003):
+    """The arm straightens up under an overhead beam: links 3/4 (around the elbow) make the contact, so the
+    stacked Jacobian has structurally-zero columns for the distal joints and full column rank on the rest --
+    unlike `arm_table`, where a single distal link touching gives a rank-6 system in 7 unknowns and the
+    reference's QR pivot is decided by round-off."""
+    res = 0.04
+    rng = np.random.Generator(np.random.MT19937(seed))
+    obstacles = arm_room_obstacles() + [(make_transform((0.35, 0.0, 1.78)), (0.12, 0.3, 0.06), 8)]  # beam, bottom at z = 1.72
+    start = np.array([0.0, 0.9, 0.0, 2.0, 0.0, -1.5, 0.0])  # forearm folded down, hand forward above the table
+    starts = start[None, :] + rng.normal(0.0, 0.02, (n_particles, 7))
+    target = np.array([0.1, 0.3, 0.0, 2.0, 0.0, -1.5, 0.0])
+    return Workload("arm_elbow", capi.ROBOT_LINKED, obstacles, res, arm_robot(), starts, target.reshape(1, 7),
+                    "7-DoF arm whose elbow (links 3/4) rises into an overhead beam")
+
+
 WORKLOADS = {
     "se2_arena": se2_arena,
     "se3_narrow_passage": se3_narrow_passage,
     "arm_table": arm_table,
     "se3_highres": se3_highres,
     "arm_selfcollision": arm_selfcollision,
+    "arm_elbow": arm_elbow,
 }
 
 

@@ -166,7 +166,7 @@ typedef struct fks_result_tail {
     uint32_t n_steps;          /* controller steps executed (spcs.hpp:863)         */
 } fks_result_tail;
 
-/* keys of GetStatistics (spcs.hpp:488-500), in this order, then two extra totals */
+/* keys of GetStatistics (spcs.hpp:488-500), in this order, then three extra totals */
 enum {
     FKS_STAT_SUCCESSFUL_RESOLVES = 0,
     FKS_STAT_UNSUCCESSFUL_RESOLVES = 1,
@@ -178,7 +178,8 @@ enum {
     FKS_STAT_RECOVERED_UNSUCCESSFUL_RESOLVES = 7,
     FKS_STAT_TOTAL_MICROSTEPS = 8,
     FKS_STAT_TOTAL_RESOLVER_ITERATIONS = 9,
-    FKS_NUM_STATS = 10
+    FKS_STAT_TOTAL_CORRECTED_POINTS = 10, /* sum over resolver iterations of the points that got a correction (rows / 3) */
+    FKS_NUM_STATS = 11
 };
 
 typedef struct fks_env fks_env;

@@ -28,6 +28,8 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -707,6 +709,15 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
             }
 #pragma omp atomic
             g_rank_hist[bucket]++;
+            static const bool dbg = std::getenv("FKS_ORACLE_DEBUG_RANK") != nullptr;
+            if (dbg && bucket < 35) {
+#pragma omp critical
+                {
+                    std::fprintf(stderr, "near-rank pivot: rows %d cols %d k %d big %.3e max_norm %.3e norms_direct:", rows, cols, k, big, max_norm);
+                    for (int j = 0; j < cols; j++) std::fprintf(stderr, " %.3e", norms_direct[j]);
+                    std::fprintf(stderr, "\n");
+                }
+            }
         }
         transp[k] = biggest;
         if (k != biggest) {
@@ -1154,6 +1165,7 @@ struct Sim {
                 while (in_collision) {
                     collect_corrections(previous, robot, self, &Jrows, &corr, flags, sens);
                     const int rows = (int)corr.size();
+                    st[FKS_STAT_TOTAL_CORRECTED_POINTS] += (uint64_t)(rows / 3);
                     double raw[kMaxDof];
                     for (int i = 0; i < D; i++) raw[i] = 0.0;
                     if (rows == 0) {
@@ -1166,6 +1178,14 @@ struct Sim {
                         for (int r = 0; r < rows; r++)
                             for (int c = 0; c < D; c++) Acm[(size_t)c * rows + r] = Jrows[(size_t)r * D + c];
                         colpiv_qr_solve(Acm.data(), bvec.data(), rows, D, raw, sens);  // spcs:1629,1990-1998
+                    }
+                    static const bool trace = std::getenv("FKS_ORACLE_TRACE") != nullptr;
+                    if (trace) {
+                        std::fprintf(stderr, "step %u micro %u iter %u rows %d scaling %.4f corr:", step, micro, resolver_iterations, rows, scaling);
+                        for (int i = 0; i < rows && i < 9; i++) std::fprintf(stderr, " %.3e", corr[(size_t)i]);
+                        std::fprintf(stderr, " | raw:");
+                        for (int i = 0; i < D; i++) std::fprintf(stderr, " %.3e", raw[i]);
+                        std::fprintf(stderr, "\n");
                     }
                     const double est = max_motion_of_input(robot, raw, &nan_seen);  // spcs:1630
                     const double frac_raw = est / allowed_microstep_distance;
@@ -1418,6 +1438,9 @@ void oracle_truncated_normal(uint64_t seed, double sigma, int n, double* out) {
     TruncNormal tn;
     tn.init(sigma);
     for (int i = 0; i < n; i++) out[i] = tn(rng);
+}
+void oracle_philox_raw(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+    fks_philox4x32_10(ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1], out4);
 }
 double oracle_philox_truncated_normal(uint64_t seed, uint64_t particle, uint32_t step, uint32_t micro, uint32_t dof, double sigma) {
     return fks_philox_truncated_normal(seed, particle, step, micro, dof, sigma);

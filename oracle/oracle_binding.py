@@ -58,6 +58,8 @@ def load():
     lib.oracle_truncated_normal.restype = None
     lib.oracle_philox_truncated_normal.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
     lib.oracle_philox_truncated_normal.restype = C.c_double
+    lib.oracle_philox_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_philox_raw.restype = None
     lib.oracle_env_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oracle_robot_kinematics.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
@@ -121,7 +123,7 @@ class OracleSimulator:
         return out
 
     def statistics(self):
-        out = np.zeros(10, dtype=np.uint64)
+        out = np.zeros(11, dtype=np.uint64)
         lib().oracle_get_statistics(self._h, out.ctypes.data)
         return out
 
