@@ -118,6 +118,7 @@ struct WarpLayout {
     int chain;               // 12
     int cfg, pcfg, tcfg;     // cfg_stride each (SE3: alias of the T arrays)
     int target;              // cfg_stride
+    int scfg;                // cfg_stride: configuration at the start of the controller step (allow_contacts == false)
     int act, ru, du, tn, raw, stepv;  // D each
     int qr;                  // 3*D doubles + D ints (norms updated/direct, hcoeff, transpositions)
     int total;
@@ -141,6 +142,7 @@ inline __host__ __device__ WarpLayout make_warp_layout(int kind, int L, int J, i
         w.tcfg = o; o += stride;
     }
     w.target = o; o += stride;
+    w.scfg = o; o += stride;
     w.act = o; o += D;
     w.ru = o; o += D;
     w.du = o; o += D;

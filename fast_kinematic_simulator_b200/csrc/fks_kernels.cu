@@ -1123,6 +1123,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) simulate_kernel(const __grid
     double* Tprev = c.ws + c.wl.Tprev;
     double* Tcur = c.ws + c.wl.Tcur;
     double* target = c.ws + c.wl.target;
+    double* scfg = c.ws + c.wl.scfg;
     double* act = c.ws + c.wl.act;
     double* ru = c.ws + c.wl.ru;
     double* du = c.ws + c.wl.du;
@@ -1161,6 +1162,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock) simulate_kernel(const __grid
 
         for (unsigned step = 0; step < sp.n_steps; step++) {
             n_steps++;
+            if (!a.allow_contacts) {  // a colliding step is discarded as a whole: keep the step's start (spcs:904-909)
+                if (lane < c.stride) scfg[lane] = cfg[lane];
+                __syncwarp();
+            }
             // ---- GenerateControlAction (tnuva:179-198, :384-412, :598-614) ---------------------------
             if (KIND == FKS_ROBOT_SE3) {
                 if (lane == 0) {
@@ -1347,6 +1352,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock) simulate_kernel(const __grid
                     }
                 }
             } else {
+                // robot->SetPosition(resolved_configuration) is skipped: the particle stays where the step began
+                if (lane < c.stride) cfg[lane] = scfg[lane];
+                __syncwarp();
+                forward_kinematics<KIND>(c, cfg, Tcur);
                 flags |= FKS_FLAG_ENDED_BY_NOCONTACT;
                 break;
             }

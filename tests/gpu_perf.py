@@ -1,0 +1,51 @@
+"""Developer aid (not a test): device-timed throughput of several workloads / sizes."""
+import sys
+import time
+
+sys.path.insert(0, ".")
+import numpy as np
+import torch
+
+from fast_kinematic_simulator_b200 import capi, workloads as W
+
+
+def run(name, n, free=False, reps=3):
+    w = W.make(name, n_particles=n)
+    if free and name.startswith("arm"):
+        w.targets = (W.ARM_START + np.array([0.3, -0.3, 0.2, -0.3, 0.1, -0.2, 0.4])).reshape(1, 7)
+    sim = w.make_simulator()
+    dev = torch.device("cuda")
+    ds = torch.from_numpy(w.starts).to(dev)
+    dt = torch.from_numpy(w.targets).to(dev)
+    dr = torch.empty(n * sim.result_stride, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    best = 1e9
+    for i in range(reps):
+        sim.reset_statistics()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        sim.forward_simulate_device(ds, dt, n, w.targets.shape[0], dr, True, capi.NOISE_PHILOX, stream=st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    s = sim.get_statistics()
+    rec = dr.cpu().numpy().view(sim.dtype)
+    print("%-20s n=%7d free=%d  %8.2f ms  micro %9d iters %8d pts %9d  -> %.3e microsteps/s  (failed %d, contact %d)" % (
+        name, n, free, best, s["total_microsteps"], s["total_resolver_iterations"], s["total_corrected_points"],
+        s["total_microsteps"] / best * 1e3, int(((rec["flags"] & 2) != 0).sum()), int((rec["flags"] & 1).sum())), flush=True)
+    sim.close()
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        run(sys.argv[1], int(sys.argv[2]), len(sys.argv) > 3 and sys.argv[3] == "free")
+    else:
+        run("arm_table", 65536, True)
+        run("arm_table", 2368, False)
+        run("arm_table", 16384, False)
+        run("arm_table", 65536, False)
+        run("arm_elbow", 65536, False)
+        run("se3_narrow_passage", 16384)
+        run("se3_narrow_passage", 65536)
+        run("se2_arena", 128)
+        run("se2_arena", 65536)
