@@ -7,7 +7,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path():
-    return os.path.join(_HERE, "libfksgpu.so")
+    # FKSGPU_LIBRARY: developer override used to A/B kernel builds (always an in-tree libfksgpu*.so)
+    return os.environ.get("FKSGPU_LIBRARY", os.path.join(_HERE, "libfksgpu.so"))
 
 
 class FksError(RuntimeError):

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -87,8 +88,8 @@ struct fks_robot {
     int device;
     DevRobot host;
     DevRobot* d_robot;
-    double *d_px, *d_py, *d_pz;
-    int* d_plink;
+    double2* d_pxy;
+    PointZL* d_pzl;
     int stride;
 };
 
@@ -103,7 +104,7 @@ struct fks_sim {
     int grid_max;
     size_t dyn_smem;
     KernelInfo kinfo;
-    ScratchLayout sl;
+    LaunchArgs plan;  // layouts and shared-memory offsets (simulate_smem_plan)
     char* d_scratch;
     unsigned long long* d_stats;
     unsigned int* d_counter;
@@ -155,7 +156,7 @@ int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
     if (!desc || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: null argument");
     *out = nullptr;
     if (!desc->sdf || desc->nx <= 0 || desc->ny <= 0 || desc->nz <= 0 || desc->nx > 65535 || desc->ny > 65535 ||
-        desc->nz > 65535 || !(desc->sdf_resolution > 0.0) || !(desc->map_resolution > 0.0))
+        desc->nz > 65535 || (double)desc->nx * (double)desc->ny * (double)desc->nz >= 2147483648.0 || !(desc->sdf_resolution > 0.0) || !(desc->map_resolution > 0.0))
         return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: bad grid description");
     if (desc->n_normal_cells < 0 || (desc->n_normal_cells > 0 && (!desc->normal_cell_index || !desc->normal_cell_start || !desc->normal_entries)))
         return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: bad surface-normal table");
@@ -379,6 +380,7 @@ int fks_robot_create(int device, const fks_robot_desc* r, fks_robot** out) {
         acc += m;
     }
     for (int l = 0; l < L; l++) {
+        // bounding capsule: segment along the longest bounding-box axis through the box centre
         double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
         for (int p = h.link_begin[l]; p < h.link_begin[l + 1]; p++) {
             const double v[3] = {px[(size_t)p], py[(size_t)p], pz[(size_t)p]};
@@ -387,23 +389,41 @@ int fks_robot_create(int device, const fks_robot_desc* r, fks_robot** out) {
                 if (p == h.link_begin[l] || v[k] > hi[k]) hi[k] = v[k];
             }
         }
-        double rad = 0.0;
-        for (int k = 0; k < 3; k++) h.link_center[l][k] = 0.5 * (lo[k] + hi[k]);
-        for (int p = h.link_begin[l]; p < h.link_begin[l + 1]; p++) {
-            const double dx = px[(size_t)p] - h.link_center[l][0], dy = py[(size_t)p] - h.link_center[l][1], dz = pz[(size_t)p] - h.link_center[l][2];
-            rad = std::max(rad, std::sqrt(dx * dx + dy * dy + dz * dz));
+        int ax = 0;
+        for (int k = 1; k < 3; k++)
+            if (hi[k] - lo[k] > hi[ax] - lo[ax]) ax = k;
+        for (int k = 0; k < 3; k++) {
+            const double mid = 0.5 * (lo[k] + hi[k]);
+            h.cap_p0[l][k] = (k == ax) ? lo[k] : mid;
+            h.cap_p1[l][k] = (k == ax) ? hi[k] : mid;
         }
-        h.link_radius[l] = rad * (1.0 + 1e-9) + 1e-12;
+        double rad = 0.0;
+        for (int p = h.link_begin[l]; p < h.link_begin[l + 1]; p++) {
+            const double v[3] = {px[(size_t)p], py[(size_t)p], pz[(size_t)p]};
+            double d2 = 0.0;
+            for (int k = 0; k < 3; k++) {
+                const double c = (k == ax) ? std::min(std::max(v[k], lo[k]), hi[k]) : h.cap_p0[l][k];
+                d2 += (v[k] - c) * (v[k] - c);
+            }
+            rad = std::max(rad, std::sqrt(d2));
+        }
+        h.cap_radius[l] = rad * (1.0 + 1e-9) + 1e-12;
     }
     rob->stride = (r->kind == FKS_ROBOT_SE2) ? 3 : (r->kind == FKS_ROBOT_SE3 ? 12 : D);
 
     DeviceGuard guard(device);
     if (!guard.ok) { delete rob; return fail(FKS_ERR_CUDA, "fks_robot_create: cudaSetDevice failed"); }
+    std::vector<double2> pxy((size_t)h.P);
+    std::vector<PointZL> pzl((size_t)h.P);
+    for (int i = 0; i < h.P; i++) {
+        pxy[(size_t)i] = make_double2(px[(size_t)i], py[(size_t)i]);
+        pzl[(size_t)i].z = pz[(size_t)i];
+        pzl[(size_t)i].link = plink[(size_t)i];
+        pzl[(size_t)i]._pad = 0;
+    }
     int rc = upload(&rob->d_robot, &rob->host, 1);
-    if (rc == FKS_OK) rc = upload(&rob->d_px, px.data(), px.size());
-    if (rc == FKS_OK) rc = upload(&rob->d_py, py.data(), py.size());
-    if (rc == FKS_OK) rc = upload(&rob->d_pz, pz.data(), pz.size());
-    if (rc == FKS_OK) rc = upload(&rob->d_plink, plink.data(), plink.size());
+    if (rc == FKS_OK) rc = upload(&rob->d_pxy, pxy.data(), pxy.size());
+    if (rc == FKS_OK) rc = upload(&rob->d_pzl, pzl.data(), pzl.size());
     if (rc != FKS_OK) { fks_robot_destroy(rob); return rc; }
     *out = rob;
     return FKS_OK;
@@ -413,10 +433,8 @@ void fks_robot_destroy(fks_robot* robot) {
     if (!robot) return;
     DeviceGuard guard(robot->device);
     cudaFree(robot->d_robot);
-    cudaFree(robot->d_px);
-    cudaFree(robot->d_py);
-    cudaFree(robot->d_pz);
-    cudaFree(robot->d_plink);
+    cudaFree(robot->d_pxy);
+    cudaFree(robot->d_pzl);
     delete robot;
 }
 
@@ -465,21 +483,26 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     s->sp.failed_ends_motion = params->failed_resolves_end_motion ? 1 : 0;
 
     const DevRobot& h = robot->host;
-    s->dyn_smem = simulate_dyn_smem(h.kind, h.L, h.J, h.D, h.P, robot->stride);
-    int rc = simulate_kernel_info(h.kind, s->dyn_smem, &s->kinfo);
+    std::memset(&s->plan, 0, sizeof(s->plan));
+    int wpb = kWarpsPerBlock;
+    if (const char* ev = std::getenv("FKS_WARPS_PER_BLOCK")) {  // developer knob: 1..16 warps per lock-step CTA
+        const int v = std::atoi(ev);
+        if (v >= 1 && v <= kWarpsPerBlock) wpb = v;
+    }
+    s->dyn_smem = simulate_smem_plan(&s->plan, h.L, h.J, h.D, h.P, robot->stride, wpb);
+    int rc = simulate_kernel_info(h.kind, s->dyn_smem, wpb, &s->kinfo);
     if (rc != 0) { delete s; return cuda_fail((cudaError_t)rc, "fks_sim_create: kernel attributes"); }
     if (s->kinfo.max_blocks_per_sm < 1) { delete s; return fail(FKS_ERR_UNSUPPORTED, "fks_sim_create: robot does not fit one CTA's shared memory"); }
     cudaDeviceProp prop;
     cudaError_t err = cudaGetDeviceProperties(&prop, s->device);
     if (err != cudaSuccess) { delete s; return cuda_fail(err, "cudaGetDeviceProperties"); }
     s->grid_max = prop.multiProcessorCount * s->kinfo.max_blocks_per_sm;
-    s->sl = make_scratch_layout(h.D, h.P);
-    const size_t scratch_bytes = (size_t)s->grid_max * kWarpsPerBlock * s->sl.total;
+    const size_t scratch_bytes = (size_t)s->grid_max * wpb * s->plan.sl.total;
     if ((err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_scratch, scratch_bytes)) != cudaSuccess ||
-        (err = cudaMalloc((void**)&s->d_stats, FKS_NUM_STATS * sizeof(unsigned long long))) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_stats, 32 * sizeof(unsigned long long))) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_counter, sizeof(unsigned int))) != cudaSuccess ||
-        (err = cudaMemset(s->d_stats, 0, FKS_NUM_STATS * sizeof(unsigned long long))) != cudaSuccess) {
+        (err = cudaMemset(s->d_stats, 0, 32 * sizeof(unsigned long long))) != cudaSuccess) {
         fks_sim_destroy(s);
         return cuda_fail(err, "fks_sim_create: allocation");
     }
@@ -487,8 +510,8 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     std::snprintf(buf, sizeof(buf),
                   "simulate_kernel<kind=%d>: %d regs/thread, %zu B dynamic smem/CTA, %d B local/thread, %d threads/CTA, "
                   "%d CTAs/SM x %d SMs (persistent grid %d), scratch %llu B/warp, L2 window %zu B",
-                  h.kind, s->kinfo.regs, s->dyn_smem, s->kinfo.local_bytes, kThreadsPerBlock, s->kinfo.max_blocks_per_sm,
-                  prop.multiProcessorCount, s->grid_max, (unsigned long long)s->sl.total, env->l2_window_bytes);
+                  h.kind, s->kinfo.regs, s->dyn_smem, s->kinfo.local_bytes, 32 * wpb, s->kinfo.max_blocks_per_sm,
+                  prop.multiProcessorCount, s->grid_max, (unsigned long long)s->plan.sl.total, env->l2_window_bytes);
     s->info = buf;
     *out = s;
     return FKS_OK;
@@ -519,34 +542,29 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
                               uint64_t first_particle_id, void* d_results, cudaStream_t stream) {
     if (n == 0) return FKS_OK;
     if (n > 0xFFFFFF00ull) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate: too many particles for one call");
-    LaunchArgs a;
-    std::memset(&a, 0, sizeof(a));
-    a.robot = s->robot->d_robot;
-    a.px = s->robot->d_px;
-    a.py = s->robot->d_py;
-    a.pz = s->robot->d_pz;
-    a.plink = s->robot->d_plink;
+    LaunchArgs a = s->plan;
     a.env = s->env->dev;
     a.sp = s->sp;
+    a.robot = s->robot->d_robot;
+    a.pxy = s->robot->d_pxy;
+    a.pzl = s->robot->d_pzl;
     a.starts = d_starts;
     a.targets = d_targets;
-    a.n_particles = n;
-    a.n_targets = n_targets;
-    a.allow_contacts = allow_contacts ? 1 : 0;
-    a.noise_mode = noise_mode;
     a.tape = d_tape;
     a.tape_off = (const unsigned long long*)d_tape_off;
-    a.seed = s->seed;
-    a.first_id = first_particle_id;
     a.results = (char*)d_results;
-    a.cfg_stride = s->robot->stride;
-    a.rec_stride = (int)fks_sim_result_stride(s);
     a.stats = s->d_stats;
     a.counter = s->d_counter;
     a.scratch = s->d_scratch;
-    a.scratch_bytes_per_warp = s->sl.total;
-    a.ldj = s->sl.ldj;
-    const size_t blocks_needed = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    a.n_particles = n;
+    a.n_targets = n_targets;
+    a.seed = s->seed;
+    a.first_id = first_particle_id;
+    a.allow_contacts = allow_contacts ? 1 : 0;
+    a.noise_mode = noise_mode;
+    a.cfg_stride = s->robot->stride;
+    a.rec_stride = (int)fks_sim_result_stride(s);
+    const size_t blocks_needed = (n + s->plan.warps_per_block - 1) / s->plan.warps_per_block;
     const int grid = (int)std::min<size_t>((size_t)s->grid_max, blocks_needed);
     FKS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
     const int rc = launch_simulate(s->robot->host.kind, a, grid, s->dyn_smem, stream, s->env->l2_window_bytes ? s->env->d_sdf : nullptr,
@@ -633,11 +651,20 @@ int fks_reset_statistics(fks_sim* s) {
     if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_reset_statistics: null argument");
     DeviceGuard guard(s->device);
     FKS_CUDA(cudaDeviceSynchronize());
-    FKS_CUDA(cudaMemset(s->d_stats, 0, FKS_NUM_STATS * sizeof(uint64_t)));
+    FKS_CUDA(cudaMemset(s->d_stats, 0, 32 * sizeof(uint64_t)));
     return FKS_OK;
 }
 
 uint64_t fks_sim_launch_count(const fks_sim* s) { return s ? s->launches : 0; }
+
+// developer aid (not in the public header): per-phase clock totals of builds made with -DFKS_PHASE_TIMERS
+int fks_debug_phase_cycles(fks_sim* s, uint64_t* out10) {
+    if (!s || !out10) return FKS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(s->device);
+    FKS_CUDA(cudaDeviceSynchronize());
+    FKS_CUDA(cudaMemcpy(out10, s->d_stats + 16, 10 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return FKS_OK;
+}
 
 const char* fks_sim_kernel_info(fks_sim* s) { return s ? s->info.c_str() : ""; }
 

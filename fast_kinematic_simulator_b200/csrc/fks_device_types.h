@@ -4,7 +4,7 @@
 //   SDF            float[nx*ny*nz], x-major (same linear index as VoxelGrid), L2-persisting window
 //   normal table   open-addressing hash  (cell index + 1) -> (first entry, entry count); entries are
 //                  6 doubles (entry direction xyz, normal xyz)
-//   robot          one DevRobot struct + SoA point arrays (x[], y[], z[], link[]), staged into shared
+//   robot          one DevRobot struct + point arrays ({x,y}[], {z,link}[]), staged into shared
 //                  memory once by every CTA of the persistent kernel
 //   particles      starts/targets as flat doubles (cfg_stride per particle), results as fixed records
 //   scratch        one slot per resident warp: stacked Jacobian (column major) + self-collision work
@@ -22,7 +22,8 @@ constexpr int kMaxLinks = 16;
 constexpr int kMaxJoints = 16;
 constexpr int kMaxPairs = (kMaxLinks * (kMaxLinks - 1)) / 2;
 constexpr int kMaxSelfPartners = kMaxLinks - 1;
-constexpr int kWarpsPerBlock = 4;
+constexpr int kPairChunks = (kMaxPairs + 31) / 32;
+constexpr int kWarpsPerBlock = 16;  // upper bound of warps per CTA (launch bounds); the CTA's warps run in lock step
 constexpr int kThreadsPerBlock = kWarpsPerBlock * 32;
 
 struct DevAxis {
@@ -50,8 +51,8 @@ struct DevRobot {
     unsigned link_ancestors[kMaxLinks];  // bit j: joint j is on the path from the root to this link
     unsigned disallowed[kMaxLinks];      // bit j: self collision between this link and j is NOT allowed
     unsigned char pair_a[kMaxPairs], pair_b[kMaxPairs];  // the disallowed pairs, a < b
-    double link_center[kMaxLinks][3];    // bounding sphere of the link's points (link frame)
-    double link_radius[kMaxLinks];
+    double cap_p0[kMaxLinks][3], cap_p1[kMaxLinks][3];  // bounding capsule of the link's points (link frame)
+    double cap_radius[kMaxLinks];
     double link_mass[kMaxLinks];         // cumulative point counts (spcs.hpp:1244-1255)
 };
 
@@ -80,89 +81,75 @@ struct DevSolver {
     int failed_ends_motion;
 };
 
-struct LaunchArgs {
-    const DevRobot* robot;
-    const double* px;
-    const double* py;
-    const double* pz;
-    const int* plink;
-    DevEnv env;
-    DevSolver sp;
-    const double* starts;
-    const double* targets;
-    unsigned long long n_particles, n_targets;
-    int allow_contacts, noise_mode;
-    const double* tape;
-    const unsigned long long* tape_off;
-    unsigned long long seed, first_id;
-    char* results;
-    int cfg_stride, rec_stride;
-    unsigned long long* stats;
-    unsigned int* counter;
-    char* scratch;                   // per-warp-slot global scratch
-    unsigned long long scratch_bytes_per_warp;
-    int ldj;                         // leading dimension (rows) of the stacked Jacobian columns
-};
-
 // hash of a linear cell index into the normal table (same function on host and device)
 inline __host__ __device__ unsigned long long normal_hash(unsigned long long cell) {
     unsigned long long h = cell * 0x9E3779B97F4A7C15ull;
     return h ^ (h >> 29);
 }
 
-// ---- per-warp shared memory layout (doubles) -------------------------------------------------
+// ---- per-warp shared memory layout (offsets in doubles from the start of the warp's block) -----
+// Three kinematic states X = 0, 1, 2: configuration cfg + X*S and link transforms T + X*L12.  States 0 / 1
+// ping-pong between "previous" and "current" configuration of a microstep, state 2 is the scratch state of
+// the motion estimates.  G / caps are derived from the CURRENT state only.
 struct WarpLayout {
-    int Tprev, Tcur, Ttmp;   // L*12 each
-    int M;                   // J*12 joint motion matrices
-    int jaxis, jorig;        // J*3 each (world joint axes / origins for the Jacobian)
-    int chain;               // 12
-    int cfg, pcfg, tcfg;     // cfg_stride each (SE3: alias of the T arrays)
-    int target;              // cfg_stride
-    int scfg;                // cfg_stride: configuration at the start of the controller step (allow_contacts == false)
-    int act, ru, du, tn, raw, stepv;  // D each
-    int qr;                  // 3*D doubles + D ints (norms updated/direct, hcoeff, transpositions)
+    int S;        // vector slot (doubles) >= max(cfg_stride, D), even
+    int L12;      // 12 * links
+    int cfg;      // 3 * S
+    int T;        // 3 * L12
+    int G;        // L12: per link, (1/res) * inverse_origin * T_link  (world -> voxel coordinates in one transform)
+    int caps;     // 6 * L: world end points of every link's bounding capsule
+    int M;        // 12 * J: joint_transform * motion(value)
+    int jaxis, jorig;  // 3 * J each
+    int target, scfg, act, ru, du, raw, stepv;  // S each
+    int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
+    int qr;       // 4 * S
+    int stats;    // FKS_NUM_STATS u64 counters of this warp
+    int flags;    // 1 (u32 FKS_FLAG_* bits raised by any lane)
     int total;
+    int noise_batch;
 };
 
-inline __host__ __device__ WarpLayout make_warp_layout(int kind, int L, int J, int D, int stride) {
+inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int stride) {
     WarpLayout w;
+    int S = stride > D ? stride : D;
+    S = (S + 1) & ~1;
+    w.S = S;
+    w.L12 = 12 * L;
+    w.noise_batch = 32 / D < 1 ? 1 : (32 / D > 8 ? 8 : 32 / D);
     int o = 0;
-    w.Tprev = o; o += L * 12;
-    w.Tcur = o; o += L * 12;
-    w.Ttmp = o; o += L * 12;
-    w.M = o; o += J * 12;
-    w.jaxis = o; o += J * 3;
-    w.jorig = o; o += J * 3;
-    w.chain = o; o += 12;
-    if (kind == FKS_ROBOT_SE3) {
-        w.pcfg = w.Tprev; w.cfg = w.Tcur; w.tcfg = w.Ttmp;
-    } else {
-        w.cfg = o; o += stride;
-        w.pcfg = o; o += stride;
-        w.tcfg = o; o += stride;
-    }
-    w.target = o; o += stride;
-    w.scfg = o; o += stride;
-    w.act = o; o += D;
-    w.ru = o; o += D;
-    w.du = o; o += D;
-    w.tn = o; o += D;
-    w.raw = o; o += D;
-    w.stepv = o; o += D;
-    w.qr = o; o += 4 * D;
+    w.cfg = o; o += 3 * S;
+    w.T = o; o += 3 * w.L12;
+    w.G = o; o += w.L12;
+    w.caps = o; o += 6 * L;
+    w.M = o; o += 12 * J;
+    w.jaxis = o; o += 3 * J;
+    w.jorig = o; o += 3 * J;
+    o = (o + 1) & ~1;
+    w.target = o; o += S;
+    w.scfg = o; o += S;
+    w.act = o; o += S;
+    w.ru = o; o += S;
+    w.du = o; o += S;
+    w.raw = o; o += S;
+    w.stepv = o; o += S;
+    w.tn = o; o += w.noise_batch * S;
+    w.qr = o; o += 4 * S;
+    w.stats = o; o += FKS_NUM_STATS;
+    w.flags = o; o += 1;
     w.total = (o + 1) & ~1;
     return w;
 }
 
 // ---- per-warp global scratch layout (bytes) --------------------------------------------------
 struct ScratchLayout {
-    unsigned long long jstore;    // (D+1) * ldj doubles
+    unsigned long long jstore;    // (D+1) * ldj doubles, then P u64 (candidate list of collect_corrections)
     unsigned long long selfcorr;  // 3*P doubles
     unsigned long long selfwork;  // small dense solve workspace
-    unsigned long long keys;      // 3*P ints
+    unsigned long long keys;      // P packed 64-bit cell keys
     unsigned long long sflag;     // P bytes
     unsigned long long total;
     int ldj;
+    int _pad;
 };
 
 constexpr int kSelfWorkDoubles = kMaxSelfPartners * 5 + 4 + kMaxSelfPartners * (2 * kMaxSelfPartners) +
@@ -171,25 +158,63 @@ constexpr int kSelfWorkDoubles = kMaxSelfPartners * 5 + 4 + kMaxSelfPartners * (
 inline __host__ __device__ ScratchLayout make_scratch_layout(int D, int P) {
     ScratchLayout s;
     s.ldj = ((3 * P + 3) / 4) * 4;
+    s._pad = 0;
     unsigned long long o = 0;
-    s.jstore = o; o += (unsigned long long)(D + 1) * s.ldj * 8;
+    s.jstore = o; o += (unsigned long long)(D + 1) * s.ldj * 8 + (unsigned long long)P * 8;
     s.selfcorr = o; o += (unsigned long long)3 * P * 8;
     s.selfwork = o; o += (unsigned long long)kSelfWorkDoubles * 8;
-    s.keys = o; o += (((unsigned long long)3 * P * 4 + 7) / 8) * 8;
+    s.keys = o; o += (unsigned long long)P * 8;
     s.sflag = o; o += (((unsigned long long)P + 7) / 8) * 8;
     s.total = ((o + 127) / 128) * 128;
     return s;
 }
+
+// one collision point in shared memory: 32 bytes -> two conflict-free 16-byte arrays
+struct PointZL {
+    double z;
+    int link;
+    int _pad;
+};
+
+// Kernel parameter block.  The kernel copies it (and the robot) into a shared-memory Frame so that every
+// device function reads uniform data with LDS at fixed offsets.
+struct LaunchArgs {
+    DevEnv env;
+    DevSolver sp;
+    WarpLayout wl;
+    ScratchLayout sl;
+    const DevRobot* robot;
+    const double2* pxy;      // [P] link-relative x, y
+    const PointZL* pzl;      // [P] z and the link index
+    const double* starts;
+    const double* targets;
+    const double* tape;
+    const unsigned long long* tape_off;
+    char* results;
+    unsigned long long* stats;
+    unsigned int* counter;
+    char* scratch;                   // per-warp-slot global scratch
+    unsigned long long n_particles, n_targets, seed, first_id;
+    int allow_contacts, noise_mode, cfg_stride, rec_stride;
+    int P, warps_per_block;
+    int pts_off, warps_off;          // byte offsets of the point arrays / the warp blocks in dynamic shared memory
+};
+
+struct Frame {
+    LaunchArgs a;
+    DevRobot rb;
+};
 
 // launch interface implemented in fks_kernels.cu
 struct KernelInfo {
     int regs, static_smem, local_bytes, max_blocks_per_sm;
     size_t dyn_smem;
 };
-int simulate_kernel_info(int kind, size_t dyn_smem, KernelInfo* out);
+int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelInfo* out);
 int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
                     const void* l2_window_base, size_t l2_window_bytes);
-size_t simulate_dyn_smem(int kind, int L, int J, int D, int P, int stride);
+// fills args.wl / pts_off / warps_off / warps_per_block and returns the dynamic shared memory size
+size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block);
 int launch_fp64_peak(double* out, int grid, int iters, void* stream);
 int launch_gather(const float* data, unsigned long long n_mask, float* out, int grid, int iters, void* stream);
 

@@ -9,7 +9,15 @@
 //
 // Nothing here is a dense contraction, so no tensor cores: the contended units are the FP64 pipe and
 // the LSU/L2 gather path (SDF floats through the read-only path, L2-resident via an access-policy
-// window).
+// window).  Design points that follow from the profile (profiles/):
+//   * every piece of uniform data (robot, environment metadata, solver, launch scalars, layouts) sits in
+//     a shared-memory Frame at offset 0, so device functions address it with LDS + immediate offsets
+//     instead of generic loads through pointers;
+//   * per link, world->voxel coordinates are ONE 3x4 transform G_l = (1/res) * inverse_origin * T_l, rebuilt
+//     with the forward kinematics; the per-point collision test is 9 FMAs + 3 truncations + 1 gather;
+//   * "previous" and "current" kinematic state ping-pong between two buffers (no copies);
+//   * actuator noise for several microsteps is drawn at once so that all lanes do Philox/Box-Muller work;
+//   * the big building blocks are single __noinline__ copies (instruction-cache footprint).
 //
 // Reference line numbers below (spcs = simple_particle_contact_simulator.hpp, tnuva =
 // tnuva_robot_models.hpp, unc = simple_uncertainty_models.hpp, pid = simple_pid_controller.hpp)
@@ -28,29 +36,27 @@ namespace fksdev {
 
 #define FKS_FULL 0xffffffffu
 
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
 namespace {
 
 constexpr double kPi = 3.14159265358979323846;
 
-struct Ctx {
-    const DevRobot* rb;  // shared memory copy
-    const double* px;
-    const double* py;
-    const double* pz;
-    const int* plink;
-    double* ws;  // this warp's shared block
-    WarpLayout wl;
-    int lane, L, J, D, P, stride;
-    // global scratch of this warp slot
-    double* Js;
-    int ldj;
-    double* selfcorr;
-    double* selfwork;
-    int* keys;
-    unsigned char* sflag;
-    unsigned lflags;  // lane-local FKS_FLAG_* bits, OR-reduced when the particle ends
-    unsigned cand_links;
-};
+// ---- shared-memory accessors -------------------------------------------------------------------
+__device__ __forceinline__ const Frame& frame() { return *reinterpret_cast<const Frame*>(smem_raw); }
+__device__ __forceinline__ double* wsd(int wb) { return reinterpret_cast<double*>(smem_raw + wb); }
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ void raise_flag(int wb, unsigned bits) {
+    atomicOr(reinterpret_cast<unsigned*>(wsd(wb) + frame().a.wl.flags), bits);
+}
+__device__ __forceinline__ void add_stat(int wb, int which, unsigned long long v) {  // lane 0 only
+    reinterpret_cast<unsigned long long*>(wsd(wb) + frame().a.wl.stats)[which] += v;
+}
+// global scratch of this warp
+__device__ __forceinline__ char* scratch_slot() {
+    const LaunchArgs& a = frame().a;
+    return a.scratch + (size_t)(blockIdx.x * a.warps_per_block + (threadIdx.x >> 5)) * a.sl.total;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -170,7 +176,7 @@ __device__ __forceinline__ void safe_normal3(double& x, double& y, double& z) {
 }
 
 // EigenHelpers::TwistBetweenTransforms(a, b) = unhat(log(a^-1 b)) (call site tnuva:389), closed form
-__device__ void twist_between(const double* a, const double* b, double* twist) {
+__device__ __noinline__ void twist_between(const double* a, const double* b, double* twist) {
     double ai[12], Dm[12];
     iso_inverse(a, ai);
     iso_mul(ai, b, Dm);
@@ -234,8 +240,8 @@ __device__ void twist_between(const double* a, const double* b, double* twist) {
 }
 
 // TruncatedNormalUncertainVelocityActuator::GetControlValue (unc:70-75 noiseless, :77-90 noisy)
-__device__ __forceinline__ double actuate(const DevAxis& ax, double u, bool noisy, double tn, unsigned& lflags) {
-    if (isnan(u) || isinf(u)) lflags |= FKS_FLAG_WOULD_ASSERT_NAN;  // assert unc:72-73
+__device__ __forceinline__ double actuate(int wb, const DevAxis& ax, double u, bool noisy, double tn) {
+    if (isnan(u) || isinf(u)) raise_flag(wb, FKS_FLAG_WOULD_ASSERT_NAN);  // assert unc:72-73
     const double vl = ax.vlim;
     const double real_u = fmin(fmax(u, -vl), vl);
     if (!noisy) return real_u;
@@ -246,11 +252,19 @@ __device__ __forceinline__ double actuate(const DevAxis& ax, double u, bool nois
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward kinematics: SetPosition (call sites spcs:875,1423-1424,1601).  cfg and T are shared memory.
+// Kinematic state X: SetPosition (call sites spcs:875,1423-1424,1601).  Reads cfg[X] (wraps / clamps it in
+// place), writes T[X].  derive != 0 additionally rebuilds what the collision checks of the CURRENT state
+// read: G (world -> voxel transform per link) and the world end points of the link capsules.
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __forceinline__ void forward_kinematics(Ctx& c, double* cfg, double* T) {
-    const int lane = c.lane;
+__device__ __noinline__ void kinematics(int wb, int X, int derive) {
+    const Frame& fr = frame();
+    const WarpLayout& wl = fr.a.wl;
+    const DevRobot& rb = fr.rb;
+    const int lane = lane_id();
+    double* ws = wsd(wb);
+    double* cfg = ws + wl.cfg + X * wl.S;
+    double* T = ws + wl.T + X * wl.L12;
     if (KIND == FKS_ROBOT_SE2) {
         if (lane == 0) {
             const double th = wrap_angle(cfg[2]);
@@ -265,16 +279,14 @@ __device__ __forceinline__ void forward_kinematics(Ctx& c, double* cfg, double* 
         }
         __syncwarp();
     } else if (KIND == FKS_ROBOT_SE3) {
-        if (cfg != T) {
-            if (lane < 12) T[lane] = cfg[lane];
-            __syncwarp();
-        }
+        if (lane < 12) T[lane] = cfg[lane];
+        __syncwarp();
     } else {
-        const DevRobot* rb = c.rb;
-        double* M = c.ws + c.wl.M;
-        // joint values (wrap / clamp) and joint motion matrices, one joint per lane
-        for (int j = lane; j < c.J; j += 32) {
-            const DevJoint& jd = rb->joints[j];
+        double* M = ws + wl.M;
+        // one joint per lane: value (wrap / clamp), then M_j = joint_transform * motion(value)
+        for (int j = lane; j < rb.J; j += 32) {
+            const DevJoint& jd = rb.joints[j];
+            double Mj[12];
             if (jd.active >= 0) {
                 double v = cfg[jd.active];
                 if (jd.type == FKS_JOINT_CONTINUOUS) {
@@ -294,89 +306,103 @@ __device__ __forceinline__ void forward_kinematics(Ctx& c, double* cfg, double* 
                 } else {
                     rot_axis(v, jd.axis[0], jd.axis[1], jd.axis[2], R);
                 }
+                double Jt[12];
 #pragma unroll
-                for (int i = 0; i < 12; i++) M[12 * j + i] = R[i];
+                for (int i = 0; i < 12; i++) Jt[i] = jd.T[i];
+                iso_mul(Jt, R, Mj);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; i++) Mj[i] = jd.T[i];
             }
+#pragma unroll
+            for (int i = 0; i < 12; i++) M[12 * j + i] = Mj[i];
         }
-        if (lane < 12) T[lane] = rb->base[lane];
+        if (lane < 12) T[lane] = rb.base[lane];
         __syncwarp();
-        double* chain = c.ws + c.wl.chain;
         const int r = lane >> 2, cc = lane & 3;
-        for (int j = 0; j < c.J; j++) {
-            const DevJoint& jd = rb->joints[j];
+        for (int j = 0; j < rb.J; j++) {
+            const DevJoint& jd = rb.joints[j];
             if (lane < 12) {
                 const double* Tp = T + 12 * jd.parent;
-                double v = Tp[4 * r + 0] * jd.T[cc] + Tp[4 * r + 1] * jd.T[4 + cc] + Tp[4 * r + 2] * jd.T[8 + cc];
+                const double* Mj = M + 12 * j;
+                double v = Tp[4 * r + 0] * Mj[cc] + Tp[4 * r + 1] * Mj[4 + cc] + Tp[4 * r + 2] * Mj[8 + cc];
                 if (cc == 3) v += Tp[4 * r + 3];
-                chain[lane] = v;
-            }
-            __syncwarp();
-            if (lane < 12) {
-                double v;
-                if (jd.type == FKS_JOINT_FIXED) {
-                    v = chain[lane];
-                } else {
-                    const double* Mj = M + 12 * j;
-                    v = chain[4 * r + 0] * Mj[cc] + chain[4 * r + 1] * Mj[4 + cc] + chain[4 * r + 2] * Mj[8 + cc];
-                    if (cc == 3) v += chain[4 * r + 3];
-                }
                 T[12 * jd.child + lane] = v;
             }
             __syncwarp();
         }
     }
+    if (derive) {
+        const DevEnv& e = fr.a.env;
+        double* G = ws + wl.G;
+        for (int el = lane; el < wl.L12; el += 32) {
+            const int l = el / 12, rc = el - 12 * l, r = rc >> 2, cc = rc & 3;
+            const double* Tl = T + 12 * l;
+            double v = e.inv_origin[4 * r + 0] * Tl[cc] + e.inv_origin[4 * r + 1] * Tl[4 + cc] + e.inv_origin[4 * r + 2] * Tl[8 + cc];
+            if (cc == 3) v += e.inv_origin[4 * r + 3];
+            G[el] = v * e.inv_sdf_res;
+        }
+        if (KIND == FKS_ROBOT_LINKED && rb.n_pairs > 0) {
+            double* caps = ws + wl.caps;
+            for (int q = lane; q < 2 * rb.L; q += 32) {
+                const int l = q >> 1;
+                const double* cp = (q & 1) ? rb.cap_p1[l] : rb.cap_p0[l];
+                double x, y, z;
+                apply_T(T + 12 * l, cp[0], cp[1], cp[2], x, y, z);
+                caps[3 * q] = x;
+                caps[3 * q + 1] = y;
+                caps[3 * q + 2] = z;
+            }
+        }
+        __syncwarp();
+    }
 }
 
-// ApplyControlInput(input[, rng]) (tnuva:152-177 SE2, :348-382 SE3, :538-596 linked).
-// Reads (cfg_in), writes (cfg_out, T_out); in and out may alias.  tn == nullptr: noiseless overload.
+// ApplyControlInput(input[, rng]) (tnuva:152-177 SE2, :348-382 SE3, :538-596 linked): state Xout = state Xin
+// advanced by u (shared vector at offset u_off); tn_off < 0 selects the noiseless overload.  Xin == Xout allowed.
 template <int KIND>
-__device__ __forceinline__ void apply_control(Ctx& c, const double* cfg_in, double* cfg_out, double* T_out,
-                                              const double* u, const double* tn) {
-    const int lane = c.lane;
+__device__ __noinline__ void apply_control(int wb, int Xin, int Xout, int u_off, int tn_off, int derive) {
+    const Frame& fr = frame();
+    const WarpLayout& wl = fr.a.wl;
+    const int lane = lane_id();
+    double* ws = wsd(wb);
+    const double* cin = ws + wl.cfg + Xin * wl.S;
+    double* cout = ws + wl.cfg + Xout * wl.S;
+    const bool noisy = tn_off >= 0;
     if (KIND == FKS_ROBOT_SE3) {
-        double* stepv = c.ws + c.wl.stepv;
-        if (lane < 6) stepv[lane] = actuate(c.rb->axes[lane], u[lane], tn != nullptr, tn ? tn[lane] : 0.0, c.lflags);
+        double* qr = ws + wl.qr;  // free outside the QR solve: holds the actuated twist
+        if (lane < 6) qr[lane] = actuate(wb, fr.rb.axes[lane], ws[u_off + lane], noisy, noisy ? ws[tn_off + lane] : 0.0);
         __syncwarp();
         double tw[6], E[12], A[12], Cm[12];
 #pragma unroll
-        for (int i = 0; i < 6; i++) tw[i] = stepv[i];
+        for (int i = 0; i < 6; i++) tw[i] = qr[i];
         exp_twist(tw, E);
 #pragma unroll
-        for (int i = 0; i < 12; i++) A[i] = cfg_in[i];
+        for (int i = 0; i < 12; i++) A[i] = cin[i];
         iso_mul(A, E, Cm);
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < 12; i++) cfg_out[i] = Cm[i];
+            for (int i = 0; i < 12; i++) cout[i] = Cm[i];
         }
         __syncwarp();
-        (void)T_out;  // SE3: the configuration IS the link transform
     } else {
-        if (lane < c.D) cfg_out[lane] = cfg_in[lane] + actuate(c.rb->axes[lane], u[lane], tn != nullptr, tn ? tn[lane] : 0.0, c.lflags);
+        if (lane < fr.rb.D) cout[lane] = cin[lane] + actuate(wb, fr.rb.axes[lane], ws[u_off + lane], noisy, noisy ? ws[tn_off + lane] : 0.0);
         __syncwarp();
-        forward_kinematics<KIND>(c, cfg_out, T_out);
     }
+    kinematics<KIND>(wb, Xout, derive);
 }
 
 // ------------------------------------------------------------------------------------------------
 // environment queries
 // ------------------------------------------------------------------------------------------------
-// VoxelGrid::LocationToGridIndex: grid-frame point * (1 / cell), C-cast truncation
-__device__ __forceinline__ bool cell_index(const DevEnv& e, double wx, double wy, double wz, int& ix, int& iy, int& iz) {
-    const double gx = e.inv_origin[0] * wx + e.inv_origin[1] * wy + e.inv_origin[2] * wz + e.inv_origin[3];
-    const double gy = e.inv_origin[4] * wx + e.inv_origin[5] * wy + e.inv_origin[6] * wz + e.inv_origin[7];
-    const double gz = e.inv_origin[8] * wx + e.inv_origin[9] * wy + e.inv_origin[10] * wz + e.inv_origin[11];
-    ix = (int)(gx * e.inv_sdf_res);
-    iy = (int)(gy * e.inv_sdf_res);
-    iz = (int)(gz * e.inv_sdf_res);
-    return ix >= 0 && iy >= 0 && iz >= 0 && ix < e.nx && iy < e.ny && iz < e.nz;
-}
 __device__ __forceinline__ float sdf_cell(const DevEnv& e, int x, int y, int z) {
-    return __ldg(e.sdf + ((size_t)x * e.ny + y) * e.nz + z);
+    return __ldg(e.sdf + ((x * e.ny + y) * e.nz + z));
 }
 
 // SignedDistanceField::EstimateDistance4d for an in-bounds point whose cell (x,y,z) holds d0f
-__device__ __forceinline__ double estimate_distance(const DevEnv& e, double wx, double wy, double wz, int x, int y, int z, float d0f) {
+__device__ __noinline__ double estimate_distance(double wx, double wy, double wz, int x, int y, int z, float d0f) {
+    const DevEnv& e = frame().a.env;
     const double res = e.sdf_res;
     const double d0 = (double)d0f;
     const double dc = (d0 >= 0.0) ? d0 - (res * 0.5) : d0 + (res * 0.5);
@@ -405,42 +431,100 @@ __device__ __forceinline__ double estimate_distance(const DevEnv& e, double wx, 
     return dc + adj;
 }
 
-// CheckEnvironmentCollision (spcs:921-981) for the link transforms T; collision_threshold = 0.0 (spcs:424)
-__device__ __forceinline__ bool check_env(const Ctx& c, const DevEnv& e, const DevSolver& sp, const double* T) {
+// voxel of a link-relative point through the composite transform G_l; false when out of bounds.
+// VoxelGrid::LocationToGridIndex semantics: C-cast truncation of grid coordinate / cell size.
+struct Voxel {
+    int x, y, z;
+    bool inb;
+};
+__device__ __forceinline__ Voxel voxel_of(const DevEnv& e, const double* Gl, double px, double py, double pz) {
+    const double2 g01 = *reinterpret_cast<const double2*>(Gl + 0), g23 = *reinterpret_cast<const double2*>(Gl + 2);
+    const double2 g45 = *reinterpret_cast<const double2*>(Gl + 4), g67 = *reinterpret_cast<const double2*>(Gl + 6);
+    const double2 g89 = *reinterpret_cast<const double2*>(Gl + 8), gab = *reinterpret_cast<const double2*>(Gl + 10);
+    const double gx = g01.x * px + g01.y * py + g23.x * pz + g23.y;
+    const double gy = g45.x * px + g45.y * py + g67.x * pz + g67.y;
+    const double gz = g89.x * px + g89.y * py + gab.x * pz + gab.y;
+    Voxel v;
+    v.x = (int)gx;
+    v.y = (int)gy;
+    v.z = (int)gz;
+    v.inb = ((unsigned)v.x < (unsigned)e.nx) && ((unsigned)v.y < (unsigned)e.ny) && ((unsigned)v.z < (unsigned)e.nz);
+    return v;
+}
+
+constexpr int kBatch = 4;  // independent SDF gathers in flight per lane
+
+// CheckEnvironmentCollision (spcs:921-981) of the CURRENT state (G and T[X]); collision_threshold = 0.0 (spcs:424)
+__device__ __noinline__ bool check_env(int wb, int X) {
+    const Frame& fr = frame();
+    const DevEnv& e = fr.a.env;
+    const WarpLayout& wl = fr.a.wl;
+    const int lane = lane_id();
+    const double* ws = wsd(wb);
+    const double* G = ws + wl.G;
+    const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
+    const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
+    const int P = fr.a.P;
     const double res = e.sdf_res;
-    const double thr = 0.0 - (sp.check_tolerance * res);
+    const double thr = 0.0 - (fr.a.sp.check_tolerance * res);
     const double thr_deep = thr - res;
+    const float oob = e.oob;
     bool hit = false;
-#pragma unroll 2
-    for (int p = c.lane; p < c.P; p += 32) {
-        const double* Tl = T + 12 * c.plink[p];
-        double wx, wy, wz;
-        apply_T(Tl, c.px[p], c.py[p], c.pz[p], wx, wy, wz);
-        int x, y, z;
-        if (cell_index(e, wx, wy, wz, x, y, z)) {
-            const float f = sdf_cell(e, x, y, z);
-            if ((double)f < thr) {
-                if ((double)f < thr_deep) hit = true;
-                else if (estimate_distance(e, wx, wy, wz, x, y, z, f) < thr) hit = true;
+    for (int base = 0; base < P; base += 32 * kBatch) {
+        float f[kBatch];
+        Voxel vx[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            const int p = base + 32 * k + lane;
+            f[k] = INFINITY;
+            vx[k].inb = false;
+            if (p < P) {
+                const double2 xy = pxy[p];
+                const PointZL zl = pzl[p];
+                vx[k] = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
+                f[k] = vx[k].inb ? sdf_cell(e, vx[k].x, vx[k].y, vx[k].z) : oob;
             }
         }
-        // out of bounds: the value is the oob value (+inf from the builder -> never a collision, spcs:943-955);
-        // EstimateDistance4d out of bounds returns the same value, so both tiers reduce to one compare
-        else if ((double)e.oob < thr) hit = true;
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            if ((double)f[k] < thr) {
+                if ((double)f[k] < thr_deep || !vx[k].inb) {
+                    // deep inside, or out of bounds with an oob value below the threshold (EstimateDistance4d
+                    // out of bounds returns the same value, so both tiers reduce to one compare, spcs:943-975)
+                    hit = true;
+                } else {
+                    const int p = base + 32 * k + lane;
+                    const double2 xy = pxy[p];
+                    const PointZL zl = pzl[p];
+                    double wx, wy, wz;
+                    apply_T(ws + wl.T + X * wl.L12 + 12 * zl.link, xy.x, xy.y, zl.z, wx, wy, wz);
+                    if (estimate_distance(wx, wy, wz, vx[k].x, vx[k].y, vx[k].z, f[k]) < thr) hit = true;
+                }
+            }
+        }
     }
     return __any_sync(FKS_FULL, hit);
 }
 
-// EstimateMaxControlInputWorkspaceMotion(start_robot, end_robot) (spcs:1492-1527)
-__device__ __forceinline__ double max_motion(const Ctx& c, const double* Ta, const double* Tb) {
+// EstimateMaxControlInputWorkspaceMotion(start_robot, end_robot) (spcs:1492-1527) between states Xa and Xb
+__device__ __noinline__ double max_motion(int wb, int Xa, int Xb) {
+    const Frame& fr = frame();
+    const WarpLayout& wl = fr.a.wl;
+    const int lane = lane_id();
+    const double* ws = wsd(wb);
+    const double* Ta = ws + wl.T + Xa * wl.L12;
+    const double* Tb = ws + wl.T + Xb * wl.L12;
+    const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
+    const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
+    const int P = fr.a.P;
     double mx = 0.0;
 #pragma unroll 2
-    for (int p = c.lane; p < c.P; p += 32) {
-        const int l = c.plink[p];
-        const double x = c.px[p], y = c.py[p], z = c.pz[p];
+    for (int p = lane; p < P; p += 32) {
+        const double2 xy = pxy[p];
+        const PointZL zl = pzl[p];
         double ax, ay, az, bx, by, bz;
-        apply_T(Ta + 12 * l, x, y, z, ax, ay, az);
-        apply_T(Tb + 12 * l, x, y, z, bx, by, bz);
+        apply_T(Ta + 12 * zl.link, xy.x, xy.y, zl.z, ax, ay, az);
+        apply_T(Tb + 12 * zl.link, xy.x, xy.y, zl.z, bx, by, bz);
         const double dx = bx - ax, dy = by - ay, dz = bz - az;
         const double sq = dx * dx + dy * dy + dz * dz;
         if (sq > mx) mx = sq;
@@ -450,8 +534,8 @@ __device__ __forceinline__ double max_motion(const Ctx& c, const double* Ta, con
 
 // SurfaceNormalGrid::LookupSurfaceNormal + GetBestSurfaceNormal (spcs:186-198,235-256,111-132) for the
 // in-bounds cell `li`; (dx,dy,dz) is the SafeNormal'd motion direction.
-__device__ __forceinline__ void lookup_normal(const DevEnv& e, long long li, double dx, double dy, double dz,
-                                              double& nx, double& ny, double& nz, unsigned& lflags) {
+__device__ __forceinline__ void lookup_normal(int wb, const DevEnv& e, long long li, double dx, double dy, double dz,
+                                              double& nx, double& ny, double& nz) {
     nx = ny = nz = 0.0;
     const unsigned long long key = (unsigned long long)li + 1ull;
     unsigned long long h = normal_hash((unsigned long long)li) & e.nh_mask;
@@ -473,7 +557,7 @@ __device__ __forceinline__ void lookup_normal(const DevEnv& e, long long li, dou
         uy = dy / dn;
         uz = dz / dn;
     } else {
-        lflags |= FKS_FLAG_WOULD_ASSERT_NORMAL;  // assert(direction_norm > 0.0) spcs:115
+        raise_flag(wb, FKS_FLAG_WOULD_ASSERT_NORMAL);  // assert(direction_norm > 0.0) spcs:115
     }
     double best_dot = -INFINITY;
     unsigned best = range.x;
@@ -494,55 +578,82 @@ __device__ __forceinline__ void lookup_normal(const DevEnv& e, long long li, dou
 // ------------------------------------------------------------------------------------------------
 // self collisions: CollectSelfCollisions (spcs:1183-1275) + ExtractSelfCollidingPoints (spcs:983-1171)
 //
-// Two points share a cell of edge map_res only if they are within sqrt(3)*map_res of each other, so
-// a bounding-sphere test over the DISALLOWED link pairs decides exactly when the hash-grid pass can
-// be skipped (the common case).  The exact pass keeps the reference's per-cell semantics.
-// Returns true when at least one point received a correction (self_collision_map non-empty);
-// corrections are left in c.selfcorr, per-point flags in c.sflag (bit 0).
+// Two points share a cell of edge map_res only if they are within sqrt(3)*map_res of each other, so a
+// capsule test over the DISALLOWED link pairs decides exactly when the hash-grid pass can be skipped (the
+// common case).  The exact pass keeps the reference's per-cell semantics.  Returns true when at least one
+// point received a correction (self_collision_map non-empty); corrections are left in the scratch slot's
+// selfcorr array, per-point flags in sflag (bit 0).
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ bool self_collisions_exact(Ctx& c, const DevEnv& e, const DevSolver& sp, const double* Tprev, const double* Tcur);
 
-__device__ __forceinline__ bool collect_self(Ctx& c, const DevEnv& e, const DevSolver& sp, const double* Tprev, const double* Tcur) {
-    const DevRobot* rb = c.rb;
-    if (rb->n_pairs == 0) return false;  // one link, or every pair allowed (spcs:1186-1197)
-    unsigned cand = 0u;
-    const double diag = 1.7320508075688772 * e.map_res * (1.0 + 1e-6);
-    for (int q = c.lane; q < rb->n_pairs; q += 32) {
-        const int a = rb->pair_a[q], b = rb->pair_b[q];
-        double ax, ay, az, bx, by, bz;
-        apply_T(Tcur + 12 * a, rb->link_center[a][0], rb->link_center[a][1], rb->link_center[a][2], ax, ay, az);
-        apply_T(Tcur + 12 * b, rb->link_center[b][0], rb->link_center[b][1], rb->link_center[b][2], bx, by, bz);
-        const double dx = ax - bx, dy = ay - by, dz = az - bz;
-        const double reach = rb->link_radius[a] + rb->link_radius[b] + diag;
-        if (dx * dx + dy * dy + dz * dz <= reach * reach) cand |= (1u << a) | (1u << b);
+// squared distance between segments [p1,q1] and [p2,q2] (clamped closest points; degenerate segments allowed)
+__device__ __forceinline__ double segment_distance_sq(const double* p1, const double* q1, const double* p2, const double* q2) {
+    const double d1x = q1[0] - p1[0], d1y = q1[1] - p1[1], d1z = q1[2] - p1[2];
+    const double d2x = q2[0] - p2[0], d2y = q2[1] - p2[1], d2z = q2[2] - p2[2];
+    const double rx = p1[0] - p2[0], ry = p1[1] - p2[1], rz = p1[2] - p2[2];
+    const double a = d1x * d1x + d1y * d1y + d1z * d1z;
+    const double ee = d2x * d2x + d2y * d2y + d2z * d2z;
+    const double f = d2x * rx + d2y * ry + d2z * rz;
+    const double tiny = 1e-300;
+    double s, t;
+    if (a <= tiny && ee <= tiny) {
+        s = t = 0.0;
+    } else if (a <= tiny) {
+        s = 0.0;
+        t = fmin(fmax(f / ee, 0.0), 1.0);
+    } else {
+        const double cc = d1x * rx + d1y * ry + d1z * rz;
+        if (ee <= tiny) {
+            t = 0.0;
+            s = fmin(fmax(-cc / a, 0.0), 1.0);
+        } else {
+            const double bb = d1x * d2x + d1y * d2y + d1z * d2z;
+            const double denom = a * ee - bb * bb;
+            s = (denom > 0.0) ? fmin(fmax((bb * f - cc * ee) / denom, 0.0), 1.0) : 0.0;
+            t = (bb * s + f) / ee;
+            if (t < 0.0) {
+                t = 0.0;
+                s = fmin(fmax(-cc / a, 0.0), 1.0);
+            } else if (t > 1.0) {
+                t = 1.0;
+                s = fmin(fmax((bb - cc) / a, 0.0), 1.0);
+            }
+        }
     }
-    cand = __reduce_or_sync(FKS_FULL, cand);
-    if (cand == 0u) return false;
-    c.cand_links = cand;
-    return self_collisions_exact(c, e, sp, Tprev, Tcur);
+    const double cx = (p1[0] + d1x * s) - (p2[0] + d2x * t), cy = (p1[1] + d1y * s) - (p2[1] + d2y * t), cz = (p1[2] + d1z * s) - (p2[2] + d2z * t);
+    return cx * cx + cy * cy + cz * cz;
 }
 
-__device__ __forceinline__ bool key_eq(const int* keys, int a, int b) {
-    return keys[3 * a] == keys[3 * b] && keys[3 * a + 1] == keys[3 * b + 1] && keys[3 * a + 2] == keys[3 * b + 2];
-}
+struct SelfCtx {
+    unsigned cand_pairs[kPairChunks];
+    unsigned cand_links;
+    unsigned long long* keys;
+    unsigned char* sflag;
+    double* selfcorr;
+    double* selfwork;
+};
 
 // scan the points of `link` for members of the cell of point `ref`: count, first member, and the
 // momentum sum (point velocities added in point order, spcs:1040-1054)
-__device__ __forceinline__ void scan_link_cell(const Ctx& c, const double* Tprev, const double* Tcur, int link, int ref,
+__device__ __forceinline__ void scan_link_cell(const SelfCtx& sc, const double* Tprev, const double* Tcur, int link, int ref,
                                                double time_multiplier, int& count, int& first, double& mx, double& my, double& mz) {
-    const DevRobot* rb = c.rb;
+    const Frame& fr = frame();
+    const DevRobot& rb = fr.rb;
+    const int lane = lane_id();
+    const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
+    const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
     count = 0;
     first = -1;
     mx = my = mz = 0.0;
-    const int begin = rb->link_begin[link], end = rb->link_begin[link + 1];
+    const int begin = rb.link_begin[link], end = rb.link_begin[link + 1];
+    const unsigned long long kref = sc.keys[ref];
     for (int base = begin; base < end; base += 32) {
-        const int q = base + c.lane;
-        const bool match = (q < end) && key_eq(c.keys, q, ref);
+        const int q = base + lane;
+        const bool match = (q < end) && (sc.keys[q] == kref);
         double vx = 0.0, vy = 0.0, vz = 0.0;
         if (match) {
             double ax, ay, az, bx, by, bz;
-            apply_T(Tcur + 12 * link, c.px[q], c.py[q], c.pz[q], ax, ay, az);
-            apply_T(Tprev + 12 * link, c.px[q], c.py[q], c.pz[q], bx, by, bz);
+            apply_T(Tcur + 12 * link, pxy[q].x, pxy[q].y, pzl[q].z, ax, ay, az);
+            apply_T(Tprev + 12 * link, pxy[q].x, pxy[q].y, pzl[q].z, bx, by, bz);
             vx = (ax - bx) * time_multiplier;
             vy = (ay - by) * time_multiplier;
             vz = (az - bz) * time_multiplier;
@@ -560,93 +671,130 @@ __device__ __forceinline__ void scan_link_cell(const Ctx& c, const double* Tprev
     }
 }
 
-__device__ __noinline__ bool self_collisions_exact(Ctx& c, const DevEnv& e, const DevSolver& sp, const double* Tprev, const double* Tcur) {
-    const DevRobot* rb = c.rb;
-    const unsigned cand = c.cand_links;
-    const int lane = c.lane;
-    // cell keys: LocationToExtendedGridIndex (spcs:1173-1181) DIVIDES by the map resolution
-    for (int p = lane; p < c.P; p += 32) {
-        const int l = c.plink[p];
-        int kx = 0, ky = 0, kz = 0;
+__device__ __noinline__ bool self_collisions_exact(int wb, int Xprev, int Xcur, unsigned cp0, unsigned cp1, unsigned cp2, unsigned cp3) {
+    const Frame& fr = frame();
+    const DevRobot& rb = fr.rb;
+    const DevEnv& e = fr.a.env;
+    const WarpLayout& wl = fr.a.wl;
+    const int lane = lane_id();
+    const int P = fr.a.P;
+    const double* ws = wsd(wb);
+    const double* Tprev = ws + wl.T + Xprev * wl.L12;
+    const double* Tcur = ws + wl.T + Xcur * wl.L12;
+    const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
+    const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
+    char* slot = scratch_slot();
+    SelfCtx sc;
+    sc.cand_pairs[0] = cp0;
+    sc.cand_pairs[1] = cp1;
+    sc.cand_pairs[2] = cp2;
+    sc.cand_pairs[3] = cp3;
+    sc.keys = reinterpret_cast<unsigned long long*>(slot + fr.a.sl.keys);
+    sc.sflag = reinterpret_cast<unsigned char*>(slot + fr.a.sl.sflag);
+    sc.selfcorr = reinterpret_cast<double*>(slot + fr.a.sl.selfcorr);
+    sc.selfwork = reinterpret_cast<double*>(slot + fr.a.sl.selfwork);
+    unsigned cand = 0u;  // links taking part in a candidate pair
+#pragma unroll
+    for (int ch = 0; ch < kPairChunks; ch++) {
+        unsigned m = sc.cand_pairs[ch];
+        while (m) {
+            const int q = ch * 32 + (__ffs(m) - 1);
+            m &= m - 1u;
+            cand |= (1u << rb.pair_a[q]) | (1u << rb.pair_b[q]);
+        }
+    }
+    sc.cand_links = cand;
+    // cell keys: LocationToExtendedGridIndex (spcs:1173-1181) DIVIDES by the map resolution; the three
+    // truncated coordinates are packed 21 bits each (cells of one robot pose never differ by 2^21)
+    for (int p = lane; p < P; p += 32) {
+        const int l = pzl[p].link;
+        unsigned long long key = 0ull;
         if ((cand >> l) & 1u) {
             double wx, wy, wz;
-            apply_T(Tcur + 12 * l, c.px[p], c.py[p], c.pz[p], wx, wy, wz);
+            apply_T(Tcur + 12 * l, pxy[p].x, pxy[p].y, pzl[p].z, wx, wy, wz);
             const double gx = e.inv_origin[0] * wx + e.inv_origin[1] * wy + e.inv_origin[2] * wz + e.inv_origin[3];
             const double gy = e.inv_origin[4] * wx + e.inv_origin[5] * wy + e.inv_origin[6] * wz + e.inv_origin[7];
             const double gz = e.inv_origin[8] * wx + e.inv_origin[9] * wy + e.inv_origin[10] * wz + e.inv_origin[11];
-            kx = (int)(gx / e.map_res);
-            ky = (int)(gy / e.map_res);
-            kz = (int)(gz / e.map_res);
+            const long long kx = (long long)(gx / e.map_res), ky = (long long)(gy / e.map_res), kz = (long long)(gz / e.map_res);
+            key = ((unsigned long long)kx & 0x1FFFFFull) | (((unsigned long long)ky & 0x1FFFFFull) << 21) |
+                  (((unsigned long long)kz & 0x1FFFFFull) << 42);
         }
-        c.keys[3 * p] = kx;
-        c.keys[3 * p + 1] = ky;
-        c.keys[3 * p + 2] = kz;
+        sc.keys[p] = key;
+        sc.sflag[p] = 0;
     }
     __syncwarp();
-    // per point: does its cell hold a point of a link it may not touch?  is it the first of its link there?
+    // per candidate pair: mark the points of either link whose cell also holds a point of the other link.
+    // A point is always handled by the same lane ((p - link_begin) % 32), so the flag updates need no barrier.
     bool any = false;
-    for (int base = 0; base < c.P; base += 32) {
-        const int p = base + lane;
-        unsigned char flag = 0;
-        if (p < c.P) {
-            const int l = c.plink[p];
-            if ((cand >> l) & 1u) {
-                unsigned dis = rb->disallowed[l] & cand;
-                bool collides = false;
-                while (dis && !collides) {
-                    const int m = __ffs(dis) - 1;
-                    dis &= dis - 1u;
-                    for (int q = rb->link_begin[m]; q < rb->link_begin[m + 1]; q++)
-                        if (key_eq(c.keys, q, p)) {
-                            collides = true;
-                            break;
-                        }
-                }
-                if (collides) {
-                    bool leader = true;
-                    for (int q = rb->link_begin[l]; q < p; q++)
-                        if (key_eq(c.keys, q, p)) {
-                            leader = false;
-                            break;
-                        }
-                    flag = leader ? 3 : 1;
+#pragma unroll
+    for (int ch = 0; ch < kPairChunks; ch++) {
+        unsigned m = sc.cand_pairs[ch];
+        while (m) {
+            const int q = ch * 32 + (__ffs(m) - 1);
+            m &= m - 1u;
+#pragma unroll
+            for (int role = 0; role < 2; role++) {
+                const int la = role ? rb.pair_b[q] : rb.pair_a[q];
+                const int lb = role ? rb.pair_a[q] : rb.pair_b[q];
+                const int a0 = rb.link_begin[la], a1 = rb.link_begin[la + 1];
+                const int b0 = rb.link_begin[lb], b1 = rb.link_begin[lb + 1];
+                for (int base = a0; base < a1; base += 32) {
+                    const int p = base + lane;
+                    const unsigned long long kp = (p < a1) ? sc.keys[p] : 0ull;
+                    bool hit = false;
+#pragma unroll 4
+                    for (int qq = b0; qq < b1; qq++) hit = hit || (sc.keys[qq] == kp);
+                    hit = hit && (p < a1);
+                    if (hit) sc.sflag[p] = 1;
+                    any = any || __any_sync(FKS_FULL, hit);
                 }
             }
-            c.sflag[p] = flag;
         }
-        any = any || __any_sync(FKS_FULL, flag != 0);
     }
     __syncwarp();
     if (!any) return false;
-    const double time_multiplier = 1.0 / sp.interval;
-    double* sw = c.selfwork;
+    // leaders: the first point of its link in a colliding cell
+    for (int p = lane; p < P; p += 32) {
+        if (sc.sflag[p] & 1) {
+            bool leader = true;
+            for (int q = rb.link_begin[pzl[p].link]; q < p; q++)
+                if (sc.keys[q] == sc.keys[p]) {
+                    leader = false;
+                    break;
+                }
+            if (leader) sc.sflag[p] = 3;
+        }
+    }
+    __syncwarp();
+    const double time_multiplier = 1.0 / fr.a.sp.interval;
+    double* sw = sc.selfwork;
     // one (cell, link) group at a time, the whole warp working on it
-    for (int base = 0; base < c.P; base += 32) {
+    for (int base = 0; base < P; base += 32) {
         const int p = base + lane;
-        unsigned leaders = __ballot_sync(FKS_FULL, (p < c.P) && (c.sflag[p] == 3));
+        unsigned leaders = __ballot_sync(FKS_FULL, (p < P) && (sc.sflag[p] == 3));
         while (leaders) {
             const int gp = base + (__ffs(leaders) - 1);
             leaders &= leaders - 1u;
-            const int l = c.plink[gp];
+            const int l = pzl[gp].link;
             int cnt_i, first_i;
             double mix, miy, miz;
-            scan_link_cell(c, Tprev, Tcur, l, gp, time_multiplier, cnt_i, first_i, mix, miy, miz);
+            scan_link_cell(sc, Tprev, Tcur, l, gp, time_multiplier, cnt_i, first_i, mix, miy, miz);
             double aix, aiy, aiz;
-            apply_T(Tprev + 12 * l, c.px[first_i], c.py[first_i], c.pz[first_i], aix, aiy, aiz);
+            apply_T(Tprev + 12 * l, pxy[first_i].x, pxy[first_i].y, pzl[first_i].z, aix, aiy, aiz);
             const double inv_i = 1.0 / (double)cnt_i;
             const double vix = mix * inv_i, viy = miy * inv_i, viz = miz * inv_i;
             // colliding links in ascending order (std::map iteration, spcs:1000-1017)
             int m = 0;
-            unsigned dis = rb->disallowed[l] & cand;
+            unsigned dis = rb.disallowed[l] & sc.cand_links;
             while (dis) {
                 const int s = __ffs(dis) - 1;
                 dis &= dis - 1u;
                 int cnt_s, first_s;
                 double msx, msy, msz;
-                scan_link_cell(c, Tprev, Tcur, s, gp, time_multiplier, cnt_s, first_s, msx, msy, msz);
+                scan_link_cell(sc, Tprev, Tcur, s, gp, time_multiplier, cnt_s, first_s, msx, msy, msz);
                 if (cnt_s == 0) continue;
                 double ox, oy, oz;
-                apply_T(Tprev + 12 * s, c.px[first_s], c.py[first_s], c.pz[first_s], ox, oy, oz);
+                apply_T(Tprev + 12 * s, pxy[first_s].x, pxy[first_s].y, pzl[first_s].z, ox, oy, oz);
                 double nx = ox - aix, ny = oy - aiy, nz = oz - aiz;
                 safe_normal3(nx, ny, nz);
                 const double inv_s = 1.0 / (double)cnt_s;
@@ -657,7 +805,7 @@ __device__ __noinline__ bool self_collisions_exact(Ctx& c, const DevEnv& e, cons
                     sw[5 * m + 1] = ny;
                     sw[5 * m + 2] = nz;
                     sw[5 * m + 3] = rhs;
-                    sw[5 * m + 4] = rb->link_mass[s];
+                    sw[5 * m + 4] = rb.link_mass[s];
                 }
                 m++;
             }
@@ -665,9 +813,9 @@ __device__ __noinline__ bool self_collisions_exact(Ctx& c, const DevEnv& e, cons
             __syncwarp();
             if (lane == 0) {
                 // A = N^T C^T M^-1 C N (spcs:1135), inverse by partial-pivot Gauss elimination, lambda = A^-1 r
-                double* Mx = out + 4;                                  // m x 2m augmented
+                double* Mx = out + 4;                                          // m x 2m augmented
                 double* Ainv = Mx + kMaxSelfPartners * 2 * kMaxSelfPartners;  // m x m
-                const double mass_i = rb->link_mass[l];
+                const double mass_i = rb.link_mass[l];
                 const int n = m;
                 for (int a = 0; a < n; a++)
                     for (int b = 0; b < n; b++) {
@@ -720,12 +868,13 @@ __device__ __noinline__ bool self_collisions_exact(Ctx& c, const DevEnv& e, cons
             }
             __syncwarp();
             const double ppx = out[0], ppy = out[1], ppz = out[2];
-            if (isnan(ppx) || isnan(ppy) || isnan(ppz)) c.lflags |= FKS_FLAG_WOULD_ASSERT_NAN;  // asserts spcs:1151-1153
-            for (int q = rb->link_begin[l] + lane; q < rb->link_begin[l + 1]; q += 32)
-                if (key_eq(c.keys, q, gp)) {
-                    c.selfcorr[3 * q] = ppx;
-                    c.selfcorr[3 * q + 1] = ppy;
-                    c.selfcorr[3 * q + 2] = ppz;
+            if (isnan(ppx) || isnan(ppy) || isnan(ppz)) raise_flag(wb, FKS_FLAG_WOULD_ASSERT_NAN);  // asserts spcs:1151-1153
+            const unsigned long long kgp = sc.keys[gp];
+            for (int q = rb.link_begin[l] + lane; q < rb.link_begin[l + 1]; q += 32)
+                if (sc.keys[q] == kgp) {
+                    sc.selfcorr[3 * q] = ppx;
+                    sc.selfcorr[3 * q + 1] = ppy;
+                    sc.selfcorr[3 * q + 2] = ppz;
                 }
             __syncwarp();
         }
@@ -733,32 +882,83 @@ __device__ __noinline__ bool self_collisions_exact(Ctx& c, const DevEnv& e, cons
     return true;
 }
 
-// CheckCollision (spcs:1418-1436)
+// broad phase over the disallowed link pairs, on the capsule end points kinematics() left in shared memory
+__device__ __forceinline__ bool collect_self(int wb, int Xprev, int Xcur) {
+    const Frame& fr = frame();
+    const DevRobot& rb = fr.rb;
+    if (rb.n_pairs == 0) return false;  // one link, or every pair allowed (spcs:1186-1197)
+    const int lane = lane_id();
+    const double* caps = wsd(wb) + fr.a.wl.caps;
+    const double diag = 1.7320508075688772 * fr.a.env.map_res * (1.0 + 1e-6) + 1e-9;
+    unsigned cp[kPairChunks] = {0u, 0u, 0u, 0u};
+    bool anyc = false;
+    const int nch = (rb.n_pairs + 31) >> 5;
+    for (int ch = 0; ch < nch; ch++) {
+        const int q = ch * 32 + lane;
+        bool hit = false;
+        if (q < rb.n_pairs) {
+            const int a = rb.pair_a[q], b = rb.pair_b[q];
+            const double d2 = segment_distance_sq(caps + 6 * a, caps + 6 * a + 3, caps + 6 * b, caps + 6 * b + 3);
+            const double reach = rb.cap_radius[a] + rb.cap_radius[b] + diag;
+            hit = d2 <= reach * reach;
+        }
+        const unsigned m = __ballot_sync(FKS_FULL, hit);
+        if (ch == 0) cp[0] = m;
+        else if (ch == 1) cp[1] = m;
+        else if (ch == 2) cp[2] = m;
+        else cp[3] = m;
+        anyc = anyc || (m != 0u);
+    }
+    if (!anyc) return false;
+    return self_collisions_exact(wb, Xprev, Xcur, cp[0], cp[1], cp[2], cp[3]);
+}
+
+// CheckCollision (spcs:1418-1436): bit 0 = in collision, bit 1 = self-collision map non-empty
 template <int KIND>
-__device__ __forceinline__ bool check_collision(Ctx& c, const DevEnv& e, const DevSolver& sp, const double* Tprev, const double* Tcur, bool& has_self) {
-    const bool envc = check_env(c, e, sp, Tcur);
-    has_self = (KIND == FKS_ROBOT_LINKED) ? collect_self(c, e, sp, Tprev, Tcur) : false;
-    return envc || has_self;
+__device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur) {
+    const bool envc = check_env(wb, Xcur);
+    const bool has_self = (KIND == FKS_ROBOT_LINKED) ? collect_self(wb, Xprev, Xcur) : false;
+    return ((envc || has_self) ? 1u : 0u) | (has_self ? 2u : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
 // CollectPointCorrectionsAndJacobians (spcs:1818-1939): fills the stacked Jacobian (column major,
-// leading dimension c.ldj, column D holds the corrections), rows in link-major point-minor order.
+// leading dimension ldj, column D holds the corrections), rows in link-major point-minor order.
 // Returns the number of rows.
+//
+// Two passes.  Pass 1 is the cheap voxel test of check_env over all points, kBatch gathers in flight per
+// lane: EstimateDistance4d = f -/+ res/2 + (|.| <= sqrt(3)/2 res) cannot be negative when the raw cell value
+// f >= 2 res, so only "near" points (and points holding a self-collision correction) survive, compacted in
+// point order into the scratch slot's key array.  Pass 2 runs the expensive part -- 6 more gathers, the
+// normal lookup, the Jacobian row -- on the survivors only.
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __forceinline__ int collect_corrections(Ctx& c, const DevEnv& e, const double* Tprev, const double* Tcur, bool has_self) {
-    const int lane = c.lane;
-    const DevRobot* rb = c.rb;
-    double* A = c.Js;
-    const int ld = c.ldj;
-    const int D = c.D;
-    double* jaxis = c.ws + c.wl.jaxis;
-    double* jorig = c.ws + c.wl.jorig;
+__device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, bool has_self) {
+    const Frame& fr = frame();
+    const DevRobot& rb = fr.rb;
+    const DevEnv& e = fr.a.env;
+    const WarpLayout& wl = fr.a.wl;
+    const int lane = lane_id();
+    const int P = fr.a.P, D = rb.D;
+    double* ws = wsd(wb);
+    const double* Tprev = ws + wl.T + Xprev * wl.L12;
+    const double* Tcur = ws + wl.T + Xcur * wl.L12;
+    const double* G = ws + wl.G;
+    const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
+    const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
+    char* slot = scratch_slot();
+    double* A = reinterpret_cast<double*>(slot + fr.a.sl.jstore);
+    const int ld = fr.a.sl.ldj;
+    const unsigned char* sflag = reinterpret_cast<const unsigned char*>(slot + fr.a.sl.sflag);
+    const double* selfcorr = reinterpret_cast<const double*>(slot + fr.a.sl.selfcorr);
+    // candidate list (point index, bit 31 = needs the environment estimate), stored behind the Jacobian columns
+    unsigned* cand = reinterpret_cast<unsigned*>(A + (size_t)(D + 1) * ld);
+    double* jaxis = ws + wl.jaxis;
+    double* jorig = ws + wl.jorig;
     if (KIND == FKS_ROBOT_LINKED) {
         // world axis / origin of every joint (frame = child link transform)
-        for (int j = lane; j < c.J; j += 32) {
-            const DevJoint& jd = rb->joints[j];
+        for (int j = lane; j < rb.J; j += 32) {
+            const DevJoint& jd = rb.joints[j];
             const double* Tj = Tcur + 12 * jd.child;
             jaxis[3 * j + 0] = Tj[0] * jd.axis[0] + Tj[1] * jd.axis[1] + Tj[2] * jd.axis[2];
             jaxis[3 * j + 1] = Tj[4] * jd.axis[0] + Tj[5] * jd.axis[1] + Tj[6] * jd.axis[2];
@@ -767,48 +967,80 @@ __device__ __forceinline__ int collect_corrections(Ctx& c, const DevEnv& e, cons
             jorig[3 * j + 1] = Tj[7];
             jorig[3 * j + 2] = Tj[11];
         }
-        __syncwarp();
     }
     const double res = e.sdf_res;
+    const float near = (float)(2.0 * res);
+    // ---- pass 1 -----------------------------------------------------------------------------------
+    int ncand = 0;
+    for (int base = 0; base < P; base += 32 * kBatch) {
+        float f[kBatch];
+        Voxel vx[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            const int p = base + 32 * k + lane;
+            f[k] = INFINITY;
+            vx[k].x = vx[k].y = vx[k].z = 0;
+            vx[k].inb = false;
+            if (p < P) {
+                const double2 xy = pxy[p];
+                const PointZL zl = pzl[p];
+                vx[k] = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
+                if (vx[k].inb) f[k] = sdf_cell(e, vx[k].x, vx[k].y, vx[k].z);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            const int p = base + 32 * k + lane;
+            const bool is_near = vx[k].inb && (f[k] < near);
+            const bool keep = (p < P) && (is_near || (has_self && (sflag[p] & 1)));
+            const unsigned mask = __ballot_sync(FKS_FULL, keep);
+            if (keep) cand[ncand + __popc(mask & ((1u << lane) - 1u))] = (unsigned)p | (is_near ? 0x80000000u : 0u);
+            ncand += __popc(mask);
+        }
+    }
+    __syncwarp();
+    // ---- pass 2 -----------------------------------------------------------------------------------
     int npts = 0;
-    for (int base = 0; base < c.P; base += 32) {
-        const int p = base + lane;
+    for (int base = 0; base < ncand; base += 32) {
+        const int ci = base + lane;
         bool have = false;
         double cx = 0.0, cy = 0.0, cz = 0.0;
         double wx = 0.0, wy = 0.0, wz = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
         int l = 0;
-        if (p < c.P) {
-            l = c.plink[p];
-            lx = c.px[p];
-            ly = c.py[p];
-            lz = c.pz[p];
-            if (has_self && (c.sflag[p] & 1)) {
-                have = true;
-                cx = cx + c.selfcorr[3 * p];
-                cy = cy + c.selfcorr[3 * p + 1];
-                cz = cz + c.selfcorr[3 * p + 2];
-            }
+        if (ci < ncand) {
+            const unsigned rec = cand[ci];
+            const int p = (int)(rec & 0x7FFFFFFFu);
+            const double2 xy = pxy[p];
+            const PointZL zl = pzl[p];
+            l = zl.link;
+            lx = xy.x;
+            ly = xy.y;
+            lz = zl.z;
             apply_T(Tcur + 12 * l, lx, ly, lz, wx, wy, wz);
-            int x, y, z;
-            if (cell_index(e, wx, wy, wz, x, y, z)) {
-                const float f = sdf_cell(e, x, y, z);
-                // EstimateDistance = f -/+ res/2 + (|.| <= sqrt(3)/2 res): cannot be negative when f >= 2 res
-                if ((double)f < 2.0 * res) {
-                    const double est = estimate_distance(e, wx, wy, wz, x, y, z, f);
-                    if (est < 0.0) {  // resolution_distance_threshold_ = 0.0 (spcs:425,1874)
-                        double qx, qy, qz;
-                        apply_T(Tprev + 12 * l, lx, ly, lz, qx, qy, qz);
-                        double dx = wx - qx, dy = wy - qy, dz = wz - qz;
-                        safe_normal3(dx, dy, dz);
-                        double nx, ny, nz;
-                        lookup_normal(e, ((long long)x * e.ny + y) * e.nz + z, dx, dy, dz, nx, ny, nz, c.lflags);
-                        safe_normal3(nx, ny, nz);
-                        const double pen = fabs(0.0 - est);
-                        cx = cx + nx * pen;
-                        cy = cy + ny * pen;
-                        cz = cz + nz * pen;
-                        have = true;
-                    }
+            if (has_self && (sflag[p] & 1)) {
+                have = true;
+                cx = cx + selfcorr[3 * p];
+                cy = cy + selfcorr[3 * p + 1];
+                cz = cz + selfcorr[3 * p + 2];
+            }
+            if (rec >> 31) {
+                const Voxel v = voxel_of(e, G + 12 * l, lx, ly, lz);  // same arithmetic as pass 1: same voxel
+                const int vxx = v.x, vyy = v.y, vzz = v.z;
+                const float f = sdf_cell(e, vxx, vyy, vzz);
+                const double est = estimate_distance(wx, wy, wz, vxx, vyy, vzz, f);
+                if (est < 0.0) {  // resolution_distance_threshold_ = 0.0 (spcs:425,1874)
+                    double qx, qy, qz;
+                    apply_T(Tprev + 12 * l, lx, ly, lz, qx, qy, qz);
+                    double dx = wx - qx, dy = wy - qy, dz = wz - qz;
+                    safe_normal3(dx, dy, dz);
+                    double nx, ny, nz;
+                    lookup_normal(wb, e, ((long long)vxx * e.ny + vyy) * e.nz + vzz, dx, dy, dz, nx, ny, nz);
+                    safe_normal3(nx, ny, nz);
+                    const double pen = fabs(0.0 - est);
+                    cx = cx + nx * pen;
+                    cy = cy + ny * pen;
+                    cz = cz + nz * pen;
+                    have = true;
                 }
             }
         }
@@ -821,22 +1053,19 @@ __device__ __forceinline__ int collect_corrections(Ctx& c, const DevEnv& e, cons
             b[2] = cz;
             // ComputeLinkPointTranslationJacobian (3 x D)
             if (KIND == FKS_ROBOT_SE2) {
-                const double* T = Tcur;
-                const double rx = wx - T[3], ry = wy - T[7], rz = wz - 0.0;
-                (void)rz;
+                const double rx = wx - Tcur[3], ry = wy - Tcur[7];
                 double* a0 = A + row0;
                 a0[0] = 1.0; a0[1] = 0.0; a0[2] = 0.0;
                 double* a1 = A + ld + row0;
                 a1[0] = 0.0; a1[1] = 1.0; a1[2] = 0.0;
                 double* a2 = A + 2 * ld + row0;  // z x (p_world - (x, y, 0))
-                a2[0] = 0.0 * rz - 1.0 * ry;
-                a2[1] = 1.0 * rx - 0.0 * rz;
-                a2[2] = 0.0 * ry - 0.0 * rx;
+                a2[0] = 0.0 - ry;
+                a2[1] = rx;
+                a2[2] = 0.0;
             } else if (KIND == FKS_ROBOT_SE3) {
-                const double* T = Tcur;
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
-                    const double t0 = T[4 * r + 0], t1 = T[4 * r + 1], t2 = T[4 * r + 2];
+                    const double t0 = Tcur[4 * r + 0], t1 = Tcur[4 * r + 1], t2 = Tcur[4 * r + 2];
                     A[0 * ld + row0 + r] = t0;
                     A[1 * ld + row0 + r] = t1;
                     A[2 * ld + row0 + r] = t2;
@@ -845,13 +1074,13 @@ __device__ __forceinline__ int collect_corrections(Ctx& c, const DevEnv& e, cons
                     A[5 * ld + row0 + r] = t0 * (-ly) + t1 * lx;
                 }
             } else {
-                const unsigned anc = rb->link_ancestors[l];
+                const unsigned anc = rb.link_ancestors[l];
                 for (int a = 0; a < D; a++) {
-                    const int j = rb->active_joint[a];
+                    const int j = rb.active_joint[a];
                     double jx = 0.0, jy = 0.0, jz = 0.0;
                     if ((anc >> j) & 1u) {
                         const double ax = jaxis[3 * j], ay = jaxis[3 * j + 1], az = jaxis[3 * j + 2];
-                        if (rb->joints[j].type == FKS_JOINT_PRISMATIC) {
+                        if (rb.joints[j].type == FKS_JOINT_PRISMATIC) {
                             jx = ax; jy = ay; jz = az;
                         } else {
                             const double rx = wx - jorig[3 * j], ry = wy - jorig[3 * j + 1], rz = wz - jorig[3 * j + 2];
@@ -875,14 +1104,19 @@ __device__ __forceinline__ int collect_corrections(Ctx& c, const DevEnv& e, cons
 
 // ------------------------------------------------------------------------------------------------
 // ComputeResolverCorrectionStepStackedJacobian (spcs:1990-1998): x = J.colPivHouseholderQr().solve(c),
-// Eigen 3.3 semantics.  A is rows x cols column major (leading dimension ld), b = column
-// `cols` of the same store.  Lanes stride over rows.  Result in x (shared memory, cols entries).
+// Eigen 3.3 semantics.  A is rows x cols column major (leading dimension ld) in the scratch
+// slot, b = column `cols` of the same store.  Lanes stride over rows.  Result in the shared vector at x_off.
 // ------------------------------------------------------------------------------------------------
-__device__ void colpiv_qr_solve(Ctx& c, double* A, int ld, int rows, int cols, double* x) {
-    const int lane = c.lane;
-    double* nu = c.ws + c.wl.qr;  // norms updated
-    double* nd = nu + cols;       // norms direct
-    double* hc = nd + cols;       // householder coefficients
+__device__ __noinline__ void colpiv_qr_solve(int wb, int rows, int cols, int x_off) {
+    const Frame& fr = frame();
+    const int lane = lane_id();
+    double* ws = wsd(wb);
+    double* A = reinterpret_cast<double*>(scratch_slot() + fr.a.sl.jstore);
+    const int ld = fr.a.sl.ldj;
+    double* x = ws + x_off;
+    double* nu = ws + fr.a.wl.qr;  // norms updated
+    double* nd = nu + cols;        // norms direct
+    double* hc = nd + cols;        // householder coefficients
     int* transp = (int*)(hc + cols);
     double* b = A + (size_t)cols * ld;
     const int size = rows < cols ? rows : cols;
@@ -916,7 +1150,7 @@ __device__ void colpiv_qr_solve(Ctx& c, double* A, int ld, int rows, int cols, d
         const double big_sq = big * big;
         const double cut = threshold_helper * (double)(rows - k);
         if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
-        if (max_norm > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) c.lflags |= FKS_FLAG_NEAR_RANK_CUT;
+        if (lane == 0 && max_norm > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
         __syncwarp();
         double* ck = A + (size_t)k * ld;
         if (k != biggest) {
@@ -1019,265 +1253,419 @@ __device__ void colpiv_qr_solve(Ctx& c, double* A, int ld, int rows, int cols, d
     if (lane < cols) x[lane] = 0.0;
     __syncwarp();
     if (lane == 0 && nonzero_pivots > 0) {
-        // back substitution on the leading nz x nz upper triangle, then un-permute
+        // back substitution on the leading nz x nz upper triangle, then un-permute (perm kept as 4-bit nibbles)
         for (int i = nonzero_pivots - 1; i >= 0; i--) {
             double s = b[i];
             for (int j = i + 1; j < nonzero_pivots; j++) s -= A[(size_t)j * ld + i] * b[j];
             b[i] = s / A[(size_t)i * ld + i];
         }
-        int perm[kMaxDof];
-        for (int j = 0; j < cols; j++) perm[j] = j;
+        unsigned long long perm = 0xFEDCBA9876543210ull;
         for (int k = 0; k < size; k++) {
-            const int t = perm[k];
-            perm[k] = perm[transp[k]];
-            perm[transp[k]] = t;
+            const int t = transp[k];
+            const unsigned long long pk = (perm >> (4 * k)) & 0xFull, pt = (perm >> (4 * t)) & 0xFull;
+            perm &= ~((0xFull << (4 * k)) | (0xFull << (4 * t)));
+            perm |= (pt << (4 * k)) | (pk << (4 * t));
         }
-        for (int i = 0; i < nonzero_pivots; i++) x[perm[i]] = b[i];
+        for (int i = 0; i < nonzero_pivots; i++) x[(perm >> (4 * i)) & 0xFull] = b[i];
     }
     __syncwarp();
 }
 
-struct Stats {
-    unsigned long long v[FKS_NUM_STATS];
-};
-
-// EstimateMaxControlInputWorkspaceMotion(robot, control_input) (spcs:1538-1544): noiseless apply on a copy
-template <int KIND>
-__device__ __forceinline__ double max_motion_of_input(Ctx& c, const double* u) {
-    double* cfg = c.ws + c.wl.cfg;
-    double* tcfg = c.ws + c.wl.tcfg;
-    double* Tcur = c.ws + c.wl.Tcur;
-    double* Ttmp = c.ws + c.wl.Ttmp;
-    apply_control<KIND>(c, cfg, tcfg, Ttmp, u, nullptr);
-    return max_motion(c, Tcur, Ttmp);
+// Register-resident variant of the same solve for the common small systems: rows <= 64, NC columns known at
+// compile time (3 / 6 / 7: the reference's three robots).  Lane l keeps rows l and l + 32 of all NC columns
+// and of the right-hand side in registers; rows beyond `rows` are zero, which leaves every Householder
+// quantity unchanged.  Column swaps are register selects, the dot products of one reflector against all
+// trailing columns go through ONE interleaved shuffle tree, and the reflectors are applied to the
+// right-hand side as they are formed (only those below the rank cut, as Eigen's solve does).
+template <int NC>
+__device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
+    const Frame& fr = frame();
+    const int lane = lane_id();
+    double* ws = wsd(wb);
+    const double* A = reinterpret_cast<const double*>(scratch_slot() + fr.a.sl.jstore);
+    const int ld = fr.a.sl.ldj;
+    double a0[NC + 1], a1[NC + 1];  // slot 0: row lane, slot 1: row lane + 32; index NC = right-hand side
+#pragma unroll
+    for (int c = 0; c <= NC; c++) {
+        a0[c] = (lane < rows) ? A[(size_t)c * ld + lane] : 0.0;
+        a1[c] = (lane + 32 < rows) ? A[(size_t)c * ld + lane + 32] : 0.0;
+    }
+    const int size = rows < NC ? rows : NC;
+    double nu[NC], nd[NC], hc[NC];
+    {
+        double sq[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) sq[c] = a0[c] * a0[c] + a1[c] * a1[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int c = 0; c < NC; c++) sq[c] += __shfl_xor_sync(FKS_FULL, sq[c], o);
+#pragma unroll
+        for (int c = 0; c < NC; c++) nd[c] = nu[c] = sqrt(sq[c]);
+    }
+    double max_norm = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) max_norm = fmax(max_norm, nu[c]);
+    const double eps = DBL_EPSILON;
+    const double threshold_helper = ((max_norm * eps) * (max_norm * eps)) / (double)rows;
+    const double norm_downdate_threshold = sqrt(eps);
+    int nonzero_pivots = size;
+    unsigned transp = 0u;
+    bool near_cut = false;
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        hc[k] = 0.0;
+        if (k < size) {
+            int biggest = k;
+            double big = nu[k];
+#pragma unroll
+            for (int j = k + 1; j < NC; j++)
+                if (nu[j] > big) {
+                    big = nu[j];
+                    biggest = j;
+                }
+            const double big_sq = big * big;
+            const double cut = threshold_helper * (double)(rows - k);
+            if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
+            if (max_norm > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
+            transp |= (unsigned)biggest << (4 * k);
+            // swap columns k <-> biggest (registers, runtime `biggest`)
+            {
+                const double o0 = a0[k], o1 = a1[k], onu = nu[k], ond = nd[k];
+                double p0 = o0, p1 = o1, pnu = onu, pnd = ond;
+#pragma unroll
+                for (int j = k + 1; j < NC; j++)
+                    if (j == biggest) {
+                        p0 = a0[j]; p1 = a1[j]; pnu = nu[j]; pnd = nd[j];
+                        a0[j] = o0; a1[j] = o1; nu[j] = onu; nd[j] = ond;
+                    }
+                a0[k] = p0; a1[k] = p1; nu[k] = pnu; nd[k] = pnd;
+            }
+            // makeHouseholderInPlace on col(k).tail(rows - k)
+            const bool below = lane > k;  // slot 0 rows below the diagonal (slot 1 rows always are)
+            const double tail_sq = warp_sum((below ? a0[k] * a0[k] : 0.0) + a1[k] * a1[k]);
+            const double c0 = __shfl_sync(FKS_FULL, a0[k], k);
+            double tau, beta;
+            if (tail_sq <= DBL_MIN) {
+                tau = 0.0;
+                beta = c0;
+                if (below) a0[k] = 0.0;
+                a1[k] = 0.0;
+            } else {
+                beta = sqrt(c0 * c0 + tail_sq);
+                if (c0 >= 0.0) beta = -beta;
+                const double denom = c0 - beta;
+                if (below) a0[k] = a0[k] / denom;
+                a1[k] = a1[k] / denom;
+                tau = (beta - c0) / beta;
+            }
+            hc[k] = tau;
+            if (lane == k) a0[k] = beta;
+            const bool apply_b = nonzero_pivots > k;  // Eigen's solve applies the first nonzero_pivots reflectors to c
+            // applyHouseholderOnTheLeft to the trailing columns (and the right-hand side)
+            if (rows - k == 1) {
+                if (lane == k) {
+#pragma unroll
+                    for (int j = k + 1; j < NC; j++) a0[j] *= (1.0 - tau);
+                    if (apply_b) a0[NC] *= (1.0 - tau);
+                }
+            } else if (tau != 0.0) {
+                double dt[NC + 1];
+#pragma unroll
+                for (int j = k + 1; j <= NC; j++) dt[j] = (below ? a0[k] * a0[j] : 0.0) + a1[k] * a1[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int j = k + 1; j <= NC; j++) dt[j] += __shfl_xor_sync(FKS_FULL, dt[j], o);
+#pragma unroll
+                for (int j = k + 1; j <= NC; j++) {
+                    if (j == NC && !apply_b) continue;
+                    const double tmp = dt[j] + __shfl_sync(FKS_FULL, a0[j], k);
+                    if (lane == k) a0[j] -= tau * tmp;
+                    else if (below) a0[j] -= (tau * a0[k]) * tmp;
+                    a1[j] -= (tau * a1[k]) * tmp;
+                }
+            }
+            // LAPACK-style norm downdate
+#pragma unroll
+            for (int j = k + 1; j < NC; j++) {
+                const double akj = __shfl_sync(FKS_FULL, a0[j], k);
+                if (nu[j] != 0.0) {
+                    double temp = fabs(akj) / nu[j];
+                    temp = (1.0 + temp) * (1.0 - temp);
+                    temp = temp < 0.0 ? 0.0 : temp;
+                    const double ratio = nu[j] / nd[j];
+                    const double temp2 = temp * (ratio * ratio);
+                    if (temp2 <= norm_downdate_threshold) {
+                        const double s2 = warp_sum((below ? a0[j] * a0[j] : 0.0) + a1[j] * a1[j]);
+                        nd[j] = sqrt(s2);
+                        nu[j] = nd[j];
+                    } else {
+                        nu[j] = nu[j] * sqrt(temp);
+                    }
+                }
+            }
+        }
+    }
+    if (near_cut && lane == 0) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
+    // back substitution on the leading nz x nz upper triangle: lane i owns row i
+    double y[NC];
+    double sres = a0[NC];
+#pragma unroll
+    for (int j = NC - 1; j >= 0; j--) {
+        y[j] = 0.0;
+        if (j < nonzero_pivots) {
+            y[j] = __shfl_sync(FKS_FULL, sres / a0[j], j);
+            sres -= a0[j] * y[j];
+        }
+    }
+    if (lane < NC) ws[x_off + lane] = 0.0;
+    __syncwarp();
+    if (lane == 0) {
+        unsigned long long perm = 0xFEDCBA9876543210ull;
+        for (int k = 0; k < size; k++) {
+            const int t = (int)((transp >> (4 * k)) & 0xFu);
+            const unsigned long long pk = (perm >> (4 * k)) & 0xFull, pt = (perm >> (4 * t)) & 0xFull;
+            perm &= ~((0xFull << (4 * k)) | (0xFull << (4 * t)));
+            perm |= (pt << (4 * k)) | (pk << (4 * t));
+        }
+#pragma unroll
+        for (int i = 0; i < NC; i++)
+            if (i < nonzero_pivots) ws[x_off + (int)((perm >> (4 * i)) & 0xFull)] = y[i];
+    }
+    __syncwarp();
 }
 
-template <int KIND>
-__device__ __forceinline__ void copy_state(Ctx& c, int cfg_from, int T_from, int cfg_to, int T_to) {
-    if (KIND != FKS_ROBOT_SE3)
-        if (c.lane < c.stride) c.ws[cfg_to + c.lane] = c.ws[cfg_from + c.lane];
-    for (int i = c.lane; i < c.L * 12; i += 32) c.ws[T_to + i] = c.ws[T_from + i];
+// actuator noise of the next `count` microsteps, one truncated-normal draw per axis in axis order
+__device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned step, unsigned micro0, int count,
+                                        unsigned long long tape_pos, unsigned long long tape_end) {
+    const Frame& fr = frame();
+    const int lane = lane_id();
+    const int D = fr.rb.D;
+    double* tn = wsd(wb) + fr.a.wl.tn;
+    const int m = lane / D, dof = lane - m * D;
+    if (m < count) {
+        double v = 0.0;
+        if (fr.a.noise_mode == FKS_NOISE_INJECTED) {
+            const unsigned long long pos = tape_pos + (unsigned long long)(m * D + dof);
+            if (pos < tape_end) v = fr.a.tape[pos];  // read-ahead past the end is checked where the draw is consumed
+        } else if (fr.a.noise_mode == FKS_NOISE_PHILOX) {
+            v = fks_philox_truncated_normal(fr.a.seed, fr.a.first_id + pid, step, micro0 + (unsigned)m, (uint32_t)dof, fr.rb.axes[dof].sigma);
+        }
+        tn[m * fr.a.wl.S + dof] = v;
+    }
     __syncwarp();
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// The kernel: a persistent grid, ONE CTA of kWarpsPerBlock warps per SM, one particle per warp.
+//
+// The nested loops of the reference (controller step -> microstep -> resolver iteration) are flattened into
+// a per-warp state machine whose every cycle has the same shape:
+//
+//     phase A   advance a kinematic state      apply_control / kinematics        (one call site)
+//     phase B   measure it                     max_motion  or  check_collision   (one call site each)
+//     phase T   bookkeeping, next operation    scalar code, noise draws
+//     phase C   collect corrections            only warps inside a contact resolution
+//     phase D   stacked-Jacobian QR solve      idem
+//
+// with CTA barriers between phases, so the warps of an SM execute the SAME building block at the same
+// time.  The profile of the free-running version (profiles/) showed 60 % of the issue slots lost to
+// instruction fetch: ~200 KB of SASS walked by 16 warps at unrelated places against a 32 KB instruction
+// cache.  In lock step the working set of a phase is a few KB.
 // ------------------------------------------------------------------------------------------------
+namespace {
+enum { OP_NONE = 0, OP_KIN = 1, OP_APPLY = 2 };
+enum { M_NONE = 0, M_MOTION = 1, M_CHECK = 2 };
+enum {
+    AF_FETCH = 0,       // no particle: fetch the next one
+    AF_INIT,            // initial kinematics done -> begin the first controller step
+    AF_EST_RU,          // motion of the whole controller step is known -> number of microsteps
+    AF_EST_DU,          // motion of one microstep is known -> start the microstep loop
+    AF_MICRO_CHECK,     // a noisy microstep was applied and checked
+    AF_EST_RAW,         // motion of the raw correction step is known -> scale and apply it
+    AF_RESOLVE_CHECK,   // a correction step was applied and checked
+    AF_FAIL_KIN,        // previous configuration restored after a failed resolve
+    AF_STOP_KIN,        // previous configuration restored after a collision with allow_contacts == false
+    AF_NOCONTACT_KIN,   // step-start configuration restored -> the particle ends
+    AF_DONE             // no particles left
+};
+}  // namespace
+
 template <int KIND>
-__global__ void __launch_bounds__(kThreadsPerBlock) simulate_kernel(const __grid_constant__ LaunchArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // ---- stage the robot description and its points into shared memory, once per CTA -------------
-    DevRobot* rb = reinterpret_cast<DevRobot*>(smem_raw);
+__global__ void __launch_bounds__(kThreadsPerBlock, 1) simulate_kernel(const __grid_constant__ LaunchArgs args) {
+    // ---- stage parameters, robot and points into shared memory, once per CTA ---------------------
     {
-        const unsigned* src = reinterpret_cast<const unsigned*>(a.robot);
-        unsigned* dst = reinterpret_cast<unsigned*>(rb);
-        for (int i = threadIdx.x; i < (int)(sizeof(DevRobot) / 4); i += blockDim.x) dst[i] = src[i];
+        Frame* f = reinterpret_cast<Frame*>(smem_raw);
+        const unsigned* src = reinterpret_cast<const unsigned*>(&args);
+        unsigned* dst = reinterpret_cast<unsigned*>(&f->a);
+        for (int i = threadIdx.x; i < (int)(sizeof(LaunchArgs) / 4); i += blockDim.x) dst[i] = src[i];
+        const unsigned* rsrc = reinterpret_cast<const unsigned*>(args.robot);
+        unsigned* rdst = reinterpret_cast<unsigned*>(&f->rb);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevRobot) / 4); i += blockDim.x) rdst[i] = rsrc[i];
+        double2* pxy = reinterpret_cast<double2*>(smem_raw + args.pts_off);
+        PointZL* pzl = reinterpret_cast<PointZL*>(pxy + args.P);
+        for (int i = threadIdx.x; i < args.P; i += blockDim.x) {
+            pxy[i] = args.pxy[i];
+            pzl[i] = args.pzl[i];
+        }
     }
-    const int P = a.robot->P;
-    size_t off = (sizeof(DevRobot) + 15) & ~(size_t)15;
-    double* spx = reinterpret_cast<double*>(smem_raw + off);
-    double* spy = spx + P;
-    double* spz = spy + P;
-    int* splink = reinterpret_cast<int*>(spz + P);
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        spx[i] = a.px[i];
-        spy[i] = a.py[i];
-        spz[i] = a.pz[i];
-        splink[i] = a.plink[i];
-    }
-    off += (size_t)P * 24 + (((size_t)P * 4 + 15) & ~(size_t)15);
     __syncthreads();
-
-    Ctx c;
-    c.rb = rb;
-    c.px = spx;
-    c.py = spy;
-    c.pz = spz;
-    c.plink = splink;
-    c.lane = threadIdx.x & 31;
-    c.L = rb->L;
-    c.J = rb->J;
-    c.D = rb->D;
-    c.P = P;
-    c.stride = a.cfg_stride;
-    c.wl = make_warp_layout(KIND, c.L, c.J, c.D, c.stride);
-    const int warp_in_block = threadIdx.x >> 5;
-    c.ws = reinterpret_cast<double*>(smem_raw + off) + (size_t)warp_in_block * c.wl.total;
-    const ScratchLayout sl = make_scratch_layout(c.D, P);
-    char* slot = a.scratch + (size_t)(blockIdx.x * kWarpsPerBlock + warp_in_block) * a.scratch_bytes_per_warp;
-    c.Js = reinterpret_cast<double*>(slot + sl.jstore);
-    c.ldj = sl.ldj;
-    c.selfcorr = reinterpret_cast<double*>(slot + sl.selfcorr);
-    c.selfwork = reinterpret_cast<double*>(slot + sl.selfwork);
-    c.keys = reinterpret_cast<int*>(slot + sl.keys);
-    c.sflag = reinterpret_cast<unsigned char*>(slot + sl.sflag);
-    c.cand_links = 0u;
-
-    const int lane = c.lane;
-    const int D = c.D;
-    const DevEnv& e = a.env;
+    const Frame& fr = frame();
+    const LaunchArgs& a = fr.a;
+    const DevRobot& rb = fr.rb;
+    const WarpLayout& wl = a.wl;
     const DevSolver& sp = a.sp;
-    double* cfg = c.ws + c.wl.cfg;
-    double* Tprev = c.ws + c.wl.Tprev;
-    double* Tcur = c.ws + c.wl.Tcur;
-    double* target = c.ws + c.wl.target;
-    double* scfg = c.ws + c.wl.scfg;
-    double* act = c.ws + c.wl.act;
-    double* ru = c.ws + c.wl.ru;
-    double* du = c.ws + c.wl.du;
-    double* tn = c.ws + c.wl.tn;
-    double* raw = c.ws + c.wl.raw;
-    double* stepv = c.ws + c.wl.stepv;
+    const int lane = lane_id();
+    const int wb = a.warps_off + (threadIdx.x >> 5) * wl.total * 8;
+    double* ws = wsd(wb);
+    const int D = rb.D, S = wl.S, stride = a.cfg_stride;
+    if (lane < FKS_NUM_STATS) reinterpret_cast<unsigned long long*>(ws + wl.stats)[lane] = 0ull;
+    __syncwarp();
+    const double target_microstep_distance = a.env.map_res * 0.125;
+    const double allowed_microstep_distance = a.env.map_res * 1.0;
 
-    Stats st;
-#pragma unroll
-    for (int i = 0; i < FKS_NUM_STATS; i++) st.v[i] = 0ull;
+    // ---- warp state (uniform across the lanes unless noted) ----------------------------------------
+    int after = AF_FETCH;
+    int op = OP_NONE, op_in = 0, op_out = 0, op_u = 0, op_tn = -1, op_derive = 0, measure = M_NONE;
+    int cur = 0, prev = 0;
+    unsigned long long pid = 0ull, tape_pos = 0ull, tape_end = 0ull;
+    unsigned step = 0u, micro = 0u, number_microsteps = 0u, resolver_iterations = 0u;
+    unsigned flags = 0u, n_micro_total = 0u, n_iter_total = 0u, n_steps = 0u;
+    bool collided = false, any_resolve_failed = false, step_collided = false, step_failed = false, step_stopped = false;
+    double scaling = 0.0;
+    double pid_integral = 0.0, pid_last_error = 0.0;  // per lane: lane i owns axis i
+    double m_result = 0.0;
+    unsigned cc = 0u;
 
-    while (true) {
-        unsigned long long pid = 0ull;
-        if (lane == 0) pid = (unsigned long long)atomicAdd(a.counter, 1u);
-        pid = __shfl_sync(FKS_FULL, pid, 0);
-        if (pid >= a.n_particles) break;
-
-        // ---- ForwardSimulateRobot (spcs:824-829): clone + ResetPosition(start) -----------------------
-        c.lflags = 0u;
-        const double* start = a.starts + (size_t)pid * c.stride;
-        const double* tgt = a.targets + (a.n_targets == a.n_particles ? (size_t)pid * c.stride : 0);
-        if (lane < c.stride) {
-            cfg[lane] = start[lane];
-            target[lane] = tgt[lane];
-        }
-        __syncwarp();
-        forward_kinematics<KIND>(c, cfg, Tcur);
-        double pid_integral = 0.0, pid_last_error = 0.0;  // lane i owns axis i (pid:98-102 zeroed)
-        unsigned long long tape_pos = 0ull, tape_end = 0ull;
-        if (a.noise_mode == FKS_NOISE_INJECTED) {
-            tape_pos = a.tape_off[pid];
-            tape_end = a.tape_off[pid + 1];
-        }
-        bool collided = false, any_resolve_failed = false;
-        unsigned flags = 0u, n_micro_total = 0u, n_iter_total = 0u, n_steps = 0u;
-
-        for (unsigned step = 0; step < sp.n_steps; step++) {
-            n_steps++;
-            if (!a.allow_contacts) {  // a colliding step is discarded as a whole: keep the step's start (spcs:904-909)
-                if (lane < c.stride) scfg[lane] = cfg[lane];
-                __syncwarp();
-            }
-            // ---- GenerateControlAction (tnuva:179-198, :384-412, :598-614) ---------------------------
-            if (KIND == FKS_ROBOT_SE3) {
-                if (lane == 0) {
-                    double cur[12], tg[12], tw[6];
-#pragma unroll
-                    for (int i = 0; i < 12; i++) {
-                        cur[i] = cfg[i];
-                        tg[i] = target[i];
-                    }
-                    twist_between(cur, tg, tw);
-#pragma unroll
-                    for (int i = 0; i < 6; i++) stepv[i] = tw[i];
-                }
-                __syncwarp();
-            }
-            if (lane < D) {
-                double err;
-                if (KIND == FKS_ROBOT_SE2) {
-                    err = target[lane] - cfg[lane];
-                    if (lane == 2) err = wrap_angle(err);
-                } else if (KIND == FKS_ROBOT_SE3) {
-                    err = stepv[lane];
-                } else {
-                    err = target[lane] - cfg[lane];
-                    if (rb->joints[rb->active_joint[lane]].type == FKS_JOINT_CONTINUOUS) err = wrap_angle(err);
-                }
-                // SimplePIDController::ComputeFeedbackTerm (pid:122-135)
-                const DevAxis& ax = rb->axes[lane];
-                const double dt = sp.interval;
-                const double timestep_error_integral = ((err * 0.5) + (pid_last_error * 0.5)) * dt;
-                const double new_error_integral = pid_integral + timestep_error_integral;
-                pid_integral = fmax(-ax.iclamp, fmin(ax.iclamp, new_error_integral));
-                const double error_derivative = (err - pid_last_error) / dt;
-                pid_last_error = err;
-                const double term = (err * ax.kp) + (pid_integral * ax.ki) + (error_derivative * ax.kd);
-                const double action = actuate(ax, term, false, 0.0, c.lflags);
-                act[lane] = action;
-                ru[lane] = action * sp.interval;  // real_control_input (spcs:1549)
-            }
-            __syncwarp();
-
-            // ---- ResolveForwardSimulation (spcs:1546-1816) -------------------------------------------
-            const double computed_step_motion = max_motion_of_input<KIND>(c, ru);
-            const double target_microstep_distance = e.map_res * 0.125;
-            const double allowed_microstep_distance = e.map_res * 1.0;
-            const double ratio = computed_step_motion / target_microstep_distance;
-            unsigned number_microsteps = (unsigned)ceil(ratio);
-            if (number_microsteps < 1u) number_microsteps = 1u;
-            if (lane < D) du[lane] = ru[lane] / (double)number_microsteps;
-            __syncwarp();
-            const double computed_microstep_motion = max_motion_of_input<KIND>(c, du);
-            if (computed_microstep_motion > allowed_microstep_distance) flags |= FKS_FLAG_WOULD_ASSERT_MICROSTEP;
-
-            bool step_collided = false, step_failed = false, step_stopped = false;
-            bool has_self = false;
-            for (unsigned micro = 0; micro < number_microsteps; micro++) {
-                n_micro_total++;
-                copy_state<KIND>(c, c.wl.cfg, c.wl.Tcur, c.wl.pcfg, c.wl.Tprev);  // previous_configuration (spcs:1597)
-                // actuator noise: one truncated-normal draw per axis, in axis order
-                if (lane < D) {
-                    double v = 0.0;
-                    if (a.noise_mode == FKS_NOISE_INJECTED) {
-                        if (tape_pos + lane < tape_end) v = a.tape[tape_pos + lane];
-                        else c.lflags |= FKS_FLAG_TAPE_EXHAUSTED;
-                    } else if (a.noise_mode == FKS_NOISE_PHILOX) {
-                        v = fks_philox_truncated_normal(a.seed, a.first_id + pid, step, micro, (uint32_t)lane, rb->axes[lane].sigma);
-                    }
-                    tn[lane] = v;
-                }
-                tape_pos += (unsigned long long)D;
-                __syncwarp();
-                apply_control<KIND>(c, cfg, cfg, Tcur, du, tn);  // spcs:1599-1601
-                bool in_collision = check_collision<KIND>(c, e, sp, Tprev, Tcur, has_self);  // spcs:1608
-                if (in_collision) step_collided = true;
-                if (in_collision && a.allow_contacts) {
-                    unsigned resolver_iterations = 0u;
-                    double scaling = sp.initial_step;
-                    while (in_collision) {
-                        const int rows = collect_corrections<KIND>(c, e, Tprev, Tcur, has_self);  // spcs:1627
-                        st.v[FKS_STAT_TOTAL_CORRECTED_POINTS] += (unsigned long long)(rows / 3);
-                        if (rows == 0) {
-                            // Eigen would return an empty vector and ApplyControlInput would assert; documented
-                            // device behaviour: zero correction step
-                            flags |= FKS_FLAG_EMPTY_JACOBIAN;
-                            if (lane < D) raw[lane] = 0.0;
-                            __syncwarp();
-                        } else {
-                            colpiv_qr_solve(c, c.Js, c.ldj, rows, D, raw);  // spcs:1629,1990-1998
+#ifdef FKS_PHASE_TIMERS
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t0 = clock64(), t1;
+#define FKS_TICK(i) { t1 = clock64(); tacc[i] += t1 - t0; t0 = t1; }
+#else
+#define FKS_TICK(i)
+#endif
+    for (;;) {
+        // =========================== phase A: advance a kinematic state ===============================
+        if (op == OP_KIN) kinematics<KIND>(wb, op_out, op_derive);
+        else if (op == OP_APPLY) apply_control<KIND>(wb, op_in, op_out, op_u, op_tn, op_derive);
+        FKS_TICK(0)
+        __syncthreads();
+        FKS_TICK(1)
+        // =========================== phase B: measure =================================================
+        if (measure == M_MOTION) m_result = max_motion(wb, op_in, op_out);  // spcs:1492-1527
+        else if (measure == M_CHECK) cc = check_collision<KIND>(wb, prev, cur);  // spcs:1418-1436
+        FKS_TICK(2)
+        __syncthreads();
+        FKS_TICK(3)
+        // =========================== phase T: transitions =============================================
+        bool want_solve = false;
+        op = OP_NONE;
+        measure = M_NONE;
+        // Each pass of this loop handles one event; it ends as soon as the next operation is known.
+        // `ev` is a small program counter: 0 = dispatch on `after`, 1 = begin controller step,
+        // 2 = begin microstep, 3 = end of controller step, 4 = end of particle.
+        int ev = 0;
+        while (op == OP_NONE && !want_solve && after != AF_DONE) {
+            if (ev == 0) {
+                switch (after) {
+                    case AF_FETCH: {
+                        if (lane == 0) pid = (unsigned long long)atomicAdd(a.counter, 1u);
+                        pid = __shfl_sync(FKS_FULL, pid, 0);
+                        if (pid >= a.n_particles) {
+                            after = AF_DONE;
+                            break;
                         }
-                        const double est = max_motion_of_input<KIND>(c, raw);  // spcs:1630
-                        const double step_fraction = fmax(est / allowed_microstep_distance, 1.0);  // spcs:1681
-                        if (lane < D) stepv[lane] = (raw[lane] / step_fraction) * fabs(scaling);  // spcs:1682
+                        // ForwardSimulateRobot (spcs:824-829): clone + ResetPosition(start)
+                        cur = 0;
+                        const double* start = a.starts + (size_t)pid * stride;
+                        const double* tgt = a.targets + (a.n_targets == a.n_particles ? (size_t)pid * stride : 0);
+                        if (lane < stride) {
+                            ws[wl.cfg + lane] = start[lane];
+                            ws[wl.target + lane] = tgt[lane];
+                        }
+                        if (lane == 0) *reinterpret_cast<unsigned*>(ws + wl.flags) = 0u;
                         __syncwarp();
-                        if (KIND == FKS_ROBOT_SE3) {
-                            // apply_control<SE3> uses stepv as its own temporary: hand the step over in `act`
-                            // (the controller action of this step is no longer needed)
-                            if (lane < D) act[lane] = stepv[lane];
-                            __syncwarp();
-                            apply_control<KIND>(c, cfg, cfg, Tcur, act, nullptr);  // spcs:1689
-                        } else {
-                            apply_control<KIND>(c, cfg, cfg, Tcur, stepv, nullptr);
+                        pid_integral = 0.0;  // pid:98-102 zeroed
+                        pid_last_error = 0.0;
+                        tape_pos = tape_end = 0ull;
+                        if (a.noise_mode == FKS_NOISE_INJECTED) {
+                            tape_pos = a.tape_off[pid];
+                            tape_end = a.tape_off[pid + 1];
                         }
-                        in_collision = check_collision<KIND>(c, e, sp, Tprev, Tcur, has_self);  // spcs:1694-1698
+                        collided = any_resolve_failed = false;
+                        flags = n_micro_total = n_iter_total = n_steps = 0u;
+                        step = 0u;
+                        op = OP_KIN;
+                        op_out = cur;
+                        op_derive = 1;
+                        after = AF_INIT;
+                        break;
+                    }
+                    case AF_INIT:
+                        ev = 1;
+                        break;
+                    case AF_EST_RU: {  // spcs:1559-1568
+                        const double ratio = m_result / target_microstep_distance;
+                        number_microsteps = (unsigned)ceil(ratio);
+                        if (number_microsteps < 1u) number_microsteps = 1u;
+                        if (lane < D) ws[wl.du + lane] = ws[wl.ru + lane] / (double)number_microsteps;
+                        __syncwarp();
+                        op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.du; op_tn = -1; op_derive = 0;
+                        measure = M_MOTION;
+                        after = AF_EST_DU;
+                        break;
+                    }
+                    case AF_EST_DU:  // spcs:1569-1575
+                        if (m_result > allowed_microstep_distance) flags |= FKS_FLAG_WOULD_ASSERT_MICROSTEP;
+                        step_collided = step_failed = step_stopped = false;
+                        micro = 0u;
+                        ev = 2;
+                        break;
+                    case AF_MICRO_CHECK: {  // spcs:1608-1625
+                        const bool in_collision = (cc & 1u) != 0u;
+                        if (in_collision) step_collided = true;
+                        if (in_collision && a.allow_contacts) {
+                            resolver_iterations = 0u;
+                            scaling = sp.initial_step;
+                            want_solve = true;
+                        } else if (in_collision) {  // spcs:1769-1786
+                            if (lane == 0) add_stat(wb, FKS_STAT_SUCCESSFUL_RESOLVES, 1ull);
+                            cur = prev;
+                            step_stopped = true;
+                            op = OP_KIN; op_out = cur; op_derive = 1;
+                            after = AF_STOP_KIN;
+                        } else {
+                            micro++;
+                            ev = (micro < number_microsteps) ? 2 : 3;
+                        }
+                        break;
+                    }
+                    case AF_EST_RAW: {  // spcs:1681-1689
+                        const double step_fraction = fmax(m_result / allowed_microstep_distance, 1.0);
+                        if (lane < D) ws[wl.stepv + lane] = (ws[wl.raw + lane] / step_fraction) * fabs(scaling);
+                        __syncwarp();
+                        op = OP_APPLY; op_in = cur; op_out = cur; op_u = wl.stepv; op_tn = -1; op_derive = 1;
+                        measure = M_CHECK;
+                        after = AF_RESOLVE_CHECK;
+                        break;
+                    }
+                    case AF_RESOLVE_CHECK: {  // spcs:1694-1761
+                        const bool in_collision = (cc & 1u) != 0u;
                         resolver_iterations++;
                         n_iter_total++;
                         if (resolver_iterations > sp.max_iters) {  // spcs:1705-1746
-                            st.v[FKS_STAT_UNSUCCESSFUL_RESOLVES]++;
-                            if (has_self) st.v[FKS_STAT_UNSUCCESSFUL_SELF_COLLISION_RESOLVES]++;
-                            else st.v[FKS_STAT_UNSUCCESSFUL_ENV_COLLISION_RESOLVES]++;
-                            copy_state<KIND>(c, c.wl.pcfg, c.wl.Tprev, c.wl.cfg, c.wl.Tcur);  // return previous_configuration
+                            if (lane == 0) {
+                                add_stat(wb, FKS_STAT_UNSUCCESSFUL_RESOLVES, 1ull);
+                                add_stat(wb, (cc & 2u) ? FKS_STAT_UNSUCCESSFUL_SELF_COLLISION_RESOLVES : FKS_STAT_UNSUCCESSFUL_ENV_COLLISION_RESOLVES, 1ull);
+                            }
+                            cur = prev;  // return previous_configuration
                             step_collided = true;
                             step_failed = true;
+                            op = OP_KIN; op_out = cur; op_derive = 1;
+                            after = AF_FAIL_KIN;
                             break;
                         }
                         if ((resolver_iterations % sp.decay_iters) == 0u) {  // spcs:1747-1761
@@ -1288,98 +1676,230 @@ __global__ void __launch_bounds__(kThreadsPerBlock) simulate_kernel(const __grid
                                 scaling = -sp.min_scaling;
                             }
                         }
-                    }
-                    if (step_failed) break;
-                } else if (in_collision && !a.allow_contacts) {  // spcs:1769-1786
-                    st.v[FKS_STAT_SUCCESSFUL_RESOLVES]++;
-                    copy_state<KIND>(c, c.wl.pcfg, c.wl.Tprev, c.wl.cfg, c.wl.Tcur);
-                    step_stopped = true;
-                    break;
-                }
-            }
-            if (!step_failed && !step_stopped) {  // spcs:1802-1814
-                st.v[FKS_STAT_SUCCESSFUL_RESOLVES]++;
-                if (step_collided) st.v[FKS_STAT_COLLISION_RESOLVES]++;
-                else st.v[FKS_STAT_FREE_RESOLVES]++;
-            }
-
-            // ---- back in ForwardSimulateMutableRobot (spcs:873-909) ------------------------------------
-            if (a.allow_contacts || !step_collided) {
-                if (step_collided) collided = true;
-                if (step_failed) {
-                    flags |= FKS_FLAG_RESOLVE_FAILED;
-                    if (sp.failed_ends_motion) {
-                        flags |= FKS_FLAG_ENDED_BY_FAILURE;
+                        if (in_collision) {
+                            want_solve = true;
+                        } else {
+                            micro++;
+                            ev = (micro < number_microsteps) ? 2 : 3;
+                        }
                         break;
                     }
-                    any_resolve_failed = true;
-                } else if (any_resolve_failed) {
-                    st.v[FKS_STAT_RECOVERED_UNSUCCESSFUL_RESOLVES]++;
+                    case AF_FAIL_KIN:
+                    case AF_STOP_KIN:
+                        ev = 3;
+                        break;
+                    case AF_NOCONTACT_KIN:
+                        ev = 4;
+                        break;
+                    default:
+                        break;
                 }
-                if (sp.shortcut_distance > 0.0) {  // ComputeConfigurationDistanceTo (spcs:898); a distance is never < 0
-                    double dist;
-                    if (KIND == FKS_ROBOT_SE2) {
-                        const double dx = fabs(target[0] - cfg[0]), dy = fabs(target[1] - cfg[1]);
-                        const double dr = fabs(wrap_angle(target[2] - cfg[2]));
-                        dist = (sqrt(dx * dx + dy * dy) * rb->pos_w) + (dr * rb->rot_w);
-                    } else if (KIND == FKS_ROBOT_SE3) {
-                        double cur[12], tg[12], ci[12], Dm[12];
+            } else if (ev == 1) {
+                // ---- begin controller step: GenerateControlAction (tnuva:179-198, :384-412, :598-614) --------
+                ev = 0;
+                n_steps++;
+                double* cfg = ws + wl.cfg + cur * S;
+                if (!a.allow_contacts) {  // a colliding step is discarded as a whole: keep the step's start (spcs:904-909)
+                    if (lane < stride) ws[wl.scfg + lane] = cfg[lane];
+                    __syncwarp();
+                }
+                if (KIND == FKS_ROBOT_SE3) {
+                    if (lane == 0) {
+                        double c12[12], tg[12], tw[6];
 #pragma unroll
                         for (int i = 0; i < 12; i++) {
-                            cur[i] = cfg[i];
-                            tg[i] = target[i];
+                            c12[i] = cfg[i];
+                            tg[i] = ws[wl.target + i];
                         }
-                        const double dx = tg[3] - cur[3], dy = tg[7] - cur[7], dz = tg[11] - cur[11];
-                        iso_inverse(cur, ci);
-                        iso_mul(ci, tg, Dm);
-                        const double cc = fmin(fmax(0.5 * (Dm[0] + Dm[5] + Dm[10] - 1.0), -1.0), 1.0);
-                        dist = (sqrt(dx * dx + dy * dy + dz * dz) * rb->pos_w) + (acos(cc) * rb->rot_w);
+                        twist_between(c12, tg, tw);
+#pragma unroll
+                        for (int i = 0; i < 6; i++) ws[wl.stepv + i] = tw[i];
+                    }
+                    __syncwarp();
+                }
+                if (lane < D) {
+                    double err;
+                    if (KIND == FKS_ROBOT_SE2) {
+                        err = ws[wl.target + lane] - cfg[lane];
+                        if (lane == 2) err = wrap_angle(err);
+                    } else if (KIND == FKS_ROBOT_SE3) {
+                        err = ws[wl.stepv + lane];
                     } else {
-                        double s = 0.0;
-                        for (int j = 0; j < c.J; j++) {
-                            const DevJoint& jd = rb->joints[j];
-                            if (jd.active < 0) continue;
-                            double dj = target[jd.active] - cfg[jd.active];
-                            if (jd.type == FKS_JOINT_CONTINUOUS) dj = wrap_angle(dj);
-                            const double wd = dj * jd.weight;
-                            s += wd * wd;
+                        err = ws[wl.target + lane] - cfg[lane];
+                        if (rb.joints[rb.active_joint[lane]].type == FKS_JOINT_CONTINUOUS) err = wrap_angle(err);
+                    }
+                    // SimplePIDController::ComputeFeedbackTerm (pid:122-135)
+                    const DevAxis& ax = rb.axes[lane];
+                    const double dt = sp.interval;
+                    const double timestep_error_integral = ((err * 0.5) + (pid_last_error * 0.5)) * dt;
+                    const double new_error_integral = pid_integral + timestep_error_integral;
+                    pid_integral = fmax(-ax.iclamp, fmin(ax.iclamp, new_error_integral));
+                    const double error_derivative = (err - pid_last_error) / dt;
+                    pid_last_error = err;
+                    const double term = (err * ax.kp) + (pid_integral * ax.ki) + (error_derivative * ax.kd);
+                    const double action = actuate(wb, ax, term, false, 0.0);
+                    ws[wl.act + lane] = action;
+                    ws[wl.ru + lane] = action * sp.interval;  // real_control_input (spcs:1549)
+                }
+                __syncwarp();
+                // ResolveForwardSimulation (spcs:1546-1816) starts with the motion estimate of the whole step
+                op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.ru; op_tn = -1; op_derive = 0;
+                measure = M_MOTION;
+                after = AF_EST_RU;
+            } else if (ev == 2) {
+                // ---- begin microstep (spcs:1590-1608) ---------------------------------------------------------
+                ev = 0;
+                n_micro_total++;
+                const int nb = wl.noise_batch;
+                const int slot = (int)(micro % (unsigned)nb);
+                if (slot == 0) {
+                    const unsigned left = number_microsteps - micro;
+                    fill_noise(wb, pid, step, micro, left < (unsigned)nb ? (int)left : nb, tape_pos, tape_end);
+                }
+                if (a.noise_mode == FKS_NOISE_INJECTED && tape_pos + (unsigned long long)D > tape_end) flags |= FKS_FLAG_TAPE_EXHAUSTED;
+                tape_pos += (unsigned long long)D;
+                // previous_configuration (spcs:1597) is the old current state; the new one is built in the other buffer
+                prev = cur;
+                cur ^= 1;
+                op = OP_APPLY; op_in = prev; op_out = cur; op_u = wl.du; op_tn = wl.tn + slot * S; op_derive = 1;  // spcs:1599-1601
+                measure = M_CHECK;
+                after = AF_MICRO_CHECK;
+            } else if (ev == 3) {
+                // ---- end of controller step (spcs:1797-1815, then back in ForwardSimulateMutableRobot :873-909) ----
+                ev = 0;
+                if (!step_failed && !step_stopped && lane == 0) {
+                    add_stat(wb, FKS_STAT_SUCCESSFUL_RESOLVES, 1ull);
+                    add_stat(wb, step_collided ? FKS_STAT_COLLISION_RESOLVES : FKS_STAT_FREE_RESOLVES, 1ull);
+                }
+                bool ends = false;
+                if (a.allow_contacts || !step_collided) {
+                    if (step_collided) collided = true;
+                    if (step_failed) {
+                        flags |= FKS_FLAG_RESOLVE_FAILED;
+                        if (sp.failed_ends_motion) {
+                            flags |= FKS_FLAG_ENDED_BY_FAILURE;
+                            ends = true;
                         }
-                        dist = sqrt(s);
+                        any_resolve_failed = true;
+                    } else if (any_resolve_failed) {
+                        if (lane == 0) add_stat(wb, FKS_STAT_RECOVERED_UNSUCCESSFUL_RESOLVES, 1ull);
                     }
-                    if (dist < sp.shortcut_distance) {
-                        flags |= FKS_FLAG_ENDED_BY_SHORTCUT;
-                        break;
+                    if (!ends && sp.shortcut_distance > 0.0) {  // ComputeConfigurationDistanceTo (spcs:898); never < 0
+                        const double* c2 = ws + wl.cfg + cur * S;
+                        const double* target = ws + wl.target;
+                        double dist;
+                        if (KIND == FKS_ROBOT_SE2) {
+                            const double dx = fabs(target[0] - c2[0]), dy = fabs(target[1] - c2[1]);
+                            const double dr = fabs(wrap_angle(target[2] - c2[2]));
+                            dist = (sqrt(dx * dx + dy * dy) * rb.pos_w) + (dr * rb.rot_w);
+                        } else if (KIND == FKS_ROBOT_SE3) {
+                            double c12[12], tg[12], ci[12], Dm[12];
+#pragma unroll
+                            for (int i = 0; i < 12; i++) {
+                                c12[i] = c2[i];
+                                tg[i] = target[i];
+                            }
+                            const double dx = tg[3] - c12[3], dy = tg[7] - c12[7], dz = tg[11] - c12[11];
+                            iso_inverse(c12, ci);
+                            iso_mul(ci, tg, Dm);
+                            const double cs = fmin(fmax(0.5 * (Dm[0] + Dm[5] + Dm[10] - 1.0), -1.0), 1.0);
+                            dist = (sqrt(dx * dx + dy * dy + dz * dz) * rb.pos_w) + (acos(cs) * rb.rot_w);
+                        } else {
+                            double sacc = 0.0;
+                            for (int j = 0; j < rb.J; j++) {
+                                const DevJoint& jd = rb.joints[j];
+                                if (jd.active < 0) continue;
+                                double dj = target[jd.active] - c2[jd.active];
+                                if (jd.type == FKS_JOINT_CONTINUOUS) dj = wrap_angle(dj);
+                                const double wd = dj * jd.weight;
+                                sacc += wd * wd;
+                            }
+                            dist = sqrt(sacc);
+                        }
+                        if (dist < sp.shortcut_distance) {
+                            flags |= FKS_FLAG_ENDED_BY_SHORTCUT;
+                            ends = true;
+                        }
                     }
+                    step++;
+                    if (!ends && step < sp.n_steps) ev = 1;
+                    else ev = 4;
+                } else {
+                    // robot->SetPosition(resolved_configuration) is skipped: the particle stays where the step began
+                    if (lane < stride) ws[wl.cfg + cur * S + lane] = ws[wl.scfg + lane];
+                    __syncwarp();
+                    flags |= FKS_FLAG_ENDED_BY_NOCONTACT;
+                    op = OP_KIN; op_out = cur; op_derive = 1;
+                    after = AF_NOCONTACT_KIN;
                 }
             } else {
-                // robot->SetPosition(resolved_configuration) is skipped: the particle stays where the step began
-                if (lane < c.stride) cfg[lane] = scfg[lane];
+                // ---- end of particle: result record = cfg_stride doubles + fks_result_tail -------------------
+                ev = 0;
+                if (collided) flags |= FKS_FLAG_DID_CONTACT;
                 __syncwarp();
-                forward_kinematics<KIND>(c, cfg, Tcur);
-                flags |= FKS_FLAG_ENDED_BY_NOCONTACT;
-                break;
+                flags |= *reinterpret_cast<const unsigned*>(ws + wl.flags);
+                char* rec = a.results + (size_t)pid * a.rec_stride;
+                if (lane < stride) reinterpret_cast<double*>(rec)[lane] = ws[wl.cfg + cur * S + lane];
+                if (lane == 0) {
+                    unsigned* tail = reinterpret_cast<unsigned*>(rec + (size_t)stride * 8);
+                    tail[0] = flags;
+                    tail[1] = n_micro_total;
+                    tail[2] = n_iter_total;
+                    tail[3] = n_steps;
+                    add_stat(wb, FKS_STAT_TOTAL_MICROSTEPS, n_micro_total);
+                    add_stat(wb, FKS_STAT_TOTAL_RESOLVER_ITERATIONS, n_iter_total);
+                }
+                __syncwarp();
+                after = AF_FETCH;
             }
         }
-        if (collided) flags |= FKS_FLAG_DID_CONTACT;
-        flags |= __reduce_or_sync(FKS_FULL, c.lflags);
-        // ---- result record: cfg_stride doubles + fks_result_tail --------------------------------------
-        char* rec = a.results + (size_t)pid * a.rec_stride;
-        if (lane < c.stride) reinterpret_cast<double*>(rec)[lane] = cfg[lane];
-        if (lane == 0) {
-            unsigned* tail = reinterpret_cast<unsigned*>(rec + (size_t)c.stride * 8);  // fks_result_tail
-            tail[0] = flags;
-            tail[1] = n_micro_total;
-            tail[2] = n_iter_total;
-            tail[3] = n_steps;
+        FKS_TICK(4)
+        __syncthreads();
+        FKS_TICK(5)
+        // =========================== phase C: collect corrections (spcs:1627) ==========================
+        int rows = 0;
+        if (want_solve) {
+            rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
+            if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
         }
-        st.v[FKS_STAT_TOTAL_MICROSTEPS] += n_micro_total;
-        st.v[FKS_STAT_TOTAL_RESOLVER_ITERATIONS] += n_iter_total;
-        __syncwarp();
+        FKS_TICK(6)
+        __syncthreads();
+        FKS_TICK(7)
+        // =========================== phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
+        if (want_solve) {
+            if (rows == 0) {
+                // Eigen would return an empty vector and ApplyControlInput would assert; documented device
+                // behaviour: zero correction step
+                flags |= FKS_FLAG_EMPTY_JACOBIAN;
+                if (lane < D) ws[wl.raw + lane] = 0.0;
+                __syncwarp();
+            } else if (rows <= 64 && KIND == FKS_ROBOT_SE2) {
+                colpiv_qr_solve_reg<3>(wb, rows, wl.raw);
+            } else if (rows <= 64 && KIND == FKS_ROBOT_SE3) {
+                colpiv_qr_solve_reg<6>(wb, rows, wl.raw);
+            } else if (rows <= 64 && KIND == FKS_ROBOT_LINKED && D == 7) {
+                colpiv_qr_solve_reg<7>(wb, rows, wl.raw);
+            } else {
+                colpiv_qr_solve(wb, rows, D, wl.raw);
+            }
+            // motion estimate of the raw correction (spcs:1630) is the next operation
+            op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.raw; op_tn = -1; op_derive = 0;
+            measure = M_MOTION;
+            after = AF_EST_RAW;
+        }
+        FKS_TICK(8)
+        const bool all_done = __syncthreads_and(after == AF_DONE);
+        FKS_TICK(9)
+        if (all_done) break;
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < FKS_NUM_STATS; i++)
-            if (st.v[i]) atomicAdd(a.stats + i, st.v[i]);
+#ifdef FKS_PHASE_TIMERS
+    if (lane == 0)
+        for (int i = 0; i < 10; i++) atomicAdd(a.stats + 16 + i, (unsigned long long)tacc[i]);
+#endif
+    __syncwarp();
+    if (lane < FKS_NUM_STATS) {
+        const unsigned long long v = reinterpret_cast<const unsigned long long*>(ws + wl.stats)[lane];
+        if (v) atomicAdd(a.stats + lane, v);
     }
 }
 
@@ -1416,11 +1936,16 @@ __global__ void gather_kernel(const float* __restrict__ data, unsigned long long
 // ------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------------
-size_t simulate_dyn_smem(int kind, int L, int J, int D, int P, int stride) {
-    const WarpLayout wl = make_warp_layout(kind, L, J, D, stride);
-    size_t off = (sizeof(DevRobot) + 15) & ~(size_t)15;
-    off += (size_t)P * 24 + (((size_t)P * 4 + 15) & ~(size_t)15);
-    off += (size_t)kWarpsPerBlock * wl.total * 8;
+size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block) {
+    args->wl = make_warp_layout(L, J, D, stride);
+    args->sl = make_scratch_layout(D, P);
+    args->P = P;
+    args->warps_per_block = warps_per_block;
+    size_t off = (sizeof(Frame) + 15) & ~(size_t)15;
+    args->pts_off = (int)off;
+    off += (size_t)P * (sizeof(double2) + sizeof(PointZL));
+    args->warps_off = (int)off;
+    off += (size_t)warps_per_block * args->wl.total * 8;
     return off;
 }
 
@@ -1433,7 +1958,7 @@ static const void* kernel_ptr(int kind) {
     return nullptr;
 }
 
-int simulate_kernel_info(int kind, size_t dyn_smem, KernelInfo* out) {
+int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelInfo* out) {
     const void* fn = kernel_ptr(kind);
     if (!fn) return (int)cudaErrorInvalidValue;
     cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
@@ -1442,7 +1967,7 @@ int simulate_kernel_info(int kind, size_t dyn_smem, KernelInfo* out) {
     err = cudaFuncGetAttributes(&fa, fn);
     if (err != cudaSuccess) return (int)err;
     int nb = 0;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, kThreadsPerBlock, dyn_smem);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 32 * warps_per_block, dyn_smem);
     if (err != cudaSuccess) return (int)err;
     out->regs = fa.numRegs;
     out->static_smem = (int)fa.sharedSizeBytes;
@@ -1454,11 +1979,12 @@ int simulate_kernel_info(int kind, size_t dyn_smem, KernelInfo* out) {
 
 int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
                     const void* l2_window_base, size_t l2_window_bytes) {
+    const int block_threads = 32 * args.warps_per_block;
     const void* fn = kernel_ptr(kind);
     if (!fn) return (int)cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreadsPerBlock);
+    cfg.blockDim = dim3((unsigned)block_threads);
     cfg.dynamicSmemBytes = dyn_smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];

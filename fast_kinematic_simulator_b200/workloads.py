@@ -245,6 +245,17 @@ def arm_table(n_particles=65536, seed=1003):
                     "target drives the last link into the table")
 
 
+def arm_free(n_particles=256, seed=1003):
+    """Raised arm moving through free space (no contact anywhere): FK, env check, self-collision broad phase."""
+    res = 0.04
+    rng = np.random.Generator(np.random.MT19937(seed))
+    start = np.array([0.0, 0.5, 0.0, 0.9, 0.0, 0.5, 0.0])
+    target = np.array([0.4, 0.6, 0.3, 1.0, 0.2, 0.6, 0.5])
+    starts = start[None, :] + rng.normal(0.0, 0.02, (n_particles, 7))
+    return Workload("arm_free", capi.ROBOT_LINKED, arm_room_obstacles(), res, arm_robot(), starts, target.reshape(1, 7),
+                    "7-DoF arm moving through free space")
+
+
 def arm_selfcollision(n_particles=256, seed=1003):
     """A folded arm whose distal links sweep through the proximal ones: exercises the self-collision path."""
     res = 0.04
@@ -278,6 +289,7 @@ WORKLOADS = {
     "se3_highres": se3_highres,
     "arm_selfcollision": arm_selfcollision,
     "arm_elbow": arm_elbow,
+    "arm_free": arm_free,
 }
 
 

@@ -666,6 +666,7 @@ struct Robot {
 // ------------------------------------------------------------------------------------------------
 // debug histogram of log10(pivot_norm^2 / rank_cut) for pivots near the rank decision (oracle_debug_rank_hist)
 long long g_rank_hist[42];
+long long g_rows_hist[16];  // debug: histogram of stacked-Jacobian row counts, bucket = min(15, rows / 24)
 void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32_t* sens) {
     const int size = std::min(rows, cols);
     double hcoeff[kMaxDof];
@@ -1166,6 +1167,8 @@ struct Sim {
                     collect_corrections(previous, robot, self, &Jrows, &corr, flags, sens);
                     const int rows = (int)corr.size();
                     st[FKS_STAT_TOTAL_CORRECTED_POINTS] += (uint64_t)(rows / 3);
+#pragma omp atomic
+                    g_rows_hist[std::min(15, rows / 24)]++;
                     double raw[kMaxDof];
                     for (int i = 0; i < D; i++) raw[i] = 0.0;
                     if (rows == 0) {
@@ -1404,6 +1407,12 @@ void oracle_copy_sensitivity(const oracle_sim* o, uint32_t* out) {
 void oracle_get_statistics(const oracle_sim* o, uint64_t* out) { std::memcpy(out, o->s.stats, sizeof(o->s.stats)); }
 void oracle_reset_statistics(oracle_sim* o) { std::memset(o->s.stats, 0, sizeof(o->s.stats)); }
 
+void oracle_debug_rows_hist(long long* out16, int reset) {
+    for (int i = 0; i < 16; i++) {
+        out16[i] = g_rows_hist[i];
+        if (reset) g_rows_hist[i] = 0;
+    }
+}
 void oracle_debug_rank_hist(long long* out42, int reset) {
     for (int i = 0; i < 42; i++) {
         out42[i] = g_rank_hist[i];

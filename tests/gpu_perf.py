@@ -33,6 +33,15 @@ def run(name, n, free=False, reps=3):
     print("%-20s n=%7d free=%d  %8.2f ms  micro %9d iters %8d pts %9d  -> %.3e microsteps/s  (failed %d, contact %d)" % (
         name, n, free, best, s["total_microsteps"], s["total_resolver_iterations"], s["total_corrected_points"],
         s["total_microsteps"] / best * 1e3, int(((rec["flags"] & 2) != 0).sum()), int((rec["flags"] & 1).sum())), flush=True)
+    import ctypes as C
+    if hasattr(capi.lib, "fks_debug_phase_cycles"):
+        ph = (C.c_uint64 * 10)()
+        capi.lib.fks_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
+        capi.lib.fks_debug_phase_cycles(sim._h, ph)
+        tot = float(sum(ph)) or 1.0
+        if sum(ph):
+            names = ["A apply", "bar1", "B measure", "bar2", "T trans", "bar3", "C collect", "bar4", "D solve", "bar5"]
+            print("    phases: " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(names, ph)), flush=True)
     sim.close()
 
 
@@ -40,7 +49,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run(sys.argv[1], int(sys.argv[2]), len(sys.argv) > 3 and sys.argv[3] == "free")
     else:
-        run("arm_table", 65536, True)
+        run("arm_free", 65536)
         run("arm_table", 2368, False)
         run("arm_table", 16384, False)
         run("arm_table", 65536, False)

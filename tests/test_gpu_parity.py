@@ -49,11 +49,21 @@ def test_arm_table_parity():
 
 def test_arm_free_motion_parity():
     """No contact: a target above the table.  Every particle must match (nothing is near a threshold)."""
-    w = W.arm_table(256)
-    w.targets = (W.ARM_START + np.array([0.3, -0.3, 0.2, -0.3, 0.1, -0.2, 0.4])).reshape(1, 7)
+    w = W.arm_free(256)
     rep, gpu, ref, sens = parity.run_parity(w, 256)
     _assert_parity(rep, sens, 0.9)
     assert not gpu.did_contact.any()
+    assert rep["n_match"] == 256
+
+
+def test_arm_elbow_parity():
+    """Contact on the proximal links: structurally-zero Jacobian columns, spherical-shoulder rank loss (rank 2 of 3),
+    failing resolves.  Every particle must reproduce exactly."""
+    w = W.arm_elbow(256)
+    rep, gpu, ref, sens = parity.run_parity(w, 256)
+    _assert_parity(rep, sens)
+    assert rep["n_match"] == 256 and gpu.resolve_failed.any()
+    assert rep["gpu_stats"] == rep["oracle_stats"]
 
 
 def test_arm_selfcollision_parity():
@@ -115,8 +125,7 @@ def test_statistics_accumulate_and_reset():
 
 def test_philox_matches_oracle_statistically():
     """Philox mode: device libm differs from glibc in the last ulp, so compare with a tolerance on a free-space run."""
-    w = W.arm_table(64)
-    w.targets = (W.ARM_START + np.array([0.3, -0.3, 0.2, -0.3, 0.1, -0.2, 0.4])).reshape(1, 7)
+    w = W.arm_free(64)
     sim = w.make_simulator()
     gpu = sim.forward_simulate_robots(w.starts, w.targets, True, capi.NOISE_PHILOX)
     orc = parity.make_oracle(w)
