@@ -78,7 +78,6 @@ struct fks_env {
     DevEnv dev;
     float* d_sdf;
     unsigned long long* d_keys;
-    uint2* d_vals;
     double* d_entries;
     size_t sdf_bytes;
     size_t l2_window_bytes;
@@ -179,8 +178,7 @@ int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
     const size_t ncell_n = (size_t)desc->n_normal_cells;
     size_t cap = 2;
     while (cap < 2 * ncell_n) cap <<= 1;
-    std::vector<unsigned long long> keys(cap, 0ull);
-    std::vector<uint2> vals(cap, make_uint2(0u, 0u));
+    std::vector<unsigned long long> keys(2 * cap, 0ull);  // {key, start | count << 32} pairs
     const size_t nentries = ncell_n ? (size_t)desc->normal_cell_start[ncell_n] : 0;
     for (size_t i = 0; i < ncell_n; i++) {
         const int64_t li = desc->normal_cell_index[i];
@@ -189,15 +187,16 @@ int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
             return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: surface-normal cell out of range");
         }
         size_t h = (size_t)(normal_hash((unsigned long long)li) & (cap - 1));
-        while (keys[h] != 0ull) {
-            if (keys[h] == (unsigned long long)li + 1ull) {
+        while (keys[2 * h] != 0ull) {
+            if (keys[2 * h] == (unsigned long long)li + 1ull) {
                 fks_env_destroy(env);
                 return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_create: duplicate surface-normal cell");
             }
             h = (h + 1) & (cap - 1);
         }
-        keys[h] = (unsigned long long)li + 1ull;
-        vals[h] = make_uint2(desc->normal_cell_start[i], desc->normal_cell_start[i + 1] - desc->normal_cell_start[i]);
+        keys[2 * h] = (unsigned long long)li + 1ull;
+        keys[2 * h + 1] = (unsigned long long)desc->normal_cell_start[i] |
+                          ((unsigned long long)(desc->normal_cell_start[i + 1] - desc->normal_cell_start[i]) << 32);
     }
     std::vector<double> entries(std::max<size_t>(nentries, 1) * 6, 0.0);
     for (size_t en = 0; en < nentries; en++) {
@@ -209,8 +208,7 @@ int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
         entries[6 * en + 4] = src[5];
         entries[6 * en + 5] = src[6];
     }
-    rc = upload(&env->d_keys, keys.data(), cap);
-    if (rc == FKS_OK) rc = upload(&env->d_vals, vals.data(), cap);
+    rc = upload(&env->d_keys, keys.data(), 2 * cap);
     if (rc == FKS_OK) rc = upload(&env->d_entries, entries.data(), entries.size());
     if (rc != FKS_OK) { fks_env_destroy(env); return rc; }
 
@@ -227,7 +225,6 @@ int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
     d.oob = desc->oob_value;
     d.sdf = env->d_sdf;
     d.nh_keys = env->d_keys;
-    d.nh_vals = env->d_vals;
     d.nh_mask = (unsigned long long)(cap - 1);
     d.normal_entries = env->d_entries;
 
@@ -248,7 +245,6 @@ void fks_env_destroy(fks_env* env) {
     DeviceGuard guard(env->device);
     cudaFree(env->d_sdf);
     cudaFree(env->d_keys);
-    cudaFree(env->d_vals);
     cudaFree(env->d_entries);
     delete env;
 }
@@ -658,11 +654,11 @@ int fks_reset_statistics(fks_sim* s) {
 uint64_t fks_sim_launch_count(const fks_sim* s) { return s ? s->launches : 0; }
 
 // developer aid (not in the public header): per-phase clock totals of builds made with -DFKS_PHASE_TIMERS
-int fks_debug_phase_cycles(fks_sim* s, uint64_t* out10) {
-    if (!s || !out10) return FKS_ERR_INVALID_ARGUMENT;
+int fks_debug_phase_cycles(fks_sim* s, uint64_t* out16) {
+    if (!s || !out16) return FKS_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(s->device);
     FKS_CUDA(cudaDeviceSynchronize());
-    FKS_CUDA(cudaMemcpy(out10, s->d_stats + 16, 10 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    FKS_CUDA(cudaMemcpy(out16, s->d_stats + 16, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return FKS_OK;
 }
 

@@ -65,9 +65,8 @@ struct DevEnv {
     int nx, ny, nz;
     float oob;
     const float* sdf;
-    // normal hash: keys hold (linear cell index + 1), 0 = empty slot
+    // normal hash: 16-byte entries {linear cell index + 1 (0 = empty slot), first entry | entry count << 32}
     const unsigned long long* nh_keys;
-    const uint2* nh_vals;
     unsigned long long nh_mask;
     const double* normal_entries;  // 6 doubles: entry direction xyz, normal xyz
 };
@@ -103,6 +102,7 @@ struct WarpLayout {
     int target, scfg, act, ru, du, raw, stepv;  // S each
     int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
     int qr;       // 4 * S
+    int cand;     // 64: candidate records of collect_corrections
     int stats;    // FKS_NUM_STATS u64 counters of this warp
     int flags;    // 1 (u32 FKS_FLAG_* bits raised by any lane)
     int total;
@@ -134,6 +134,7 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.stepv = o; o += S;
     w.tn = o; o += w.noise_batch * S;
     w.qr = o; o += 4 * S;
+    w.cand = o; o += 64;
     w.stats = o; o += FKS_NUM_STATS;
     w.flags = o; o += 1;
     w.total = (o + 1) & ~1;

@@ -35,6 +35,9 @@
 namespace fksdev {
 
 #define FKS_FULL 0xffffffffu
+#ifndef FKS_MIN_BLOCKS
+#define FKS_MIN_BLOCKS 1  // lock-step CTAs (16 warps each) per SM the register allocation is planned for
+#endif
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -452,7 +455,8 @@ __device__ __forceinline__ Voxel voxel_of(const DevEnv& e, const double* Gl, dou
     return v;
 }
 
-constexpr int kBatch = 4;  // independent SDF gathers in flight per lane
+constexpr int kBatch = 4;       // independent SDF gathers in flight per lane
+constexpr int kCandShared = 64;  // candidate points of collect_corrections kept in shared memory
 
 // CheckEnvironmentCollision (spcs:921-981) of the CURRENT state (G and T[X]); collision_threshold = 0.0 (spcs:424)
 __device__ __noinline__ bool check_env(int wb, int X) {
@@ -534,21 +538,23 @@ __device__ __noinline__ double max_motion(int wb, int Xa, int Xb) {
 
 // SurfaceNormalGrid::LookupSurfaceNormal + GetBestSurfaceNormal (spcs:186-198,235-256,111-132) for the
 // in-bounds cell `li`; (dx,dy,dz) is the SafeNormal'd motion direction.
-__device__ __forceinline__ void lookup_normal(int wb, const DevEnv& e, long long li, double dx, double dy, double dz,
-                                              double& nx, double& ny, double& nz) {
-    nx = ny = nz = 0.0;
+// SurfaceNormalGrid::LookupSurfaceNormal + GetBestSurfaceNormal (spcs:186-198,235-256,111-132).
+// The hash probe is split from the selection so that its (dependent) loads can be issued before the
+// EstimateDistance gathers of the same point and consumed after them.
+__device__ __forceinline__ uint2 normal_range_probe(const DevEnv& e, long long li) {
     const unsigned long long key = (unsigned long long)li + 1ull;
     unsigned long long h = normal_hash((unsigned long long)li) & e.nh_mask;
-    uint2 range = make_uint2(0u, 0u);
     while (true) {
-        const unsigned long long k = __ldg(e.nh_keys + h);
-        if (k == key) {
-            range = __ldg(e.nh_vals + h);
-            break;
-        }
-        if (k == 0ull) break;
+        const ulonglong2 ent = __ldg(reinterpret_cast<const ulonglong2*>(e.nh_keys) + h);  // {key, start | count << 32}
+        if (ent.x == key) return make_uint2((unsigned)(ent.y & 0xFFFFFFFFull), (unsigned)(ent.y >> 32));
+        if (ent.x == 0ull) return make_uint2(0u, 0u);
         h = (h + 1ull) & e.nh_mask;
     }
+}
+// (dx,dy,dz) is the SafeNormal'd motion direction
+__device__ __forceinline__ void select_normal(int wb, const DevEnv& e, uint2 range, double dx, double dy, double dz,
+                                              double& nx, double& ny, double& nz) {
+    nx = ny = nz = 0.0;
     if (range.y == 0u) return;  // empty cell -> zero normal
     const double dn = sqrt(dx * dx + dy * dy + dz * dz);
     double ux = 0.0, uy = 0.0, uz = 0.0;
@@ -560,19 +566,17 @@ __device__ __forceinline__ void lookup_normal(int wb, const DevEnv& e, long long
         raise_flag(wb, FKS_FLAG_WOULD_ASSERT_NORMAL);  // assert(direction_norm > 0.0) spcs:115
     }
     double best_dot = -INFINITY;
-    unsigned best = range.x;
     for (unsigned en = range.x; en < range.x + range.y; en++) {
-        const double* q = e.normal_entries + 6 * (size_t)en;
-        const double dp = __ldg(q + 0) * ux + __ldg(q + 1) * uy + __ldg(q + 2) * uz;
-        if (dp > best_dot) {
+        const double2* q = reinterpret_cast<const double2*>(e.normal_entries + 6 * (size_t)en);
+        const double2 q01 = __ldg(q), q23 = __ldg(q + 1), q45 = __ldg(q + 2);
+        const double dp = q01.x * ux + q01.y * uy + q23.x * uz;
+        if (dp > best_dot) {  // strict: the first maximum wins (spcs:119-128)
             best_dot = dp;
-            best = en;
+            nx = q23.y;
+            ny = q45.x;
+            nz = q45.y;
         }
     }
-    const double* q = e.normal_entries + 6 * (size_t)best;
-    nx = __ldg(q + 3);
-    ny = __ldg(q + 4);
-    nz = __ldg(q + 5);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -951,8 +955,10 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     const int ld = fr.a.sl.ldj;
     const unsigned char* sflag = reinterpret_cast<const unsigned char*>(slot + fr.a.sl.sflag);
     const double* selfcorr = reinterpret_cast<const double*>(slot + fr.a.sl.selfcorr);
-    // candidate list (point index, bit 31 = needs the environment estimate), stored behind the Jacobian columns
-    unsigned* cand = reinterpret_cast<unsigned*>(A + (size_t)(D + 1) * ld);
+    // candidate list: {point index | bit 31 = needs the environment estimate, raw cell value}; the first kCandShared
+    // live in shared memory, the rest behind the Jacobian columns
+    uint2* cand_s = reinterpret_cast<uint2*>(ws + wl.cand);
+    uint2* cand_g = reinterpret_cast<uint2*>(A + (size_t)(D + 1) * ld);
     double* jaxis = ws + wl.jaxis;
     double* jorig = ws + wl.jorig;
     if (KIND == FKS_ROBOT_LINKED) {
@@ -994,7 +1000,12 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
             const bool is_near = vx[k].inb && (f[k] < near);
             const bool keep = (p < P) && (is_near || (has_self && (sflag[p] & 1)));
             const unsigned mask = __ballot_sync(FKS_FULL, keep);
-            if (keep) cand[ncand + __popc(mask & ((1u << lane) - 1u))] = (unsigned)p | (is_near ? 0x80000000u : 0u);
+            if (keep) {
+                const int ci = ncand + __popc(mask & ((1u << lane) - 1u));
+                const uint2 rec = make_uint2((unsigned)p | (is_near ? 0x80000000u : 0u), __float_as_uint(f[k]));
+                if (ci < kCandShared) cand_s[ci] = rec;
+                else cand_g[ci] = rec;
+            }
             ncand += __popc(mask);
         }
     }
@@ -1008,7 +1019,8 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
         double wx = 0.0, wy = 0.0, wz = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
         int l = 0;
         if (ci < ncand) {
-            const unsigned rec = cand[ci];
+            const uint2 rec2 = (ci < kCandShared) ? cand_s[ci] : cand_g[ci];
+            const unsigned rec = rec2.x;
             const int p = (int)(rec & 0x7FFFFFFFu);
             const double2 xy = pxy[p];
             const PointZL zl = pzl[p];
@@ -1026,7 +1038,9 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
             if (rec >> 31) {
                 const Voxel v = voxel_of(e, G + 12 * l, lx, ly, lz);  // same arithmetic as pass 1: same voxel
                 const int vxx = v.x, vyy = v.y, vzz = v.z;
-                const float f = sdf_cell(e, vxx, vyy, vzz);
+                const float f = __uint_as_float(rec2.y);
+                const long long li = ((long long)vxx * e.ny + vyy) * e.nz + vzz;
+                const uint2 nrange = (f < 0.5f * near) ? normal_range_probe(e, li) : make_uint2(0u, 0u);  // issued early
                 const double est = estimate_distance(wx, wy, wz, vxx, vyy, vzz, f);
                 if (est < 0.0) {  // resolution_distance_threshold_ = 0.0 (spcs:425,1874)
                     double qx, qy, qz;
@@ -1034,7 +1048,9 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
                     double dx = wx - qx, dy = wy - qy, dz = wz - qz;
                     safe_normal3(dx, dy, dz);
                     double nx, ny, nz;
-                    lookup_normal(wb, e, ((long long)vxx * e.ny + vyy) * e.nz + vzz, dx, dy, dz, nx, ny, nz);
+                    // est < 0 needs f < res/2 + sqrt(3)/2 res < 2 res: the probe above covered every such point
+                    const uint2 nr = (f < 0.5f * near) ? nrange : normal_range_probe(e, li);
+                    select_normal(wb, e, nr, dx, dy, dz, nx, ny, nz);
                     safe_normal3(nx, ny, nz);
                     const double pen = fabs(0.0 - est);
                     cx = cx + nx * pen;
@@ -1271,108 +1287,131 @@ __device__ __noinline__ void colpiv_qr_solve(int wb, int rows, int cols, int x_o
     __syncwarp();
 }
 
-// Register-resident variant of the same solve for the common small systems: rows <= 64, NC columns known at
-// compile time (3 / 6 / 7: the reference's three robots).  Lane l keeps rows l and l + 32 of all NC columns
-// and of the right-hand side in registers; rows beyond `rows` are zero, which leaves every Householder
-// quantity unchanged.  Column swaps are register selects, the dot products of one reflector against all
-// trailing columns go through ONE interleaved shuffle tree, and the reflectors are applied to the
-// right-hand side as they are formed (only those below the rank cut, as Eigen's solve does).
-template <int NC>
+// Register-resident variant of the same solve for the common small systems: rows <= 32 * R, NC columns known
+// at compile time (3 / 6 / 7: the reference's three robots).  Lane l keeps rows l, l + 32, ... of all NC columns
+// and of the right-hand side in registers; rows beyond `rows` are zero, which leaves every Householder quantity
+// unchanged.  The critical path per Householder step is two interleaved shuffle trees, one square root and one
+// division:
+//   * tree 1 sums, for every not-yet-eliminated column, the squares of the rows below the diagonal row k; with
+//     the diagonal-row entries broadcast from lane k this gives all residual column norms (pivot selection, rank
+//     cut) AND the tail norm of whichever column is picked.  Eigen keeps these norms by LAPACK-style downdating
+//     (a division and a square root per column per step, recomputed when they lose half their digits); the direct
+//     sums here are the exact quantities those approximate, so the pivot order only differs on ties that the
+//     oracle reports as SENS_PIVOT_TIE / SENS_RANK_CUT;
+//   * tree 2 forms the dot products of the reflector with all trailing columns and the right-hand side.
+// Column swaps are register selects; reflectors are applied to the right-hand side as they are formed (only those
+// below the rank cut, as Eigen's solve does).
+template <int NC, int R>
 __device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
     const Frame& fr = frame();
     const int lane = lane_id();
     double* ws = wsd(wb);
     const double* A = reinterpret_cast<const double*>(scratch_slot() + fr.a.sl.jstore);
     const int ld = fr.a.sl.ldj;
-    double a0[NC + 1], a1[NC + 1];  // slot 0: row lane, slot 1: row lane + 32; index NC = right-hand side
+    double a[R][NC + 1];  // slot s holds row lane + 32 s; column index NC = right-hand side
 #pragma unroll
-    for (int c = 0; c <= NC; c++) {
-        a0[c] = (lane < rows) ? A[(size_t)c * ld + lane] : 0.0;
-        a1[c] = (lane + 32 < rows) ? A[(size_t)c * ld + lane + 32] : 0.0;
-    }
+    for (int sl = 0; sl < R; sl++)
+#pragma unroll
+        for (int c = 0; c <= NC; c++) a[sl][c] = (lane + 32 * sl < rows) ? A[(size_t)c * ld + lane + 32 * sl] : 0.0;
     const int size = rows < NC ? rows : NC;
-    double nu[NC], nd[NC], hc[NC];
-    {
-        double sq[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) sq[c] = a0[c] * a0[c] + a1[c] * a1[c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int c = 0; c < NC; c++) sq[c] += __shfl_xor_sync(FKS_FULL, sq[c], o);
-#pragma unroll
-        for (int c = 0; c < NC; c++) nd[c] = nu[c] = sqrt(sq[c]);
-    }
-    double max_norm = 0.0;
-#pragma unroll
-    for (int c = 0; c < NC; c++) max_norm = fmax(max_norm, nu[c]);
     const double eps = DBL_EPSILON;
-    const double threshold_helper = ((max_norm * eps) * (max_norm * eps)) / (double)rows;
-    const double norm_downdate_threshold = sqrt(eps);
+    double threshold_helper = 0.0;
     int nonzero_pivots = size;
     unsigned transp = 0u;
     bool near_cut = false;
+    double rdiag[NC];  // 1 / R(k,k)
 #pragma unroll
     for (int k = 0; k < NC; k++) {
-        hc[k] = 0.0;
+        rdiag[k] = 0.0;
         if (k < size) {
+            // ---- tree 1: squares below row k of every remaining column -------------------------------------
+            const bool below = lane > k;  // slot 0 rows below the diagonal (higher slots always are)
+            double sq[NC];
+#pragma unroll
+            for (int j = k; j < NC; j++) {
+                double v = below ? a[0][j] * a[0][j] : 0.0;
+#pragma unroll
+                for (int sl = 1; sl < R; sl++) v += a[sl][j] * a[sl][j];
+                sq[j] = v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int j = k; j < NC; j++) sq[j] += __shfl_xor_sync(FKS_FULL, sq[j], o);
+            double dk[NC], nsq[NC];  // entry of row k, squared residual norm (rows >= k)
+#pragma unroll
+            for (int j = k; j < NC; j++) {
+                dk[j] = __shfl_sync(FKS_FULL, a[0][j], k);
+                nsq[j] = dk[j] * dk[j] + sq[j];
+            }
+            if (k == 0) {  // threshold from the largest initial column norm (Eigen: colNormsUpdated.maxCoeff())
+                double mx = 0.0;
+#pragma unroll
+                for (int j = 0; j < NC; j++) mx = fmax(mx, nsq[j]);
+                threshold_helper = (mx * (eps * eps)) / (double)rows;
+            }
             int biggest = k;
-            double big = nu[k];
+            double big_sq = nsq[k];
 #pragma unroll
             for (int j = k + 1; j < NC; j++)
-                if (nu[j] > big) {
-                    big = nu[j];
+                if (nsq[j] > big_sq) {
+                    big_sq = nsq[j];
                     biggest = j;
                 }
-            const double big_sq = big * big;
             const double cut = threshold_helper * (double)(rows - k);
             if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
-            if (max_norm > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
+            if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
             transp |= (unsigned)biggest << (4 * k);
-            // swap columns k <-> biggest (registers, runtime `biggest`)
-            {
-                const double o0 = a0[k], o1 = a1[k], onu = nu[k], ond = nd[k];
-                double p0 = o0, p1 = o1, pnu = onu, pnd = ond;
+            // ---- swap columns k <-> biggest (registers, runtime `biggest`) ----------------------------------
+            double tail_sq = sq[k], c0 = dk[k];
 #pragma unroll
-                for (int j = k + 1; j < NC; j++)
-                    if (j == biggest) {
-                        p0 = a0[j]; p1 = a1[j]; pnu = nu[j]; pnd = nd[j];
-                        a0[j] = o0; a1[j] = o1; nu[j] = onu; nd[j] = ond;
+            for (int j = k + 1; j < NC; j++)
+                if (j == biggest) {
+                    tail_sq = sq[j];
+                    c0 = dk[j];
+#pragma unroll
+                    for (int sl = 0; sl < R; sl++) {
+                        const double t = a[sl][k];
+                        a[sl][k] = a[sl][j];
+                        a[sl][j] = t;
                     }
-                a0[k] = p0; a1[k] = p1; nu[k] = pnu; nd[k] = pnd;
-            }
-            // makeHouseholderInPlace on col(k).tail(rows - k)
-            const bool below = lane > k;  // slot 0 rows below the diagonal (slot 1 rows always are)
-            const double tail_sq = warp_sum((below ? a0[k] * a0[k] : 0.0) + a1[k] * a1[k]);
-            const double c0 = __shfl_sync(FKS_FULL, a0[k], k);
+                }
+            // ---- makeHouseholderInPlace on col(k).tail(rows - k) ---------------------------------------------
             double tau, beta;
             if (tail_sq <= DBL_MIN) {
                 tau = 0.0;
                 beta = c0;
-                if (below) a0[k] = 0.0;
-                a1[k] = 0.0;
+                if (below) a[0][k] = 0.0;
+#pragma unroll
+                for (int sl = 1; sl < R; sl++) a[sl][k] = 0.0;
             } else {
                 beta = sqrt(c0 * c0 + tail_sq);
                 if (c0 >= 0.0) beta = -beta;
                 const double denom = c0 - beta;
-                if (below) a0[k] = a0[k] / denom;
-                a1[k] = a1[k] / denom;
+                if (below) a[0][k] = a[0][k] / denom;
+#pragma unroll
+                for (int sl = 1; sl < R; sl++) a[sl][k] = a[sl][k] / denom;
                 tau = (beta - c0) / beta;
             }
-            hc[k] = tau;
-            if (lane == k) a0[k] = beta;
+            rdiag[k] = 1.0 / beta;
+            if (lane == k) a[0][k] = beta;
             const bool apply_b = nonzero_pivots > k;  // Eigen's solve applies the first nonzero_pivots reflectors to c
-            // applyHouseholderOnTheLeft to the trailing columns (and the right-hand side)
+            // ---- applyHouseholderOnTheLeft to the trailing columns (and the right-hand side) -----------------
             if (rows - k == 1) {
                 if (lane == k) {
 #pragma unroll
-                    for (int j = k + 1; j < NC; j++) a0[j] *= (1.0 - tau);
-                    if (apply_b) a0[NC] *= (1.0 - tau);
+                    for (int j = k + 1; j < NC; j++) a[0][j] *= (1.0 - tau);
+                    if (apply_b) a[0][NC] *= (1.0 - tau);
                 }
             } else if (tau != 0.0) {
                 double dt[NC + 1];
 #pragma unroll
-                for (int j = k + 1; j <= NC; j++) dt[j] = (below ? a0[k] * a0[j] : 0.0) + a1[k] * a1[j];
+                for (int j = k + 1; j <= NC; j++) {
+                    double v = below ? a[0][k] * a[0][j] : 0.0;
+#pragma unroll
+                    for (int sl = 1; sl < R; sl++) v += a[sl][k] * a[sl][j];
+                    dt[j] = v;
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -1380,29 +1419,11 @@ __device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
 #pragma unroll
                 for (int j = k + 1; j <= NC; j++) {
                     if (j == NC && !apply_b) continue;
-                    const double tmp = dt[j] + __shfl_sync(FKS_FULL, a0[j], k);
-                    if (lane == k) a0[j] -= tau * tmp;
-                    else if (below) a0[j] -= (tau * a0[k]) * tmp;
-                    a1[j] -= (tau * a1[k]) * tmp;
-                }
-            }
-            // LAPACK-style norm downdate
+                    const double tmp = dt[j] + __shfl_sync(FKS_FULL, a[0][j], k);
+                    if (lane == k) a[0][j] -= tau * tmp;
+                    else if (below) a[0][j] -= (tau * a[0][k]) * tmp;
 #pragma unroll
-            for (int j = k + 1; j < NC; j++) {
-                const double akj = __shfl_sync(FKS_FULL, a0[j], k);
-                if (nu[j] != 0.0) {
-                    double temp = fabs(akj) / nu[j];
-                    temp = (1.0 + temp) * (1.0 - temp);
-                    temp = temp < 0.0 ? 0.0 : temp;
-                    const double ratio = nu[j] / nd[j];
-                    const double temp2 = temp * (ratio * ratio);
-                    if (temp2 <= norm_downdate_threshold) {
-                        const double s2 = warp_sum((below ? a0[j] * a0[j] : 0.0) + a1[j] * a1[j]);
-                        nd[j] = sqrt(s2);
-                        nu[j] = nd[j];
-                    } else {
-                        nu[j] = nu[j] * sqrt(temp);
-                    }
+                    for (int sl = 1; sl < R; sl++) a[sl][j] -= (tau * a[sl][k]) * tmp;
                 }
             }
         }
@@ -1410,13 +1431,13 @@ __device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
     if (near_cut && lane == 0) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
     // back substitution on the leading nz x nz upper triangle: lane i owns row i
     double y[NC];
-    double sres = a0[NC];
+    double sres = a[0][NC];
 #pragma unroll
     for (int j = NC - 1; j >= 0; j--) {
         y[j] = 0.0;
         if (j < nonzero_pivots) {
-            y[j] = __shfl_sync(FKS_FULL, sres / a0[j], j);
-            sres -= a0[j] * y[j];
+            y[j] = __shfl_sync(FKS_FULL, sres * rdiag[j], j);
+            sres -= a[0][j] * y[j];
         }
     }
     if (lane < NC) ws[x_off + lane] = 0.0;
@@ -1495,7 +1516,7 @@ enum {
 }  // namespace
 
 template <int KIND>
-__global__ void __launch_bounds__(kThreadsPerBlock, 1) simulate_kernel(const __grid_constant__ LaunchArgs args) {
+__global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_kernel(const __grid_constant__ LaunchArgs args) {
     // ---- stage parameters, robot and points into shared memory, once per CTA ---------------------
     {
         Frame* f = reinterpret_cast<Frame*>(smem_raw);
@@ -1542,6 +1563,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 1) simulate_kernel(const __g
 
 #ifdef FKS_PHASE_TIMERS
     long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tqr[4] = {0, 0, 0, 0};
     long long t0 = clock64(), t1;
 #define FKS_TICK(i) { t1 = clock64(); tacc[i] += t1 - t0; t0 = t1; }
 #else
@@ -1859,7 +1881,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 1) simulate_kernel(const __g
         // =========================== phase C: collect corrections (spcs:1627) ==========================
         int rows = 0;
         if (want_solve) {
+#ifdef FKS_PHASE_TIMERS
+            const long long tc0 = clock64();
+#endif
             rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
+#ifdef FKS_PHASE_TIMERS
+            tacc[10] += clock64() - tc0;
+            tacc[11] += 1;
+#endif
             if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
         }
         FKS_TICK(6)
@@ -1867,6 +1896,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 1) simulate_kernel(const __g
         FKS_TICK(7)
         // =========================== phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
         if (want_solve) {
+#ifdef FKS_PHASE_TIMERS
+            const long long tq0 = clock64();
+#endif
             if (rows == 0) {
                 // Eigen would return an empty vector and ApplyControlInput would assert; documented device
                 // behaviour: zero correction step
@@ -1874,14 +1906,23 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 1) simulate_kernel(const __g
                 if (lane < D) ws[wl.raw + lane] = 0.0;
                 __syncwarp();
             } else if (rows <= 64 && KIND == FKS_ROBOT_SE2) {
-                colpiv_qr_solve_reg<3>(wb, rows, wl.raw);
+                colpiv_qr_solve_reg<3, 2>(wb, rows, wl.raw);
             } else if (rows <= 64 && KIND == FKS_ROBOT_SE3) {
-                colpiv_qr_solve_reg<6>(wb, rows, wl.raw);
+                colpiv_qr_solve_reg<6, 2>(wb, rows, wl.raw);
             } else if (rows <= 64 && KIND == FKS_ROBOT_LINKED && D == 7) {
-                colpiv_qr_solve_reg<7>(wb, rows, wl.raw);
+                colpiv_qr_solve_reg<7, 2>(wb, rows, wl.raw);
+            } else if (rows <= 128 && KIND == FKS_ROBOT_SE2) {
+                colpiv_qr_solve_reg<3, 4>(wb, rows, wl.raw);
+            } else if (rows <= 128 && KIND == FKS_ROBOT_SE3) {
+                colpiv_qr_solve_reg<6, 4>(wb, rows, wl.raw);
+            } else if (rows <= 128 && KIND == FKS_ROBOT_LINKED && D == 7) {
+                colpiv_qr_solve_reg<7, 4>(wb, rows, wl.raw);
             } else {
                 colpiv_qr_solve(wb, rows, D, wl.raw);
             }
+#ifdef FKS_PHASE_TIMERS
+            if (rows <= 128) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
+#endif
             // motion estimate of the raw correction (spcs:1630) is the next operation
             op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.raw; op_tn = -1; op_derive = 0;
             measure = M_MOTION;
@@ -1894,7 +1935,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 1) simulate_kernel(const __g
     }
 #ifdef FKS_PHASE_TIMERS
     if (lane == 0)
-        for (int i = 0; i < 10; i++) atomicAdd(a.stats + 16 + i, (unsigned long long)tacc[i]);
+    {
+        for (int i = 0; i < 12; i++) atomicAdd(a.stats + 16 + i, (unsigned long long)tacc[i]);
+        for (int i = 0; i < 4; i++) atomicAdd(a.stats + 28 + i, (unsigned long long)tqr[i]);
+    }
 #endif
     __syncwarp();
     if (lane < FKS_NUM_STATS) {

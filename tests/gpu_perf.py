@@ -35,13 +35,15 @@ def run(name, n, free=False, reps=3):
         s["total_microsteps"] / best * 1e3, int(((rec["flags"] & 2) != 0).sum()), int((rec["flags"] & 1).sum())), flush=True)
     import ctypes as C
     if hasattr(capi.lib, "fks_debug_phase_cycles"):
-        ph = (C.c_uint64 * 10)()
+        ph = (C.c_uint64 * 16)()
         capi.lib.fks_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
         capi.lib.fks_debug_phase_cycles(sim._h, ph)
-        tot = float(sum(ph)) or 1.0
-        if sum(ph):
+        tot = float(sum(ph[:10])) or 1.0
+        if sum(ph[:10]):
             names = ["A apply", "bar1", "B measure", "bar2", "T trans", "bar3", "C collect", "bar4", "D solve", "bar5"]
             print("    phases: " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(names, ph)), flush=True)
+            print("    per call: collect %.0f clk (n=%d), qr<=64rows %.0f clk (n=%d), qr>64rows %.0f clk (n=%d)" % (
+                ph[10] / max(ph[11], 1), ph[11], ph[12] / max(ph[13], 1), ph[13], ph[14] / max(ph[15], 1), ph[15]), flush=True)
     sim.close()
 
 
