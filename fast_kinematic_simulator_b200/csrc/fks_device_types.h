@@ -199,6 +199,7 @@ struct LaunchArgs {
     int allow_contacts, noise_mode, cfg_stride, rec_stride;
     int P, warps_per_block;
     int pts_off, warps_off;          // byte offsets of the point arrays / the warp blocks in dynamic shared memory
+    int sync_off, _pad;              // byte offset of the CTA-level synchronisation word
 };
 
 struct Frame {

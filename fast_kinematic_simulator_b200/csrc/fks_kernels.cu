@@ -61,6 +61,20 @@ __device__ __forceinline__ char* scratch_slot() {
     return a.scratch + (size_t)(blockIdx.x * a.warps_per_block + (threadIdx.x >> 5)) * a.sl.total;
 }
 
+// named barriers over a subset of the CTA's warps (PTX barrier.sync / barrier.red with a thread count)
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ bool named_barrier_or(int id, int threads, bool pred) {
+    unsigned out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(out)
+        : "r"(id), "r"(threads), "r"((unsigned)pred)
+        : "memory");
+    return out != 0u;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FKS_FULL, v, o);
@@ -1532,6 +1546,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             pxy[i] = args.pxy[i];
             pzl[i] = args.pzl[i];
         }
+        if (threadIdx.x < 4) reinterpret_cast<unsigned*>(smem_raw + args.sync_off)[threadIdx.x] = 0u;
     }
     __syncthreads();
     const Frame& fr = frame();
@@ -1569,21 +1584,35 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #else
 #define FKS_TICK(i)
 #endif
+    // Barriers.  Round 0 of a super-cycle is run by the whole CTA (barrier 0).  If some warps then need a
+    // contact solve (group 2: collect + QR, barrier 2), the others (group 1) do not wait for them: they keep
+    // running lock-step A / B / T rounds among themselves on barrier 1 until group 2 is finished.  Two code
+    // regions are live at any time instead of one -- still a few KB each.
+    const int n_warps = a.warps_per_block;
+    volatile unsigned* g2_done = reinterpret_cast<volatile unsigned*>(smem_raw + a.sync_off);
+    bool want_solve = false;
     for (;;) {
+        int bar_id = 0, bar_threads = 32 * n_warps, n_solvers = 0;
+        bool counted_solver = false;
+        for (int round = 0;; round++) {
         // =========================== phase A: advance a kinematic state ===============================
-        if (op == OP_KIN) kinematics<KIND>(wb, op_out, op_derive);
-        else if (op == OP_APPLY) apply_control<KIND>(wb, op_in, op_out, op_u, op_tn, op_derive);
+        if (!want_solve) {
+            if (op == OP_KIN) kinematics<KIND>(wb, op_out, op_derive);
+            else if (op == OP_APPLY) apply_control<KIND>(wb, op_in, op_out, op_u, op_tn, op_derive);
+        }
         FKS_TICK(0)
-        __syncthreads();
+        named_barrier(bar_id, bar_threads);
         FKS_TICK(1)
         // =========================== phase B: measure =================================================
-        if (measure == M_MOTION) m_result = max_motion(wb, op_in, op_out);  // spcs:1492-1527
-        else if (measure == M_CHECK) cc = check_collision<KIND>(wb, prev, cur);  // spcs:1418-1436
+        if (!want_solve) {
+            if (measure == M_MOTION) m_result = max_motion(wb, op_in, op_out);  // spcs:1492-1527
+            else if (measure == M_CHECK) cc = check_collision<KIND>(wb, prev, cur);  // spcs:1418-1436
+        }
         FKS_TICK(2)
-        __syncthreads();
+        named_barrier(bar_id, bar_threads);
         FKS_TICK(3)
         // =========================== phase T: transitions =============================================
-        bool want_solve = false;
+        if (!want_solve) {
         op = OP_NONE;
         measure = M_NONE;
         // Each pass of this loop handles one event; it ends as soon as the next operation is known.
@@ -1875,12 +1904,24 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 after = AF_FETCH;
             }
         }
+        }  // if (!want_solve): end of phase T
         FKS_TICK(4)
-        __syncthreads();
-        FKS_TICK(5)
+        if (round == 0) {
+            n_solvers = __syncthreads_count(want_solve) >> 5;  // full barrier; the count is in threads
+            FKS_TICK(5)
+            if (n_solvers == 0) break;         // nobody solves: next super-cycle
+            counted_solver = want_solve;
+            if (want_solve) break;             // group 2 goes to collect + solve
+            bar_id = 1;                        // group 1 keeps going on its own barrier
+            bar_threads = 32 * (n_warps - n_solvers);
+        }
+        // group 1 only: another round while group 2 is still busy (decision made uniform by the barrier reduction)
+        const bool keep = (*g2_done < (unsigned)n_solvers) && (round < 16);
+        if (!named_barrier_or(1, bar_threads, keep)) break;
+        }  // rounds
         // =========================== phase C: collect corrections (spcs:1627) ==========================
-        int rows = 0;
-        if (want_solve) {
+        if (counted_solver) {
+            int rows = 0;
 #ifdef FKS_PHASE_TIMERS
             const long long tc0 = clock64();
 #endif
@@ -1890,12 +1931,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             tacc[11] += 1;
 #endif
             if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
-        }
-        FKS_TICK(6)
-        __syncthreads();
-        FKS_TICK(7)
-        // =========================== phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
-        if (want_solve) {
+            FKS_TICK(6)
+            named_barrier(2, 32 * n_solvers);
+            FKS_TICK(7)
+            // ======================= phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
 #ifdef FKS_PHASE_TIMERS
             const long long tq0 = clock64();
 #endif
@@ -1927,11 +1966,15 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.raw; op_tn = -1; op_derive = 0;
             measure = M_MOTION;
             after = AF_EST_RAW;
+            want_solve = false;
+            __syncwarp();
+            if (lane == 0) atomicAdd(const_cast<unsigned*>(g2_done), 1u);
         }
         FKS_TICK(8)
-        const bool all_done = __syncthreads_and(after == AF_DONE);
+        const bool all_done = __syncthreads_and(after == AF_DONE && !want_solve);
         FKS_TICK(9)
         if (all_done) break;
+        if (threadIdx.x == 0) *g2_done = 0u;  // next read is at least two full barriers away
     }
 #ifdef FKS_PHASE_TIMERS
     if (lane == 0)
@@ -1990,6 +2033,8 @@ size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stri
     off += (size_t)P * (sizeof(double2) + sizeof(PointZL));
     args->warps_off = (int)off;
     off += (size_t)warps_per_block * args->wl.total * 8;
+    args->sync_off = (int)off;  // one 16-byte word of CTA-level synchronisation state
+    off += 16;
     return off;
 }
 
