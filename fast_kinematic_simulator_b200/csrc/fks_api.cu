@@ -223,6 +223,29 @@ int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
     d.ny = (int)desc->ny;
     d.nz = (int)desc->nz;
     d.oob = desc->oob_value;
+    // Link-level culling (fks_kernels.cu: active_links) relies on the SDF being a distance field: neighbouring cells
+    // differ by at most one cell size inside a sign region and by at most two across the surface.  Verified here;
+    // an SDF that is not (hand-made, inflated, ...) simply runs without culling.
+    {
+        const int64_t nx = desc->nx, ny = desc->ny, nz = desc->nz;
+        const double lim1 = desc->sdf_resolution * (1.0 + 1e-4), lim2 = 2.0 * lim1;
+        bool ok = std::isinf(desc->oob_value) && desc->oob_value > 0.0f;
+        const float* f = desc->sdf;
+#pragma omp parallel for schedule(static) reduction(&& : ok)
+        for (int64_t x = 0; x < nx; x++)
+            for (int64_t y = 0; y < ny && ok; y++)
+                for (int64_t z = 0; z < nz; z++) {
+                    const size_t i = (size_t)((x * ny + y) * nz + z);
+                    const double v = (double)f[i];
+                    const size_t nb[3] = {x + 1 < nx ? i + (size_t)(ny * nz) : i, y + 1 < ny ? i + (size_t)nz : i, z + 1 < nz ? i + 1 : i};
+                    for (int k = 0; k < 3; k++) {
+                        const double w = (double)f[nb[k]];
+                        const double lim = ((v < 0.0) != (w < 0.0)) ? lim2 : lim1;
+                        if (!(std::fabs(v - w) <= lim)) ok = false;
+                    }
+                }
+        d.cull = ok ? 1 : 0;
+    }
     d.sdf = env->d_sdf;
     d.nh_keys = env->d_keys;
     d.nh_mask = (unsigned long long)(cap - 1);
@@ -404,6 +427,13 @@ int fks_robot_create(int device, const fks_robot_desc* r, fks_robot** out) {
             rad = std::max(rad, std::sqrt(d2));
         }
         h.cap_radius[l] = rad * (1.0 + 1e-9) + 1e-12;
+        double srad = 0.0;
+        for (int k = 0; k < 3; k++) h.sph_center[l][k] = 0.5 * (lo[k] + hi[k]);
+        for (int p = h.link_begin[l]; p < h.link_begin[l + 1]; p++) {
+            const double dx = px[(size_t)p] - h.sph_center[l][0], dy = py[(size_t)p] - h.sph_center[l][1], dz = pz[(size_t)p] - h.sph_center[l][2];
+            srad = std::max(srad, std::sqrt(dx * dx + dy * dy + dz * dz));
+        }
+        h.sph_radius[l] = srad * (1.0 + 1e-9) + 1e-12;
     }
     rob->stride = (r->kind == FKS_ROBOT_SE2) ? 3 : (r->kind == FKS_ROBOT_SE3 ? 12 : D);
 
@@ -486,6 +516,8 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
         if (v >= 1 && v <= kWarpsPerBlock) wpb = v;
     }
     s->dyn_smem = simulate_smem_plan(&s->plan, h.L, h.J, h.D, h.P, robot->stride, wpb);
+    s->plan.cull_mode = 1;
+    if (const char* ev = std::getenv("FKS_CULL")) s->plan.cull_mode = std::atoi(ev);  // developer knob
     int rc = simulate_kernel_info(h.kind, s->dyn_smem, wpb, &s->kinfo);
     if (rc != 0) { delete s; return cuda_fail((cudaError_t)rc, "fks_sim_create: kernel attributes"); }
     if (s->kinfo.max_blocks_per_sm < 1) { delete s; return fail(FKS_ERR_UNSUPPORTED, "fks_sim_create: robot does not fit one CTA's shared memory"); }

@@ -23,7 +23,10 @@ constexpr int kMaxJoints = 16;
 constexpr int kMaxPairs = (kMaxLinks * (kMaxLinks - 1)) / 2;
 constexpr int kMaxSelfPartners = kMaxLinks - 1;
 constexpr int kPairChunks = (kMaxPairs + 31) / 32;
-constexpr int kWarpsPerBlock = 16;  // upper bound of warps per CTA (launch bounds); the CTA's warps run in lock step
+#ifndef FKS_MAX_WARPS
+#define FKS_MAX_WARPS 16
+#endif
+constexpr int kWarpsPerBlock = FKS_MAX_WARPS;  // upper bound of warps per CTA (launch bounds); the CTA's warps run in lock step
 constexpr int kThreadsPerBlock = kWarpsPerBlock * 32;
 
 struct DevAxis {
@@ -53,6 +56,8 @@ struct DevRobot {
     unsigned char pair_a[kMaxPairs], pair_b[kMaxPairs];  // the disallowed pairs, a < b
     double cap_p0[kMaxLinks][3], cap_p1[kMaxLinks][3];  // bounding capsule of the link's points (link frame)
     double cap_radius[kMaxLinks];
+    double sph_center[kMaxLinks][3];  // bounding sphere of the link's points (link frame): link-level SDF culling
+    double sph_radius[kMaxLinks];
     double link_mass[kMaxLinks];         // cumulative point counts (spcs.hpp:1244-1255)
 };
 
@@ -64,6 +69,8 @@ struct DevEnv {
     double inv_twice_res;    // 1.0 / (2.0 * sdf_res)
     int nx, ny, nz;
     float oob;
+    int cull;                // 1: the SDF is a true distance field (checked at upload): link-level culling is exact
+    int _pad;
     const float* sdf;
     // normal hash: 16-byte entries {linear cell index + 1 (0 = empty slot), first entry | entry count << 32}
     const unsigned long long* nh_keys;
@@ -199,7 +206,8 @@ struct LaunchArgs {
     int allow_contacts, noise_mode, cfg_stride, rec_stride;
     int P, warps_per_block;
     int pts_off, warps_off;          // byte offsets of the point arrays / the warp blocks in dynamic shared memory
-    int sync_off, _pad;              // byte offset of the CTA-level synchronisation word
+    int sync_off;                    // byte offset of the CTA-level synchronisation word
+    int cull_mode;                   // link-level SDF culling: 0 never, 1 always, 2 only while the particle is collision free
 };
 
 struct Frame {

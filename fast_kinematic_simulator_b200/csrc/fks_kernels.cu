@@ -470,10 +470,29 @@ __device__ __forceinline__ Voxel voxel_of(const DevEnv& e, const double* Gl, dou
 }
 
 constexpr int kBatch = 4;       // independent SDF gathers in flight per lane
+
+// Link-level culling.  SDF cell values are exact Euclidean distances between cell centres, hence 1-Lipschitz over
+// cell centres; a point p of a link and the link's sphere centre q lie within sqrt(3)/2 res of their cells' centres,
+// so  raw(cell(p)) >= raw(cell(q)) - R - sqrt(3) res.  A link whose centre cell value exceeds R + sqrt(3) res + `need`
+// cannot hold a point with raw value < `need`: all of its points are skipped.  Out-of-bounds centres never cull.
+__device__ __forceinline__ unsigned active_links(const DevEnv& e, const DevRobot& rb, const double* G, double need) {
+    const int lane = lane_id();
+    bool active = false;
+    if (lane < rb.L) {
+        active = true;
+        const Voxel v = voxel_of(e, G + 12 * lane, rb.sph_center[lane][0], rb.sph_center[lane][1], rb.sph_center[lane][2]);
+        if (v.inb) {
+            const double f = (double)sdf_cell(e, v.x, v.y, v.z);
+            const double reach = rb.sph_radius[lane] * (1.0 + 1e-6) + (1.7320508075688772 * (1.0 + 1e-5)) * e.sdf_res + need;
+            active = !(f > reach);
+        }
+    }
+    return __ballot_sync(FKS_FULL, active);
+}
 constexpr int kCandShared = 64;  // candidate points of collect_corrections kept in shared memory
 
 // CheckEnvironmentCollision (spcs:921-981) of the CURRENT state (G and T[X]); collision_threshold = 0.0 (spcs:424)
-__device__ __noinline__ bool check_env(int wb, int X) {
+__device__ __noinline__ bool check_env(int wb, int X, int use_cull) {
     const Frame& fr = frame();
     const DevEnv& e = fr.a.env;
     const WarpLayout& wl = fr.a.wl;
@@ -482,25 +501,46 @@ __device__ __noinline__ bool check_env(int wb, int X) {
     const double* G = ws + wl.G;
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
-    const int P = fr.a.P;
     const double res = e.sdf_res;
     const double thr = 0.0 - (fr.a.sp.check_tolerance * res);
     const double thr_deep = thr - res;
     const float oob = e.oob;
     bool hit = false;
-    for (int base = 0; base < P; base += 32 * kBatch) {
+    // points of culled links cannot collide (and an out-of-bounds value below the threshold disables culling)
+    const DevRobot& rb = fr.rb;
+    unsigned links = (!use_cull || !e.cull || (double)oob < thr) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, 0.0);
+    // walk the 32-point chunks of the active links, kBatch chunks (independent gathers) at a time
+    int link = -1, pos = 0, end = 0;
+    for (;;) {
+        int cb[kBatch], ce[kBatch];  // chunk begin / end of the link
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            if (pos >= end && links) {  // next run of consecutive active links = one contiguous point range
+                link = __ffs(links) - 1;
+                const int len = __ffs(~(links >> link)) - 1;
+                links &= ~(((len >= 32) ? 0xffffffffu : ((1u << len) - 1u)) << link);
+                pos = rb.link_begin[link];
+                end = rb.link_begin[link + len];
+            }
+            cb[k] = pos;
+            ce[k] = end;
+            if (pos < end) pos += 32;
+        }
+        if (cb[0] >= ce[0]) break;
         float f[kBatch];
         Voxel vx[kBatch];
 #pragma unroll
         for (int k = 0; k < kBatch; k++) {
-            const int p = base + 32 * k + lane;
+            const int p = cb[k] + lane;
             f[k] = INFINITY;
             vx[k].inb = false;
-            if (p < P) {
+            if (p < ce[k]) {
                 const double2 xy = pxy[p];
                 const PointZL zl = pzl[p];
                 vx[k] = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
                 f[k] = vx[k].inb ? sdf_cell(e, vx[k].x, vx[k].y, vx[k].z) : oob;
+            } else {
+                vx[k].inb = true;  // padding lane: never a collision
             }
         }
 #pragma unroll
@@ -511,7 +551,7 @@ __device__ __noinline__ bool check_env(int wb, int X) {
                     // out of bounds returns the same value, so both tiers reduce to one compare, spcs:943-975)
                     hit = true;
                 } else {
-                    const int p = base + 32 * k + lane;
+                    const int p = cb[k] + lane;
                     const double2 xy = pxy[p];
                     const PointZL zl = pzl[p];
                     double wx, wy, wz;
@@ -933,8 +973,8 @@ __device__ __forceinline__ bool collect_self(int wb, int Xprev, int Xcur) {
 
 // CheckCollision (spcs:1418-1436): bit 0 = in collision, bit 1 = self-collision map non-empty
 template <int KIND>
-__device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur) {
-    const bool envc = check_env(wb, Xcur);
+__device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur, int use_cull) {
+    const bool envc = check_env(wb, Xcur, use_cull);
     const bool has_self = (KIND == FKS_ROBOT_LINKED) ? collect_self(wb, Xprev, Xcur) : false;
     return ((envc || has_self) ? 1u : 0u) | (has_self ? 2u : 0u);
 }
@@ -992,16 +1032,33 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     const float near = (float)(2.0 * res);
     // ---- pass 1 -----------------------------------------------------------------------------------
     int ncand = 0;
-    for (int base = 0; base < P; base += 32 * kBatch) {
+    unsigned links = (fr.a.cull_mode != 1 || !e.cull || has_self) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, 2.0 * res);
+    int link = -1, pos = 0, end = 0;
+    for (;;) {
+        int cb[kBatch], ce[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            if (pos >= end && links) {  // next run of consecutive active links = one contiguous point range
+                link = __ffs(links) - 1;
+                const int len = __ffs(~(links >> link)) - 1;
+                links &= ~(((len >= 32) ? 0xffffffffu : ((1u << len) - 1u)) << link);
+                pos = rb.link_begin[link];
+                end = rb.link_begin[link + len];
+            }
+            cb[k] = pos;
+            ce[k] = end;
+            if (pos < end) pos += 32;
+        }
+        if (cb[0] >= ce[0]) break;
         float f[kBatch];
         Voxel vx[kBatch];
 #pragma unroll
         for (int k = 0; k < kBatch; k++) {
-            const int p = base + 32 * k + lane;
+            const int p = cb[k] + lane;
             f[k] = INFINITY;
             vx[k].x = vx[k].y = vx[k].z = 0;
             vx[k].inb = false;
-            if (p < P) {
+            if (p < ce[k]) {
                 const double2 xy = pxy[p];
                 const PointZL zl = pzl[p];
                 vx[k] = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
@@ -1010,9 +1067,9 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
         }
 #pragma unroll
         for (int k = 0; k < kBatch; k++) {
-            const int p = base + 32 * k + lane;
+            const int p = cb[k] + lane;
             const bool is_near = vx[k].inb && (f[k] < near);
-            const bool keep = (p < P) && (is_near || (has_self && (sflag[p] & 1)));
+            const bool keep = (p < ce[k]) && (is_near || (has_self && (sflag[p] & 1)));
             const unsigned mask = __ballot_sync(FKS_FULL, keep);
             if (keep) {
                 const int ci = ncand + __popc(mask & ((1u << lane) - 1u));
@@ -1606,7 +1663,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         // =========================== phase B: measure =================================================
         if (!want_solve) {
             if (measure == M_MOTION) m_result = max_motion(wb, op_in, op_out);  // spcs:1492-1527
-            else if (measure == M_CHECK) cc = check_collision<KIND>(wb, prev, cur);  // spcs:1418-1436
+            else if (measure == M_CHECK) cc = check_collision<KIND>(wb, prev, cur, a.cull_mode == 2 ? ((cc & 1u) ? 0 : 1) : a.cull_mode);  // spcs:1418-1436
         }
         FKS_TICK(2)
         named_barrier(bar_id, bar_threads);
