@@ -47,6 +47,13 @@ def parse_args():
     return ap.parse_args()
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -115,7 +122,8 @@ def run_reference(args, rank, world):
 
     n_per_gpu = args.particles or DEFAULT_PARTICLES.get(args.workload, 65536)
     w = W.make(args.workload, n_particles=min(n_per_gpu, 8192))
-    orc = OB.OracleSimulator(w.environment().desc, w.robot.to_c(), capi.default_solver_params(), 25.0, 42, 0)
+    # all host threads (torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly)
+    orc = OB.OracleSimulator(w.environment().desc, w.robot.to_c(), capi.default_solver_params(), 25.0, 42, host_threads())
     # calibrate the sample so that one step is ~4 s of CPU work
     n0 = min(128, w.n_particles)
     s0, t0 = w.subset(n0)
@@ -307,7 +315,7 @@ def main():
             gathers = (P * tot_local(stats, "total_microsteps") + 8 * P * tot_local(stats, "total_resolver_iterations")) / args.steps / k_s
             line["gather"] = {"achieved_gathers_per_s": gathers, "l2_peak_gathers_per_s": ga.value, "hbm_peak_gathers_per_s": gh.value,
                               "frac_of_l2_peak": gathers / ga.value}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline(args, w, capi)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -323,7 +331,7 @@ def cpu_baseline(args, w, capi):
     """The oracle port on this box's host cores, bounded sample of the same workload (rank 0, N = 1 shape)."""
     from oracle import oracle_binding as OB
 
-    orc = OB.OracleSimulator(w.environment().desc, w.robot.to_c(), capi.default_solver_params(), 25.0, 42, 0)
+    orc = OB.OracleSimulator(w.environment().desc, w.robot.to_c(), capi.default_solver_params(), 25.0, 42, host_threads())
     n0 = min(256, w.n_particles)
     s0, t0 = w.subset(n0)
     t = time.perf_counter()
