@@ -100,7 +100,7 @@ struct fks_sim {
     uint64_t seed;
     int32_t debug_level;
     cudaStream_t stream;
-    int grid_max;
+    int grid_max, num_sms;
     size_t dyn_smem;
     KernelInfo kinfo;
     LaunchArgs plan;  // layouts and shared-memory offsets (simulate_smem_plan)
@@ -525,6 +525,7 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     cudaError_t err = cudaGetDeviceProperties(&prop, s->device);
     if (err != cudaSuccess) { delete s; return cuda_fail(err, "cudaGetDeviceProperties"); }
     s->grid_max = prop.multiProcessorCount * s->kinfo.max_blocks_per_sm;
+    s->num_sms = prop.multiProcessorCount;
     const size_t scratch_bytes = (size_t)s->grid_max * wpb * s->plan.sl.total;
     if ((err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_scratch, scratch_bytes)) != cudaSuccess ||
@@ -592,10 +593,16 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
     a.noise_mode = noise_mode;
     a.cfg_stride = s->robot->stride;
     a.rec_stride = (int)fks_sim_result_stride(s);
-    const size_t blocks_needed = (n + s->plan.warps_per_block - 1) / s->plan.warps_per_block;
+    // small batches: fewer warps per CTA so that the particles spread over all SMs (one warp per particle)
+    const size_t per_sm = (n + (size_t)s->num_sms - 1) / (size_t)s->num_sms;
+    const int wpb = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->plan.warps_per_block, per_sm));
+    a.warps_per_block = wpb;
+    a.sync_off = a.warps_off + wpb * a.wl.total * 8;
+    const size_t dyn_smem = (size_t)a.sync_off + 16;
+    const size_t blocks_needed = (n + (size_t)wpb - 1) / (size_t)wpb;
     const int grid = (int)std::min<size_t>((size_t)s->grid_max, blocks_needed);
     FKS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
-    const int rc = launch_simulate(s->robot->host.kind, a, grid, s->dyn_smem, stream, s->env->l2_window_bytes ? s->env->d_sdf : nullptr,
+    const int rc = launch_simulate(s->robot->host.kind, a, grid, dyn_smem, stream, s->env->l2_window_bytes ? s->env->d_sdf : nullptr,
                                    s->env->l2_window_bytes);
     if (rc != 0) return cuda_fail((cudaError_t)rc, "simulate kernel launch");
     s->launches++;

@@ -24,7 +24,7 @@ constexpr int kMaxPairs = (kMaxLinks * (kMaxLinks - 1)) / 2;
 constexpr int kMaxSelfPartners = kMaxLinks - 1;
 constexpr int kPairChunks = (kMaxPairs + 31) / 32;
 #ifndef FKS_MAX_WARPS
-#define FKS_MAX_WARPS 16
+#define FKS_MAX_WARPS 32
 #endif
 constexpr int kWarpsPerBlock = FKS_MAX_WARPS;  // upper bound of warps per CTA (launch bounds); the CTA's warps run in lock step
 constexpr int kThreadsPerBlock = kWarpsPerBlock * 32;

@@ -2001,6 +2001,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 flags |= FKS_FLAG_EMPTY_JACOBIAN;
                 if (lane < D) ws[wl.raw + lane] = 0.0;
                 __syncwarp();
+            } else if (rows <= 32 && KIND == FKS_ROBOT_SE2) {
+                colpiv_qr_solve_reg<3, 1>(wb, rows, wl.raw);
+            } else if (rows <= 32 && KIND == FKS_ROBOT_SE3) {
+                colpiv_qr_solve_reg<6, 1>(wb, rows, wl.raw);
+            } else if (rows <= 32 && KIND == FKS_ROBOT_LINKED && D == 7) {
+                colpiv_qr_solve_reg<7, 1>(wb, rows, wl.raw);
             } else if (rows <= 64 && KIND == FKS_ROBOT_SE2) {
                 colpiv_qr_solve_reg<3, 2>(wb, rows, wl.raw);
             } else if (rows <= 64 && KIND == FKS_ROBOT_SE3) {

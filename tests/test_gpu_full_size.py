@@ -1,0 +1,83 @@
+"""Full-size checks (BASELINE configs 2 and 3 at their particle counts) through size-independent properties: the
+oracle cannot run 65,536 arm particles in seconds, so these assert invariants of the path, determinism, partition
+independence, and spot-check a contiguous window of particles against the oracle in Philox mode."""
+import numpy as np
+import pytest
+
+from fast_kinematic_simulator_b200 import capi, workloads as W
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _properties(w, window, need_free=True):
+    sim = w.make_simulator()
+    n = w.n_particles
+    r = sim.forward_simulate_robots(w.starts, w.targets, True, capi.NOISE_PHILOX)
+    st = sim.get_statistics()
+    # counters are a checksum of the per-particle records
+    assert st["total_microsteps"] == int(r.n_microsteps.sum())
+    assert st["total_resolver_iterations"] == int(r.n_resolver_iters.sum())
+    assert st["successful_resolves"] + st["unsuccessful_resolves"] == int(r.n_steps.sum())
+    assert st["successful_resolves"] == st["free_resolves"] + st["collision_resolves"]
+    failed = (r.flags & capi.FLAG_RESOLVE_FAILED) != 0
+    assert st["unsuccessful_resolves"] == int(failed.sum())          # failed_resolves_end_motion: at most one per particle
+    assert np.all(((r.flags & capi.FLAG_ENDED_BY_FAILURE) != 0) == failed)
+    assert np.all(r.n_steps[~failed] == 25) and np.all(r.n_steps >= 1) and np.all(r.n_steps <= 25)
+    assert np.all(r.n_microsteps >= r.n_steps)                       # at least one microstep per controller step
+    assert not np.any(r.flags & (capi.FLAG_WOULD_ASSERT_MICROSTEP | capi.FLAG_TAPE_EXHAUSTED | capi.FLAG_EMPTY_JACOBIAN))
+    assert np.all(r.n_resolver_iters[~r.did_contact] == 0)           # no contact -> the resolver never ran
+    assert np.all(np.isfinite(r.configs))
+    # idempotence / determinism: the same call again gives the same bytes
+    r2 = sim.forward_simulate_robots(w.starts, w.targets, True, capi.NOISE_PHILOX)
+    assert np.array_equal(r.records, r2.records)
+    # partition independence at full size: two shards with global ids == the whole batch
+    h = n // 3
+    lo = sim.forward_simulate_robots(w.starts[:h], w.targets, True, capi.NOISE_PHILOX, first_particle_id=0)
+    hi = sim.forward_simulate_robots(w.starts[h:], w.targets, True, capi.NOISE_PHILOX, first_particle_id=h)
+    assert np.array_equal(np.concatenate([lo.records, hi.records]), r.records)
+    # oracle spot check on a window of particles (Philox noise differs from the host's in the last ulp of log/cos:
+    # compare particles that never touched anything, where nothing amplifies it)
+    a, b = window
+    orc = parity.make_oracle(w)
+    ref = orc.forward_simulate(w.starts[a:b], w.targets, True, capi.NOISE_PHILOX, None, a)
+    free = ((ref["flags"] & capi.FLAG_DID_CONTACT) == 0) & ~r.did_contact[a:b]
+    assert free.sum() >= 1 or not need_free
+    if free.any():
+        assert np.array_equal(r.n_microsteps[a:b][free], ref["n_microsteps"][free])
+        assert np.max(np.abs(r.configs[a:b][free] - ref["cfg"][free])) < 1e-9
+    agree = np.mean((r.flags[a:b] & 1) == (ref["flags"] & 1))
+    assert agree > 0.9, agree
+    return r, st
+
+
+def test_se3_narrow_passage_full_size():
+    w = W.se3_narrow_passage(16384)
+    r, st = _properties(w, (4000, 4096))
+    assert 0.2 < r.did_contact.mean() < 0.9
+    R = r.configs.reshape(-1, 3, 4)[:, :, :3]
+    assert np.allclose(R @ R.transpose(0, 2, 1), np.eye(3), atol=1e-9)  # poses stay rigid
+
+
+def test_arm_table_full_size():
+    w = W.arm_table(65536)
+    r, st = _properties(w, (30000, 30064), need_free=False)  # every particle of this workload ends up in contact
+    assert r.did_contact.mean() > 0.9
+    assert np.all(np.abs(r.configs[:, 1:6]) <= 2.9 + 1e-12)              # revolute joint limits hold
+    assert np.all(np.abs(r.configs[:, [0, 6]]) <= np.pi + 1e-12)         # continuous joints stay wrapped
+
+
+def test_arm_free_full_size():
+    w = W.arm_free(65536)
+    r, st = _properties(w, (50000, 50064))
+    assert not r.did_contact.any() and st["free_resolves"] == 25 * 65536
+
+
+def test_tiny_batches_spread_over_sms():
+    w = W.se2_arena(128)
+    sim = w.make_simulator()
+    full = sim.forward_simulate_robots(w.starts, w.targets, True, capi.NOISE_PHILOX)
+    for n in (1, 2, 31, 33, 127):
+        part = sim.forward_simulate_robots(w.starts[:n], w.targets, True, capi.NOISE_PHILOX)
+        assert np.array_equal(part.records, full.records[:n])
