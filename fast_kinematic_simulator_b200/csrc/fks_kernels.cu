@@ -1658,7 +1658,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             else if (op == OP_APPLY) apply_control<KIND>(wb, op_in, op_out, op_u, op_tn, op_derive);
         }
         FKS_TICK(0)
+#ifdef FKS_BARRIER_AB
         named_barrier(bar_id, bar_threads);
+#endif
         FKS_TICK(1)
         // =========================== phase B: measure =================================================
         if (!want_solve) {
@@ -2025,10 +2027,18 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #ifdef FKS_PHASE_TIMERS
             if (rows <= 128) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
 #endif
-            // motion estimate of the raw correction (spcs:1630) is the next operation
-            op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.raw; op_tn = -1; op_derive = 0;
-            measure = M_MOTION;
-            after = AF_EST_RAW;
+            // motion estimate of the raw correction (spcs:1630) in the same solver slot: one lock-step round per
+            // resolver iteration instead of two
+            apply_control<KIND>(wb, cur, 2, wl.raw, -1, 0);
+            m_result = max_motion(wb, cur, 2);
+            {  // spcs:1681-1689
+                const double step_fraction = fmax(m_result / allowed_microstep_distance, 1.0);
+                if (lane < D) ws[wl.stepv + lane] = (ws[wl.raw + lane] / step_fraction) * fabs(scaling);
+                __syncwarp();
+            }
+            op = OP_APPLY; op_in = cur; op_out = cur; op_u = wl.stepv; op_tn = -1; op_derive = 1;
+            measure = M_CHECK;
+            after = AF_RESOLVE_CHECK;
             want_solve = false;
             __syncwarp();
             if (lane == 0) atomicAdd(const_cast<unsigned*>(g2_done), 1u);
