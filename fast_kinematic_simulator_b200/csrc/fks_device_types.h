@@ -93,6 +93,15 @@ inline __host__ __device__ unsigned long long normal_hash(unsigned long long cel
     return h ^ (h >> 29);
 }
 
+// per-particle bookkeeping of a warp, kept in shared memory (uniform across lanes)
+struct WarpVars {
+    unsigned long long pid, tape_pos, tape_end;
+    double scaling;
+    unsigned step, micro, number_microsteps, resolver_iterations, flags, n_micro_total, n_iter_total, n_steps;
+    int collided, any_resolve_failed, step_collided, step_failed, step_stopped, _pad;
+};
+constexpr int kWarpVarsDoubles = (int)((sizeof(WarpVars) + 7) / 8);
+
 // ---- per-warp shared memory layout (offsets in doubles from the start of the warp's block) -----
 // Three kinematic states X = 0, 1, 2: configuration cfg + X*S and link transforms T + X*L12.  States 0 / 1
 // ping-pong between "previous" and "current" configuration of a microstep, state 2 is the scratch state of
@@ -110,6 +119,7 @@ struct WarpLayout {
     int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
     int qr;       // 4 * S
     int cand;     // 64: candidate records of collect_corrections
+    int vars;     // WarpVars (kWarpVarsDoubles) + 2 * S doubles of PID state
     int stats;    // FKS_NUM_STATS u64 counters of this warp
     int flags;    // 1 (u32 FKS_FLAG_* bits raised by any lane)
     int total;
@@ -142,6 +152,7 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.tn = o; o += w.noise_batch * S;
     w.qr = o; o += 4 * S;
     w.cand = o; o += 64;
+    w.vars = o; o += kWarpVarsDoubles + 2 * S;
     w.stats = o; o += FKS_NUM_STATS;
     w.flags = o; o += 1;
     w.total = (o + 1) & ~1;

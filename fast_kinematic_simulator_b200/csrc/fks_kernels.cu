@@ -1620,16 +1620,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
     const double target_microstep_distance = a.env.map_res * 0.125;
     const double allowed_microstep_distance = a.env.map_res * 1.0;
 
-    // ---- warp state (uniform across the lanes unless noted) ----------------------------------------
+    // ---- warp state -----------------------------------------------------------------------------------
+    // Hot control variables stay in registers; the bookkeeping of the particle lives in the warp's shared block
+    // (WarpVars: one copy per warp instead of one per lane -- at 64 registers per thread it would otherwise spill).
     int after = AF_FETCH;
     int op = OP_NONE, op_in = 0, op_out = 0, op_u = 0, op_tn = -1, op_derive = 0, measure = M_NONE;
     int cur = 0, prev = 0;
-    unsigned long long pid = 0ull, tape_pos = 0ull, tape_end = 0ull;
-    unsigned step = 0u, micro = 0u, number_microsteps = 0u, resolver_iterations = 0u;
-    unsigned flags = 0u, n_micro_total = 0u, n_iter_total = 0u, n_steps = 0u;
-    bool collided = false, any_resolve_failed = false, step_collided = false, step_failed = false, step_stopped = false;
-    double scaling = 0.0;
-    double pid_integral = 0.0, pid_last_error = 0.0;  // per lane: lane i owns axis i
+    WarpVars* wv = reinterpret_cast<WarpVars*>(ws + wl.vars);
+    double* pid_state = ws + wl.vars + kWarpVarsDoubles;  // [0..S) integral, [S..2S) last error: lane i owns axis i
     double m_result = 0.0;
     unsigned cc = 0u;
 
@@ -1679,35 +1677,40 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         // 2 = begin microstep, 3 = end of controller step, 4 = end of particle.
         int ev = 0;
         while (op == OP_NONE && !want_solve && after != AF_DONE) {
+            __syncwarp();  // the WarpVars updates below are read-modify-writes done by every lane with the same value
             if (ev == 0) {
                 switch (after) {
                     case AF_FETCH: {
-                        if (lane == 0) pid = (unsigned long long)atomicAdd(a.counter, 1u);
-                        pid = __shfl_sync(FKS_FULL, pid, 0);
-                        if (pid >= a.n_particles) {
+                        unsigned long long next_id = 0ull;
+                        if (lane == 0) next_id = (unsigned long long)atomicAdd(a.counter, 1u);
+                        next_id = __shfl_sync(FKS_FULL, next_id, 0);
+                        wv->pid = next_id;  // every lane stores the same value
+                        if (next_id >= a.n_particles) {
                             after = AF_DONE;
                             break;
                         }
                         // ForwardSimulateRobot (spcs:824-829): clone + ResetPosition(start)
                         cur = 0;
-                        const double* start = a.starts + (size_t)pid * stride;
-                        const double* tgt = a.targets + (a.n_targets == a.n_particles ? (size_t)pid * stride : 0);
+                        const double* start = a.starts + (size_t)wv->pid * stride;
+                        const double* tgt = a.targets + (a.n_targets == a.n_particles ? (size_t)wv->pid * stride : 0);
                         if (lane < stride) {
                             ws[wl.cfg + lane] = start[lane];
                             ws[wl.target + lane] = tgt[lane];
                         }
                         if (lane == 0) *reinterpret_cast<unsigned*>(ws + wl.flags) = 0u;
                         __syncwarp();
-                        pid_integral = 0.0;  // pid:98-102 zeroed
-                        pid_last_error = 0.0;
-                        tape_pos = tape_end = 0ull;
-                        if (a.noise_mode == FKS_NOISE_INJECTED) {
-                            tape_pos = a.tape_off[pid];
-                            tape_end = a.tape_off[pid + 1];
+                        if (lane < S) {  // pid:98-102 zeroed
+                            pid_state[lane] = 0.0;
+                            pid_state[S + lane] = 0.0;
                         }
-                        collided = any_resolve_failed = false;
-                        flags = n_micro_total = n_iter_total = n_steps = 0u;
-                        step = 0u;
+                        wv->tape_pos = wv->tape_end = 0ull;
+                        if (a.noise_mode == FKS_NOISE_INJECTED) {
+                            wv->tape_pos = a.tape_off[wv->pid];
+                            wv->tape_end = a.tape_off[wv->pid + 1];
+                        }
+                        wv->collided = wv->any_resolve_failed = false;
+                        wv->flags = wv->n_micro_total = wv->n_iter_total = wv->n_steps = 0u;
+                        wv->step = 0u;
                         op = OP_KIN;
                         op_out = cur;
                         op_derive = 1;
@@ -1719,9 +1722,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         break;
                     case AF_EST_RU: {  // spcs:1559-1568
                         const double ratio = m_result / target_microstep_distance;
-                        number_microsteps = (unsigned)ceil(ratio);
-                        if (number_microsteps < 1u) number_microsteps = 1u;
-                        if (lane < D) ws[wl.du + lane] = ws[wl.ru + lane] / (double)number_microsteps;
+                        wv->number_microsteps = (unsigned)ceil(ratio);
+                        if (wv->number_microsteps < 1u) wv->number_microsteps = 1u;
+                        if (lane < D) ws[wl.du + lane] = ws[wl.ru + lane] / (double)wv->number_microsteps;
                         __syncwarp();
                         op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.du; op_tn = -1; op_derive = 0;
                         measure = M_MOTION;
@@ -1729,33 +1732,33 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         break;
                     }
                     case AF_EST_DU:  // spcs:1569-1575
-                        if (m_result > allowed_microstep_distance) flags |= FKS_FLAG_WOULD_ASSERT_MICROSTEP;
-                        step_collided = step_failed = step_stopped = false;
-                        micro = 0u;
+                        if (m_result > allowed_microstep_distance) wv->flags |= FKS_FLAG_WOULD_ASSERT_MICROSTEP;
+                        wv->step_collided = wv->step_failed = wv->step_stopped = false;
+                        wv->micro = 0u;
                         ev = 2;
                         break;
                     case AF_MICRO_CHECK: {  // spcs:1608-1625
                         const bool in_collision = (cc & 1u) != 0u;
-                        if (in_collision) step_collided = true;
+                        if (in_collision) wv->step_collided = true;
                         if (in_collision && a.allow_contacts) {
-                            resolver_iterations = 0u;
-                            scaling = sp.initial_step;
+                            wv->resolver_iterations = 0u;
+                            wv->scaling = sp.initial_step;
                             want_solve = true;
                         } else if (in_collision) {  // spcs:1769-1786
                             if (lane == 0) add_stat(wb, FKS_STAT_SUCCESSFUL_RESOLVES, 1ull);
                             cur = prev;
-                            step_stopped = true;
+                            wv->step_stopped = true;
                             op = OP_KIN; op_out = cur; op_derive = 1;
                             after = AF_STOP_KIN;
                         } else {
-                            micro++;
-                            ev = (micro < number_microsteps) ? 2 : 3;
+                            wv->micro++;
+                            ev = (wv->micro < wv->number_microsteps) ? 2 : 3;
                         }
                         break;
                     }
                     case AF_EST_RAW: {  // spcs:1681-1689
                         const double step_fraction = fmax(m_result / allowed_microstep_distance, 1.0);
-                        if (lane < D) ws[wl.stepv + lane] = (ws[wl.raw + lane] / step_fraction) * fabs(scaling);
+                        if (lane < D) ws[wl.stepv + lane] = (ws[wl.raw + lane] / step_fraction) * fabs(wv->scaling);
                         __syncwarp();
                         op = OP_APPLY; op_in = cur; op_out = cur; op_u = wl.stepv; op_tn = -1; op_derive = 1;
                         measure = M_CHECK;
@@ -1764,33 +1767,33 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                     }
                     case AF_RESOLVE_CHECK: {  // spcs:1694-1761
                         const bool in_collision = (cc & 1u) != 0u;
-                        resolver_iterations++;
-                        n_iter_total++;
-                        if (resolver_iterations > sp.max_iters) {  // spcs:1705-1746
+                        wv->resolver_iterations++;
+                        wv->n_iter_total++;
+                        if (wv->resolver_iterations > sp.max_iters) {  // spcs:1705-1746
                             if (lane == 0) {
                                 add_stat(wb, FKS_STAT_UNSUCCESSFUL_RESOLVES, 1ull);
                                 add_stat(wb, (cc & 2u) ? FKS_STAT_UNSUCCESSFUL_SELF_COLLISION_RESOLVES : FKS_STAT_UNSUCCESSFUL_ENV_COLLISION_RESOLVES, 1ull);
                             }
                             cur = prev;  // return previous_configuration
-                            step_collided = true;
-                            step_failed = true;
+                            wv->step_collided = true;
+                            wv->step_failed = true;
                             op = OP_KIN; op_out = cur; op_derive = 1;
                             after = AF_FAIL_KIN;
                             break;
                         }
-                        if ((resolver_iterations % sp.decay_iters) == 0u) {  // spcs:1747-1761
-                            if (scaling >= 0.0) {
-                                scaling = scaling * sp.decay_rate;
-                                if (scaling < sp.min_scaling) scaling = -sp.min_scaling;
+                        if ((wv->resolver_iterations % sp.decay_iters) == 0u) {  // spcs:1747-1761
+                            if (wv->scaling >= 0.0) {
+                                wv->scaling = wv->scaling * sp.decay_rate;
+                                if (wv->scaling < sp.min_scaling) wv->scaling = -sp.min_scaling;
                             } else {
-                                scaling = -sp.min_scaling;
+                                wv->scaling = -sp.min_scaling;
                             }
                         }
                         if (in_collision) {
                             want_solve = true;
                         } else {
-                            micro++;
-                            ev = (micro < number_microsteps) ? 2 : 3;
+                            wv->micro++;
+                            ev = (wv->micro < wv->number_microsteps) ? 2 : 3;
                         }
                         break;
                     }
@@ -1807,9 +1810,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             } else if (ev == 1) {
                 // ---- begin controller step: GenerateControlAction (tnuva:179-198, :384-412, :598-614) --------
                 ev = 0;
-                n_steps++;
+                wv->n_steps++;
                 double* cfg = ws + wl.cfg + cur * S;
-                if (!a.allow_contacts) {  // a colliding step is discarded as a whole: keep the step's start (spcs:904-909)
+                if (!a.allow_contacts) {  // a colliding wv->step is discarded as a whole: keep the wv->step's start (spcs:904-909)
                     if (lane < stride) ws[wl.scfg + lane] = cfg[lane];
                     __syncwarp();
                 }
@@ -1838,36 +1841,36 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         err = ws[wl.target + lane] - cfg[lane];
                         if (rb.joints[rb.active_joint[lane]].type == FKS_JOINT_CONTINUOUS) err = wrap_angle(err);
                     }
-                    // SimplePIDController::ComputeFeedbackTerm (pid:122-135)
+                    // SimplePIDController::ComputeFeedbackTerm (wv->pid:122-135)
                     const DevAxis& ax = rb.axes[lane];
                     const double dt = sp.interval;
-                    const double timestep_error_integral = ((err * 0.5) + (pid_last_error * 0.5)) * dt;
-                    const double new_error_integral = pid_integral + timestep_error_integral;
-                    pid_integral = fmax(-ax.iclamp, fmin(ax.iclamp, new_error_integral));
-                    const double error_derivative = (err - pid_last_error) / dt;
-                    pid_last_error = err;
-                    const double term = (err * ax.kp) + (pid_integral * ax.ki) + (error_derivative * ax.kd);
+                    const double timestep_error_integral = ((err * 0.5) + (pid_state[S + lane] * 0.5)) * dt;
+                    const double new_error_integral = pid_state[lane] + timestep_error_integral;
+                    pid_state[lane] = fmax(-ax.iclamp, fmin(ax.iclamp, new_error_integral));
+                    const double error_derivative = (err - pid_state[S + lane]) / dt;
+                    pid_state[S + lane] = err;
+                    const double term = (err * ax.kp) + (pid_state[lane] * ax.ki) + (error_derivative * ax.kd);
                     const double action = actuate(wb, ax, term, false, 0.0);
                     ws[wl.act + lane] = action;
                     ws[wl.ru + lane] = action * sp.interval;  // real_control_input (spcs:1549)
                 }
                 __syncwarp();
-                // ResolveForwardSimulation (spcs:1546-1816) starts with the motion estimate of the whole step
+                // ResolveForwardSimulation (spcs:1546-1816) starts with the motion estimate of the whole wv->step
                 op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.ru; op_tn = -1; op_derive = 0;
                 measure = M_MOTION;
                 after = AF_EST_RU;
             } else if (ev == 2) {
                 // ---- begin microstep (spcs:1590-1608) ---------------------------------------------------------
                 ev = 0;
-                n_micro_total++;
+                wv->n_micro_total++;
                 const int nb = wl.noise_batch;
-                const int slot = (int)(micro % (unsigned)nb);
+                const int slot = (int)(wv->micro % (unsigned)nb);
                 if (slot == 0) {
-                    const unsigned left = number_microsteps - micro;
-                    fill_noise(wb, pid, step, micro, left < (unsigned)nb ? (int)left : nb, tape_pos, tape_end);
+                    const unsigned left = wv->number_microsteps - wv->micro;
+                    fill_noise(wb, wv->pid, wv->step, wv->micro, left < (unsigned)nb ? (int)left : nb, wv->tape_pos, wv->tape_end);
                 }
-                if (a.noise_mode == FKS_NOISE_INJECTED && tape_pos + (unsigned long long)D > tape_end) flags |= FKS_FLAG_TAPE_EXHAUSTED;
-                tape_pos += (unsigned long long)D;
+                if (a.noise_mode == FKS_NOISE_INJECTED && wv->tape_pos + (unsigned long long)D > wv->tape_end) wv->flags |= FKS_FLAG_TAPE_EXHAUSTED;
+                wv->tape_pos += (unsigned long long)D;
                 // previous_configuration (spcs:1597) is the old current state; the new one is built in the other buffer
                 prev = cur;
                 cur ^= 1;
@@ -1877,21 +1880,21 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             } else if (ev == 3) {
                 // ---- end of controller step (spcs:1797-1815, then back in ForwardSimulateMutableRobot :873-909) ----
                 ev = 0;
-                if (!step_failed && !step_stopped && lane == 0) {
+                if (!wv->step_failed && !wv->step_stopped && lane == 0) {
                     add_stat(wb, FKS_STAT_SUCCESSFUL_RESOLVES, 1ull);
-                    add_stat(wb, step_collided ? FKS_STAT_COLLISION_RESOLVES : FKS_STAT_FREE_RESOLVES, 1ull);
+                    add_stat(wb, wv->step_collided ? FKS_STAT_COLLISION_RESOLVES : FKS_STAT_FREE_RESOLVES, 1ull);
                 }
                 bool ends = false;
-                if (a.allow_contacts || !step_collided) {
-                    if (step_collided) collided = true;
-                    if (step_failed) {
-                        flags |= FKS_FLAG_RESOLVE_FAILED;
+                if (a.allow_contacts || !wv->step_collided) {
+                    if (wv->step_collided) wv->collided = true;
+                    if (wv->step_failed) {
+                        wv->flags |= FKS_FLAG_RESOLVE_FAILED;
                         if (sp.failed_ends_motion) {
-                            flags |= FKS_FLAG_ENDED_BY_FAILURE;
+                            wv->flags |= FKS_FLAG_ENDED_BY_FAILURE;
                             ends = true;
                         }
-                        any_resolve_failed = true;
-                    } else if (any_resolve_failed) {
+                        wv->any_resolve_failed = true;
+                    } else if (wv->any_resolve_failed) {
                         if (lane == 0) add_stat(wb, FKS_STAT_RECOVERED_UNSUCCESSFUL_RESOLVES, 1ull);
                     }
                     if (!ends && sp.shortcut_distance > 0.0) {  // ComputeConfigurationDistanceTo (spcs:898); never < 0
@@ -1927,37 +1930,37 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             dist = sqrt(sacc);
                         }
                         if (dist < sp.shortcut_distance) {
-                            flags |= FKS_FLAG_ENDED_BY_SHORTCUT;
+                            wv->flags |= FKS_FLAG_ENDED_BY_SHORTCUT;
                             ends = true;
                         }
                     }
-                    step++;
-                    if (!ends && step < sp.n_steps) ev = 1;
+                    wv->step++;
+                    if (!ends && wv->step < sp.n_steps) ev = 1;
                     else ev = 4;
                 } else {
-                    // robot->SetPosition(resolved_configuration) is skipped: the particle stays where the step began
+                    // robot->SetPosition(resolved_configuration) is skipped: the particle stays where the wv->step began
                     if (lane < stride) ws[wl.cfg + cur * S + lane] = ws[wl.scfg + lane];
                     __syncwarp();
-                    flags |= FKS_FLAG_ENDED_BY_NOCONTACT;
+                    wv->flags |= FKS_FLAG_ENDED_BY_NOCONTACT;
                     op = OP_KIN; op_out = cur; op_derive = 1;
                     after = AF_NOCONTACT_KIN;
                 }
             } else {
                 // ---- end of particle: result record = cfg_stride doubles + fks_result_tail -------------------
                 ev = 0;
-                if (collided) flags |= FKS_FLAG_DID_CONTACT;
+                if (wv->collided) wv->flags |= FKS_FLAG_DID_CONTACT;
                 __syncwarp();
-                flags |= *reinterpret_cast<const unsigned*>(ws + wl.flags);
-                char* rec = a.results + (size_t)pid * a.rec_stride;
+                wv->flags |= *reinterpret_cast<const unsigned*>(ws + wl.flags);
+                char* rec = a.results + (size_t)wv->pid * a.rec_stride;
                 if (lane < stride) reinterpret_cast<double*>(rec)[lane] = ws[wl.cfg + cur * S + lane];
                 if (lane == 0) {
                     unsigned* tail = reinterpret_cast<unsigned*>(rec + (size_t)stride * 8);
-                    tail[0] = flags;
-                    tail[1] = n_micro_total;
-                    tail[2] = n_iter_total;
-                    tail[3] = n_steps;
-                    add_stat(wb, FKS_STAT_TOTAL_MICROSTEPS, n_micro_total);
-                    add_stat(wb, FKS_STAT_TOTAL_RESOLVER_ITERATIONS, n_iter_total);
+                    tail[0] = wv->flags;
+                    tail[1] = wv->n_micro_total;
+                    tail[2] = wv->n_iter_total;
+                    tail[3] = wv->n_steps;
+                    add_stat(wb, FKS_STAT_TOTAL_MICROSTEPS, wv->n_micro_total);
+                    add_stat(wb, FKS_STAT_TOTAL_RESOLVER_ITERATIONS, wv->n_iter_total);
                 }
                 __syncwarp();
                 after = AF_FETCH;
@@ -1999,8 +2002,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #endif
             if (rows == 0) {
                 // Eigen would return an empty vector and ApplyControlInput would assert; documented device
-                // behaviour: zero correction step
-                flags |= FKS_FLAG_EMPTY_JACOBIAN;
+                // behaviour: zero correction wv->step
+                wv->flags |= FKS_FLAG_EMPTY_JACOBIAN;
                 if (lane < D) ws[wl.raw + lane] = 0.0;
                 __syncwarp();
             } else if (rows <= 32 && KIND == FKS_ROBOT_SE2) {
@@ -2033,7 +2036,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             m_result = max_motion(wb, cur, 2);
             {  // spcs:1681-1689
                 const double step_fraction = fmax(m_result / allowed_microstep_distance, 1.0);
-                if (lane < D) ws[wl.stepv + lane] = (ws[wl.raw + lane] / step_fraction) * fabs(scaling);
+                if (lane < D) ws[wl.stepv + lane] = (ws[wl.raw + lane] / step_fraction) * fabs(wv->scaling);
                 __syncwarp();
             }
             op = OP_APPLY; op_in = cur; op_out = cur; op_u = wl.stepv; op_tn = -1; op_derive = 1;
