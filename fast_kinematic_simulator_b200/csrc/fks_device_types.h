@@ -117,7 +117,7 @@ struct WarpLayout {
     int jaxis, jorig;  // 3 * J each
     int target, scfg, act, ru, du, raw, stepv;  // S each
     int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
-    int qr;       // 4 * S
+    int qr;       // QR bookkeeping: max(4 * S, 80) doubles (register QR parks R, 1/diag and Q^T c here)
     int cand;     // 64: candidate records of collect_corrections
     int vars;     // WarpVars (kWarpVarsDoubles) + 2 * S doubles of PID state
     int stats;    // FKS_NUM_STATS u64 counters of this warp
@@ -150,7 +150,7 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.raw = o; o += S;
     w.stepv = o; o += S;
     w.tn = o; o += w.noise_batch * S;
-    w.qr = o; o += 4 * S;
+    w.qr = o; o += (4 * S > 80 ? 4 * S : 80);
     w.cand = o; o += 64;
     w.vars = o; o += kWarpVarsDoubles + 2 * S;
     w.stats = o; o += FKS_NUM_STATS;
