@@ -515,10 +515,17 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
         const int v = std::atoi(ev);
         if (v >= 1 && v <= kWarpsPerBlock) wpb = v;
     }
-    s->dyn_smem = simulate_smem_plan(&s->plan, h.L, h.J, h.D, h.P, robot->stride, wpb);
+    // largest lock-step CTA whose shared memory fits the SM (robots with many links / points get fewer warps per CTA)
+    int rc = 0;
+    for (;; wpb = (wpb > 4) ? wpb - 4 : wpb - 1) {
+        s->dyn_smem = simulate_smem_plan(&s->plan, h.L, h.J, h.D, h.P, robot->stride, wpb);
+        s->kinfo.max_blocks_per_sm = 0;
+        rc = simulate_kernel_info(h.kind, s->dyn_smem, wpb, &s->kinfo);
+        if ((rc == 0 && s->kinfo.max_blocks_per_sm >= 1) || wpb <= 1) break;
+        cudaGetLastError();
+    }
     s->plan.cull_mode = 1;
     if (const char* ev = std::getenv("FKS_CULL")) s->plan.cull_mode = std::atoi(ev);  // developer knob
-    int rc = simulate_kernel_info(h.kind, s->dyn_smem, wpb, &s->kinfo);
     if (rc != 0) { delete s; return cuda_fail((cudaError_t)rc, "fks_sim_create: kernel attributes"); }
     if (s->kinfo.max_blocks_per_sm < 1) { delete s; return fail(FKS_ERR_UNSUPPORTED, "fks_sim_create: robot does not fit one CTA's shared memory"); }
     cudaDeviceProp prop;

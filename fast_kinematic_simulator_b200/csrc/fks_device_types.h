@@ -117,8 +117,8 @@ struct WarpLayout {
     int jaxis, jorig;  // 3 * J each
     int target, scfg, act, ru, du, raw, stepv;  // S each
     int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
-    int qr;       // QR bookkeeping: max(4 * S, 80) doubles (register QR parks R, 1/diag and Q^T c here)
-    int cand;     // 64: candidate records of collect_corrections
+    int qr;       // QR bookkeeping: max(4 * S, 64) doubles (the register QR parks R, 1/diag and Q^T c here: NC^2 + 2 NC <= 63)
+    int cand;     // 32 doubles = 32 candidate records of collect_corrections
     int vars;     // WarpVars (kWarpVarsDoubles) + 2 * S doubles of PID state
     int stats;    // FKS_NUM_STATS u64 counters of this warp
     int flags;    // 1 (u32 FKS_FLAG_* bits raised by any lane)
@@ -150,8 +150,8 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.raw = o; o += S;
     w.stepv = o; o += S;
     w.tn = o; o += w.noise_batch * S;
-    w.qr = o; o += (4 * S > 80 ? 4 * S : 80);
-    w.cand = o; o += 64;
+    w.qr = o; o += (4 * S > 64 ? 4 * S : 64);
+    w.cand = o; o += 32;
     w.vars = o; o += kWarpVarsDoubles + 2 * S;
     w.stats = o; o += FKS_NUM_STATS;
     w.flags = o; o += 1;

@@ -35,6 +35,9 @@
 namespace fksdev {
 
 #define FKS_FULL 0xffffffffu
+#ifndef FKS_SKIP_SINGLE_ESTIMATE
+#define FKS_SKIP_SINGLE_ESTIMATE 1
+#endif
 #ifndef FKS_MIN_BLOCKS
 #define FKS_MIN_BLOCKS 1  // lock-step CTAs (16 warps each) per SM the register allocation is planned for
 #endif
@@ -489,7 +492,10 @@ __device__ __forceinline__ unsigned active_links(const DevEnv& e, const DevRobot
     }
     return __ballot_sync(FKS_FULL, active);
 }
-constexpr int kCandShared = 64;  // candidate points of collect_corrections kept in shared memory
+#ifndef FKS_CAND_SHARED
+#define FKS_CAND_SHARED 32
+#endif
+constexpr int kCandShared = FKS_CAND_SHARED;  // candidate points of collect_corrections kept in shared memory (<= 32)
 
 // CheckEnvironmentCollision (spcs:921-981) of the CURRENT state (G and T[X]); collision_threshold = 0.0 (spcs:424)
 __device__ __noinline__ bool check_env(int wb, int X, int use_cull) {
@@ -1359,21 +1365,21 @@ __device__ __noinline__ void colpiv_qr_solve(int wb, int rows, int cols, int x_o
 }
 
 // Register-resident variant of the same solve for the common small systems: rows <= 32 * R, NC columns known
-// at compile time (3 / 6 / 7: the reference's three robots).  Lane l keeps rows l, l + 32, ... of the not yet
-// eliminated columns and of the right-hand side in registers; rows beyond `rows` are zero, which leaves every
-// Householder quantity unchanged.  The step loop is ROLLED (the fully unrolled version was 9 000 instructions per
-// instance and thrashed the instruction cache): the pivot column is always brought to register column 0, and the
-// finished column is shifted out after each step, its row of R being parked in shared memory for the back
-// substitution.  The critical path per step is two interleaved shuffle trees, one square root and one division:
-//   * tree 1 sums, for every remaining column, the squares of the rows below the diagonal row k; with the
-//     diagonal-row entries broadcast from lane k this gives all residual column norms (pivot selection, rank cut)
-//     AND the tail norm of whichever column is picked.  Eigen keeps these norms by LAPACK-style downdating (a
-//     division and a square root per column per step, recomputed when they lose half their digits); the direct sums
-//     here are the exact quantities those approximate, so the pivot order only differs on ties that the oracle
-//     reports as SENS_PIVOT_TIE / SENS_RANK_CUT;
+// at compile time (3 / 6 / 7: the reference's three robots).  Lane l keeps rows l, l + 32, ... of all NC columns
+// and of the right-hand side in registers; rows beyond `rows` are zero, which leaves every Householder quantity
+// unchanged.  The critical path per Householder step is two interleaved shuffle trees, one square root and one
+// division:
+//   * tree 1 sums, for every not-yet-eliminated column, the squares of the rows below the diagonal row k; with
+//     the diagonal-row entries broadcast from lane k this gives all residual column norms (pivot selection, rank
+//     cut) AND the tail norm of whichever column is picked.  Eigen keeps these norms by LAPACK-style downdating
+//     (a division and a square root per column per step, recomputed when they lose half their digits); the direct
+//     sums here are the exact quantities those approximate, so the pivot order only differs on ties that the
+//     oracle reports as SENS_PIVOT_TIE / SENS_RANK_CUT;
 //   * tree 2 forms the dot products of the reflector with all trailing columns and the right-hand side.
-// Column order after each swap + shift is exactly Eigen's (first maximum wins).  Reflectors are applied to the
-// right-hand side as they are formed (only those below the rank cut, as Eigen's solve does).
+// Column swaps are register selects; reflectors are applied to the right-hand side as they are formed (only those
+// below the rank cut, as Eigen's solve does).  The step loop is fully unrolled on purpose: a rolled variant (pivot
+// column rotated to register 0, finished rows of R parked in shared memory) is 3.5x smaller but measured 15 % slower
+// on the contact workloads (profiles/r1_v1_free_running.md).
 template <int NC, int R>
 __device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
     const Frame& fr = frame();
@@ -1381,166 +1387,141 @@ __device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
     double* ws = wsd(wb);
     const double* A = reinterpret_cast<const double*>(scratch_slot() + fr.a.sl.jstore);
     const int ld = fr.a.sl.ldj;
-    double* Rrow = ws + fr.a.wl.qr;    // [NC][NC] rows of R (upper triangle, in elimination order)
-    double* rdiag = Rrow + NC * NC;    // 1 / R(k,k)
-    double* cvec = rdiag + NC;         // Q^T c
-    double a[R][NC], bv[R];            // slot s holds row lane + 32 s
+    double a[R][NC + 1];  // slot s holds row lane + 32 s; column index NC = right-hand side
 #pragma unroll
-    for (int sl = 0; sl < R; sl++) {
-        const bool in = lane + 32 * sl < rows;
+    for (int sl = 0; sl < R; sl++)
 #pragma unroll
-        for (int c = 0; c < NC; c++) a[sl][c] = in ? A[(size_t)c * ld + lane + 32 * sl] : 0.0;
-        bv[sl] = in ? A[(size_t)NC * ld + lane + 32 * sl] : 0.0;
-    }
+        for (int c = 0; c <= NC; c++) a[sl][c] = (lane + 32 * sl < rows) ? A[(size_t)c * ld + lane + 32 * sl] : 0.0;
     const int size = rows < NC ? rows : NC;
     const double eps = DBL_EPSILON;
     double threshold_helper = 0.0;
     int nonzero_pivots = size;
     unsigned transp = 0u;
     bool near_cut = false;
-#pragma unroll 1
-    for (int k = 0; k < size; k++) {
-        const int rem = NC - k;            // remaining columns live in register columns 0 .. rem-1
-        const bool below = lane > k;       // slot 0 rows below the diagonal (higher slots always are)
-        // ---- tree 1: squares below row k of every remaining column ---------------------------------------
-        double sq[NC];
+    double rdiag[NC];  // 1 / R(k,k)
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-            double v = below ? a[0][c] * a[0][c] : 0.0;
+    for (int k = 0; k < NC; k++) {
+        rdiag[k] = 0.0;
+        if (k < size) {
+            // ---- tree 1: squares below row k of every remaining column -------------------------------------
+            const bool below = lane > k;  // slot 0 rows below the diagonal (higher slots always are)
+            double sq[NC];
 #pragma unroll
-            for (int sl = 1; sl < R; sl++) v += a[sl][c] * a[sl][c];
-            sq[c] = v;
-        }
+            for (int j = k; j < NC; j++) {
+                double v = below ? a[0][j] * a[0][j] : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int c = 0; c < NC; c++) sq[c] += __shfl_xor_sync(FKS_FULL, sq[c], o);
-        double dk[NC], nsq[NC];  // entry of row k, squared residual norm (rows >= k)
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            dk[c] = __shfl_sync(FKS_FULL, a[0][c], k);
-            nsq[c] = dk[c] * dk[c] + sq[c];
-        }
-        if (k == 0) {  // threshold from the largest initial column norm (Eigen: colNormsUpdated.maxCoeff())
-            double mx = 0.0;
-#pragma unroll
-            for (int c = 0; c < NC; c++) mx = fmax(mx, nsq[c]);
-            threshold_helper = (mx * (eps * eps)) / (double)rows;
-        }
-        int biggest = 0;
-        double big_sq = nsq[0], tail_sq = sq[0], c0 = dk[0];
-#pragma unroll
-        for (int c = 1; c < NC; c++)
-            if (c < rem && nsq[c] > big_sq) {
-                big_sq = nsq[c];
-                biggest = c;
-                tail_sq = sq[c];
-                c0 = dk[c];
-            }
-        const double cut = threshold_helper * (double)(rows - k);
-        if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
-        if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
-        transp |= (unsigned)(k + biggest) << (4 * k);
-        // ---- swap register columns 0 <-> biggest ---------------------------------------------------------
-#pragma unroll
-        for (int c = 1; c < NC; c++)
-            if (c == biggest) {
-#pragma unroll
-                for (int sl = 0; sl < R; sl++) {
-                    const double t = a[sl][0];
-                    a[sl][0] = a[sl][c];
-                    a[sl][c] = t;
-                }
-            }
-        // ---- makeHouseholderInPlace on col(k).tail(rows - k) ---------------------------------------------
-        double tau, beta;
-        if (tail_sq <= DBL_MIN) {
-            tau = 0.0;
-            beta = c0;
-            if (below) a[0][0] = 0.0;
-#pragma unroll
-            for (int sl = 1; sl < R; sl++) a[sl][0] = 0.0;
-        } else {
-            beta = sqrt(c0 * c0 + tail_sq);
-            if (c0 >= 0.0) beta = -beta;
-            const double denom = c0 - beta;
-            if (below) a[0][0] = a[0][0] / denom;
-#pragma unroll
-            for (int sl = 1; sl < R; sl++) a[sl][0] = a[sl][0] / denom;
-            tau = (beta - c0) / beta;
-        }
-        const bool apply_b = nonzero_pivots > k;  // Eigen's solve applies the first nonzero_pivots reflectors to c
-        // ---- applyHouseholderOnTheLeft to the trailing columns (and the right-hand side) -----------------
-        if (rows - k == 1) {
-            if (lane == k) {
-#pragma unroll
-                for (int c = 1; c < NC; c++) a[0][c] *= (1.0 - tau);
-                if (apply_b) bv[0] *= (1.0 - tau);
-            }
-        } else if (tau != 0.0) {
-            double dt[NC + 1];  // index NC = right-hand side
-#pragma unroll
-            for (int c = 1; c <= NC; c++) {
-                double v = below ? a[0][0] * (c < NC ? a[0][c] : bv[0]) : 0.0;
-#pragma unroll
-                for (int sl = 1; sl < R; sl++) v += a[sl][0] * (c < NC ? a[sl][c] : bv[sl]);
-                dt[c] = v;
+                for (int sl = 1; sl < R; sl++) v += a[sl][j] * a[sl][j];
+                sq[j] = v;
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int c = 1; c <= NC; c++) dt[c] += __shfl_xor_sync(FKS_FULL, dt[c], o);
+                for (int j = k; j < NC; j++) sq[j] += __shfl_xor_sync(FKS_FULL, sq[j], o);
+            double dk[NC], nsq[NC];  // entry of row k, squared residual norm (rows >= k)
 #pragma unroll
-            for (int c = 1; c < NC; c++) {
-                const double tmp = dt[c] + __shfl_sync(FKS_FULL, a[0][c], k);
-                if (lane == k) a[0][c] -= tau * tmp;
-                else if (below) a[0][c] -= (tau * a[0][0]) * tmp;
-#pragma unroll
-                for (int sl = 1; sl < R; sl++) a[sl][c] -= (tau * a[sl][0]) * tmp;
+            for (int j = k; j < NC; j++) {
+                dk[j] = __shfl_sync(FKS_FULL, a[0][j], k);
+                nsq[j] = dk[j] * dk[j] + sq[j];
             }
-            {
-                const double tmp = dt[NC] + __shfl_sync(FKS_FULL, bv[0], k);  // every lane takes part in the shuffle
-                if (apply_b) {
-                    if (lane == k) bv[0] -= tau * tmp;
-                    else if (below) bv[0] -= (tau * a[0][0]) * tmp;
+            if (k == 0) {  // threshold from the largest initial column norm (Eigen: colNormsUpdated.maxCoeff())
+                double mx = 0.0;
 #pragma unroll
-                    for (int sl = 1; sl < R; sl++) bv[sl] -= (tau * a[sl][0]) * tmp;
+                for (int j = 0; j < NC; j++) mx = fmax(mx, nsq[j]);
+                threshold_helper = (mx * (eps * eps)) / (double)rows;
+            }
+            int biggest = k;
+            double big_sq = nsq[k];
+#pragma unroll
+            for (int j = k + 1; j < NC; j++)
+                if (nsq[j] > big_sq) {
+                    big_sq = nsq[j];
+                    biggest = j;
+                }
+            const double cut = threshold_helper * (double)(rows - k);
+            if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
+            if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
+            transp |= (unsigned)biggest << (4 * k);
+            // ---- swap columns k <-> biggest (registers, runtime `biggest`) ----------------------------------
+            double tail_sq = sq[k], c0 = dk[k];
+#pragma unroll
+            for (int j = k + 1; j < NC; j++)
+                if (j == biggest) {
+                    tail_sq = sq[j];
+                    c0 = dk[j];
+#pragma unroll
+                    for (int sl = 0; sl < R; sl++) {
+                        const double t = a[sl][k];
+                        a[sl][k] = a[sl][j];
+                        a[sl][j] = t;
+                    }
+                }
+            // ---- makeHouseholderInPlace on col(k).tail(rows - k) ---------------------------------------------
+            double tau, beta;
+            if (tail_sq <= DBL_MIN) {
+                tau = 0.0;
+                beta = c0;
+                if (below) a[0][k] = 0.0;
+#pragma unroll
+                for (int sl = 1; sl < R; sl++) a[sl][k] = 0.0;
+            } else {
+                beta = sqrt(c0 * c0 + tail_sq);
+                if (c0 >= 0.0) beta = -beta;
+                const double denom = c0 - beta;
+                if (below) a[0][k] = a[0][k] / denom;
+#pragma unroll
+                for (int sl = 1; sl < R; sl++) a[sl][k] = a[sl][k] / denom;
+                tau = (beta - c0) / beta;
+            }
+            rdiag[k] = 1.0 / beta;
+            if (lane == k) a[0][k] = beta;
+            const bool apply_b = nonzero_pivots > k;  // Eigen's solve applies the first nonzero_pivots reflectors to c
+            // ---- applyHouseholderOnTheLeft to the trailing columns (and the right-hand side) -----------------
+            if (rows - k == 1) {
+                if (lane == k) {
+#pragma unroll
+                    for (int j = k + 1; j < NC; j++) a[0][j] *= (1.0 - tau);
+                    if (apply_b) a[0][NC] *= (1.0 - tau);
+                }
+            } else if (tau != 0.0) {
+                double dt[NC + 1];
+#pragma unroll
+                for (int j = k + 1; j <= NC; j++) {
+                    double v = below ? a[0][k] * a[0][j] : 0.0;
+#pragma unroll
+                    for (int sl = 1; sl < R; sl++) v += a[sl][k] * a[sl][j];
+                    dt[j] = v;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int j = k + 1; j <= NC; j++) dt[j] += __shfl_xor_sync(FKS_FULL, dt[j], o);
+#pragma unroll
+                for (int j = k + 1; j <= NC; j++) {
+                    if (j == NC && !apply_b) continue;
+                    const double tmp = dt[j] + __shfl_sync(FKS_FULL, a[0][j], k);
+                    if (lane == k) a[0][j] -= tau * tmp;
+                    else if (below) a[0][j] -= (tau * a[0][k]) * tmp;
+#pragma unroll
+                    for (int sl = 1; sl < R; sl++) a[sl][j] -= (tau * a[sl][k]) * tmp;
                 }
             }
         }
-        // ---- park row k of R, shift the finished column out ----------------------------------------------
-        if (lane == k) {
-            rdiag[k] = 1.0 / beta;
-            cvec[k] = bv[0];
-#pragma unroll
-            for (int c = 1; c < NC; c++)
-                if (c < rem) Rrow[k * NC + k + c] = a[0][c];
-        }
-#pragma unroll
-        for (int sl = 0; sl < R; sl++) {
-#pragma unroll
-            for (int c = 0; c + 1 < NC; c++) a[sl][c] = a[sl][c + 1];
-            a[sl][NC - 1] = 0.0;
-        }
     }
     if (near_cut && lane == 0) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
-    __syncwarp();
+    // back substitution on the leading nz x nz upper triangle: lane i owns row i
+    double y[NC];
+    double sres = a[0][NC];
+#pragma unroll
+    for (int j = NC - 1; j >= 0; j--) {
+        y[j] = 0.0;
+        if (j < nonzero_pivots) {
+            y[j] = __shfl_sync(FKS_FULL, sres * rdiag[j], j);
+            sres -= a[0][j] * y[j];
+        }
+    }
     if (lane < NC) ws[x_off + lane] = 0.0;
     __syncwarp();
-    if (lane == 0 && nonzero_pivots > 0) {
-        // back substitution on the leading nz x nz upper triangle, then un-permute
-        double y[NC];
-#pragma unroll
-        for (int i = NC - 1; i >= 0; i--) {
-            y[i] = 0.0;
-            if (i < nonzero_pivots) {
-                double sacc = cvec[i];
-#pragma unroll
-                for (int j = i + 1; j < NC; j++)
-                    if (j < nonzero_pivots) sacc -= Rrow[i * NC + j] * y[j];
-                y[i] = sacc * rdiag[i];
-            }
-        }
+    if (lane == 0) {
         unsigned long long perm = 0xFEDCBA9876543210ull;
         for (int k = 0; k < size; k++) {
             const int t = (int)((transp >> (4 * k)) & 0xFu);
@@ -1693,7 +1674,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             else if (measure == M_CHECK) cc = check_collision<KIND>(wb, prev, cur, a.cull_mode == 2 ? ((cc & 1u) ? 0 : 1) : a.cull_mode);  // spcs:1418-1436
         }
         FKS_TICK(2)
+#ifdef FKS_BARRIER_BT
         named_barrier(bar_id, bar_threads);
+#endif
         FKS_TICK(3)
         // =========================== phase T: transitions =============================================
         if (!want_solve) {
@@ -1753,6 +1736,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         if (wv->number_microsteps < 1u) wv->number_microsteps = 1u;
                         if (lane < D) ws[wl.du + lane] = ws[wl.ru + lane] / (double)wv->number_microsteps;
                         __syncwarp();
+                        if (FKS_SKIP_SINGLE_ESTIMATE && wv->number_microsteps == 1u) {
+                            // control_input_step == real_control_input bit for bit (x / 1.0): its motion estimate
+                            // (spcs:1569) is the one just computed
+                            after = AF_EST_DU;
+                            break;
+                        }
                         op = OP_APPLY; op_in = cur; op_out = 2; op_u = wl.du; op_tn = -1; op_derive = 0;
                         measure = M_MOTION;
                         after = AF_EST_DU;
