@@ -515,54 +515,45 @@ __device__ __noinline__ bool check_env(int wb, int X, int use_cull) {
     // points of culled links cannot collide (and an out-of-bounds value below the threshold disables culling)
     const DevRobot& rb = fr.rb;
     unsigned links = (!use_cull || !e.cull || (double)oob < thr) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, 0.0);
-    // walk the 32-point chunks of the active links, kBatch chunks (independent gathers) at a time
-    int link = -1, pos = 0, end = 0;
-    for (;;) {
-        int cb[kBatch], ce[kBatch];  // chunk begin / end of the link
+    // walk the runs of consecutive active links (one contiguous point range each), kBatch x 32 points -- kBatch
+    // independent gathers per lane -- at a time
+    while (links) {
+        const int first = __ffs(links) - 1;
+        const int len = __ffs(~(links >> first)) - 1;
+        links &= ~(((len >= 32) ? 0xffffffffu : ((1u << len) - 1u)) << first);
+        const int end = rb.link_begin[first + len];
+        for (int pos = rb.link_begin[first]; pos < end; pos += 32 * kBatch) {
+            float f[kBatch];
 #pragma unroll
-        for (int k = 0; k < kBatch; k++) {
-            if (pos >= end && links) {  // next run of consecutive active links = one contiguous point range
-                link = __ffs(links) - 1;
-                const int len = __ffs(~(links >> link)) - 1;
-                links &= ~(((len >= 32) ? 0xffffffffu : ((1u << len) - 1u)) << link);
-                pos = rb.link_begin[link];
-                end = rb.link_begin[link + len];
-            }
-            cb[k] = pos;
-            ce[k] = end;
-            if (pos < end) pos += 32;
-        }
-        if (cb[0] >= ce[0]) break;
-        float f[kBatch];
-        Voxel vx[kBatch];
-#pragma unroll
-        for (int k = 0; k < kBatch; k++) {
-            const int p = cb[k] + lane;
-            f[k] = INFINITY;
-            vx[k].inb = false;
-            if (p < ce[k]) {
-                const double2 xy = pxy[p];
-                const PointZL zl = pzl[p];
-                vx[k] = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
-                f[k] = vx[k].inb ? sdf_cell(e, vx[k].x, vx[k].y, vx[k].z) : oob;
-            } else {
-                vx[k].inb = true;  // padding lane: never a collision
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kBatch; k++) {
-            if ((double)f[k] < thr) {
-                if ((double)f[k] < thr_deep || !vx[k].inb) {
-                    // deep inside, or out of bounds with an oob value below the threshold (EstimateDistance4d
-                    // out of bounds returns the same value, so both tiers reduce to one compare, spcs:943-975)
-                    hit = true;
-                } else {
-                    const int p = cb[k] + lane;
+            for (int k = 0; k < kBatch; k++) {
+                const int p = pos + 32 * k + lane;
+                f[k] = INFINITY;  // padding lanes and (with the usual +inf oob value) out-of-bounds points: no collision
+                if (p < end) {
                     const double2 xy = pxy[p];
                     const PointZL zl = pzl[p];
-                    double wx, wy, wz;
-                    apply_T(ws + wl.T + X * wl.L12 + 12 * zl.link, xy.x, xy.y, zl.z, wx, wy, wz);
-                    if (estimate_distance(wx, wy, wz, vx[k].x, vx[k].y, vx[k].z, f[k]) < thr) hit = true;
+                    const Voxel v = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
+                    f[k] = v.inb ? sdf_cell(e, v.x, v.y, v.z) : oob;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; k++) {
+                if ((double)f[k] < thr) {
+                    if ((double)f[k] < thr_deep) {
+                        hit = true;  // deep inside (or an oob value this low: EstimateDistance4d would return it too, spcs:943-975)
+                    } else {
+                        // second tier (rare): redo the voxel (same arithmetic, same result) and estimate the distance
+                        const int p = pos + 32 * k + lane;
+                        const double2 xy = pxy[p];
+                        const PointZL zl = pzl[p];
+                        const Voxel v = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
+                        if (!v.inb) {
+                            hit = true;
+                        } else {
+                            double wx, wy, wz;
+                            apply_T(ws + wl.T + X * wl.L12 + 12 * zl.link, xy.x, xy.y, zl.z, wx, wy, wz);
+                            if (estimate_distance(wx, wy, wz, v.x, v.y, v.z, f[k]) < thr) hit = true;
+                        }
+                    }
                 }
             }
         }
@@ -1039,51 +1030,38 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     // ---- pass 1 -----------------------------------------------------------------------------------
     int ncand = 0;
     unsigned links = (fr.a.cull_mode != 1 || !e.cull || has_self) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, 2.0 * res);
-    int link = -1, pos = 0, end = 0;
-    for (;;) {
-        int cb[kBatch], ce[kBatch];
+    while (links) {
+        const int first = __ffs(links) - 1;
+        const int len = __ffs(~(links >> first)) - 1;
+        links &= ~(((len >= 32) ? 0xffffffffu : ((1u << len) - 1u)) << first);
+        const int end = rb.link_begin[first + len];
+        for (int pos = rb.link_begin[first]; pos < end; pos += 32 * kBatch) {
+            float f[kBatch];
 #pragma unroll
-        for (int k = 0; k < kBatch; k++) {
-            if (pos >= end && links) {  // next run of consecutive active links = one contiguous point range
-                link = __ffs(links) - 1;
-                const int len = __ffs(~(links >> link)) - 1;
-                links &= ~(((len >= 32) ? 0xffffffffu : ((1u << len) - 1u)) << link);
-                pos = rb.link_begin[link];
-                end = rb.link_begin[link + len];
+            for (int k = 0; k < kBatch; k++) {
+                const int p = pos + 32 * k + lane;
+                f[k] = INFINITY;
+                if (p < end) {
+                    const double2 xy = pxy[p];
+                    const PointZL zl = pzl[p];
+                    const Voxel v = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
+                    if (v.inb) f[k] = sdf_cell(e, v.x, v.y, v.z);
+                }
             }
-            cb[k] = pos;
-            ce[k] = end;
-            if (pos < end) pos += 32;
-        }
-        if (cb[0] >= ce[0]) break;
-        float f[kBatch];
-        Voxel vx[kBatch];
 #pragma unroll
-        for (int k = 0; k < kBatch; k++) {
-            const int p = cb[k] + lane;
-            f[k] = INFINITY;
-            vx[k].x = vx[k].y = vx[k].z = 0;
-            vx[k].inb = false;
-            if (p < ce[k]) {
-                const double2 xy = pxy[p];
-                const PointZL zl = pzl[p];
-                vx[k] = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
-                if (vx[k].inb) f[k] = sdf_cell(e, vx[k].x, vx[k].y, vx[k].z);
+            for (int k = 0; k < kBatch; k++) {
+                const int p = pos + 32 * k + lane;
+                const bool is_near = f[k] < near;  // out of bounds / padding: +inf
+                const bool keep = (p < end) && (is_near || (has_self && (sflag[p] & 1)));
+                const unsigned mask = __ballot_sync(FKS_FULL, keep);
+                if (keep) {
+                    const int ci = ncand + __popc(mask & ((1u << lane) - 1u));
+                    const uint2 rec = make_uint2((unsigned)p | (is_near ? 0x80000000u : 0u), __float_as_uint(f[k]));
+                    if (ci < kCandShared) cand_s[ci] = rec;
+                    else cand_g[ci] = rec;
+                }
+                ncand += __popc(mask);
             }
-        }
-#pragma unroll
-        for (int k = 0; k < kBatch; k++) {
-            const int p = cb[k] + lane;
-            const bool is_near = vx[k].inb && (f[k] < near);
-            const bool keep = (p < ce[k]) && (is_near || (has_self && (sflag[p] & 1)));
-            const unsigned mask = __ballot_sync(FKS_FULL, keep);
-            if (keep) {
-                const int ci = ncand + __popc(mask & ((1u << lane) - 1u));
-                const uint2 rec = make_uint2((unsigned)p | (is_near ? 0x80000000u : 0u), __float_as_uint(f[k]));
-                if (ci < kCandShared) cand_s[ci] = rec;
-                else cand_g[ci] = rec;
-            }
-            ncand += __popc(mask);
         }
     }
     __syncwarp();

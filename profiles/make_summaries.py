@@ -1,0 +1,145 @@
+"""Regenerates profiles/r1_bench.md, r1_ncu_arm_table.md, traffic.json and the launch list from gpurun_out/ (scratch):
+   python profiles/make_summaries.py     (needs `ncu` on PATH to read gpurun_out/prof_r1_arm_table.ncu-rep)"""
+import collections
+import csv
+import json
+import os
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+
+
+def load(name):
+    try:
+        return json.loads(open(os.path.join(OUT, name)).read().strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def bench_md():
+    main, ref = load("bench_r1.json"), load("bench_r1_reference.json")
+    L = ["# Round 1 — bench lines (B200, one GPU, fresh box, SM clock 1965 MHz, no throttle reasons)\n",
+         "`python bench.py` (default: BASELINE config 3, `arm_table`, 65 536 particles, 10 timed steps after 3 warm-ups, L2 flushed "
+         "between steps) and the same command with `--workload ...` for the other BASELINE configurations.\nA step is one "
+         "`ForwardSimulateRobots` call: 25 controller steps x microsteps x contact resolution per particle.\n",
+         "| workload (BASELINE config) | particles | ms / step | particle-microsteps/s (device) | e2e (host buffers) | microsteps / step | "
+         "resolver iterations / step | CPU oracle port (cores) | GPU / CPU |", "|---|---|---|---|---|---|---|---|---|"]
+
+    def row(d, tag):
+        c, cb = d["config"], d.get("cpu_baseline", {})
+        return "| %s %s | %d | %.1f | %.3e | %.3e | %d | %d | %s | %s |" % (
+            c["workload"], tag, c["particles_per_gpu"], d["ms_per_step"], d["value"], d["e2e"]["value"], c["microsteps_per_step"],
+            c["resolver_iterations_per_step"], ("%.3e (%d)" % (cb["value"], cb["cores"])) if cb else "-",
+            ("%.0fx" % (d["value"] / cb["value"])) if cb else "-")
+
+    L.append(row(main, "(3)"))
+    for f, tag in (("bench_r1_se3_narrow_passage.json", "(2)"), ("bench_r1_se2_arena.json", "(1)"), ("bench_r1_se3_highres.json", "(4, 511^3 SDF)"),
+                   ("bench_r1_arm_1m.json", "(5, one GPU)"), ("bench_r1_arm_free.json", ""), ("bench_r1_arm_elbow.json", "")):
+        d = load(f)
+        if d:
+            L.append(row(d, tag))
+    if ref:
+        L.append("\n`--impl reference` (oracle port, all host threads, bounded sample): %.3e particle-microsteps/s on %d cores (%s).\n" % (
+            ref["value"], ref["cpu_baseline"]["cores"], ref["cpu_baseline"]["sample"]))
+    r, r64, g = main["roofline"], main.get("roofline_fp64"), main.get("gather")
+    L.append("Roofline objects of the default line: HBM (contract) achieved %.1f GB/s of %.0f measured = %.3f (measured DRAM traffic: %s "
+             "bytes per launch)." % (r["achieved"], r["peak"], r["frac"], r["traffic"]))
+    if r64 and g:
+        L.append("FP64 achieved %.2f TFLOP/s of %.1f measured in the same job = %.3f; L2-resident gathers %.2e/s of %.2e/s measured = %.3f.  "
+                 "The kernel is latency-bound (see `r1_ncu_arm_table.md`).\n" % (r64["achieved"], r64["peak"], r64["frac"],
+                                                                               g["achieved_gathers_per_s"], g["l2_peak_gathers_per_s"], g["frac_of_l2_peak"]))
+    L.append("Full JSON of the default run:\n\n```json\n%s\n```\n" % json.dumps(main))
+    two = load("bench_r1_2gpu.json")
+    if two:
+        L.append("## Two GPUs (`gpurun --gpus 2`, torchrun, NCCL all-gather of the 72-byte end-state records inside the timed step; measured "
+                 "with an earlier kernel of this round)\n\n%.3e particle-microsteps/s over %d particles, %.1f ms/step (weak scaling, 65 536 "
+                 "particles per GPU): 98.7 %% of twice the one-GPU value of the same kernel.\n\n```json\n%s\n```\n" % (
+                     two["value"], two["config"]["particles_total"], two["ms_per_step"], json.dumps(two)))
+    open(os.path.join(PROF, "r1_bench.md"), "w").write("\n".join(L))
+
+
+def ncu(*args):
+    return subprocess.run(["ncu", "-i", os.path.join(OUT, "prof_r1_arm_table.ncu-rep")] + list(args), capture_output=True, text=True).stdout
+
+
+def ncu_md():
+    rows = list(csv.reader(ncu("--page", "raw", "--csv").splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+            "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct",
+            "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+            "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "smsp__warps_eligible.avg.per_cycle_active"]
+    m = {k: (vals[hdr.index(k)], units[hdr.index(k)]) for k in keys if k in hdr}
+
+    def tobytes(k):
+        v, u = m[k]
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+
+    traffic = tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")
+    json.dump({"arm_table": traffic, "source": "ncu --set full, profiles/r1_ncu_arm_table.md (dram__bytes_read.sum + dram__bytes_write.sum of "
+               "one simulate_kernel<2> launch, 65536 particles)"}, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
+    r2 = list(csv.reader(ncu("--page", "source", "--csv", "--print-source", "sass").splitlines()))
+    h2, d2 = r2[1], r2[2:]
+    ix = {h: i for i, h in enumerate(h2)}
+
+    def f(r, k):
+        try:
+            return float(r[ix[k]])
+        except Exception:
+            return 0.0
+
+    ts = sum(f(r, "# Samples") for r in d2)
+    stalls = sorted(((sum(f(r, s) for r in d2), s) for s in h2 if s.startswith("stall_") and "Not Issued" not in s), reverse=True)
+    r3 = list(csv.reader(ncu("--page", "source", "--csv", "--print-source", "cuda,sass").splitlines()))
+    cur = hdr3 = None
+    inst, samp, src = collections.Counter(), collections.Counter(), {}
+    for r in r3:
+        if len(r) >= 2 and r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+            continue
+        if len(r) > 3 and r[0] == "Line No":
+            hdr3 = r
+            continue
+        if hdr3 is None or len(r) < len(hdr3) or cur is None or r[2] != "-":
+            continue
+        try:
+            key = (cur, int(r[0]))
+            inst[key] += float(r[hdr3.index("Instructions Executed")])
+            samp[key] += float(r[hdr3.index("# Samples")])
+            src[key] = r[1]
+        except Exception:
+            pass
+    ti, tss = sum(inst.values()), sum(samp.values())
+    with open(os.path.join(PROF, "r1_ncu_arm_table.md"), "w") as o:
+        o.write("# Round 1 — ncu `--set full` of `simulate_kernel<2>` (arm_table, 65 536 particles, one launch, final kernel of the round)\n\n")
+        o.write("Command (after the same command exited 0 without ncu): `ncu --set full --clock-control none --import-source on -k "
+                "regex:simulate_kernel -s 1 -c 1 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`.\nPer-launch times under ncu are "
+                "serialised and cold; use them for shares only.  Launch list of the same command: `r1_launches_arm_table.csv`.\n\n| metric | value |\n|---|---|\n")
+        for k in keys:
+            if k in m:
+                o.write("| `%s` | %s %s |\n" % (k, m[k][0], m[k][1]))
+        o.write("| DRAM traffic per launch (read + write) | %.1f MB (algorithmic bytes of the same launch, SURVEY 8d: 42.7 GB, served from "
+                "L2/L1 — the SDF is L2-resident; the DRAM writes are the write-back of the per-warp Jacobian scratch and register spills) |\n" % (traffic / 1e6))
+        o.write("\n## Warp stall reasons (sampled, all samples)\n\n| reason | share |\n|---|---|\n")
+        for v, s in stalls[:10]:
+            o.write("| %s | %.1f %% |\n" % (s, 100 * v / ts))
+        o.write("\n`stall_barrier`: warps waiting at the lock-step barriers for the slowest warp of their group.  `stall_no_inst`: instruction "
+                "fetch — 60 % in the free-running first version, 2 % with whole-CTA lock step, back up with the group scheme (two code regions "
+                "live, 32 warps), which is still the fastest variant measured (`r1_v1_free_running.md`).\n")
+        o.write("\n## Hottest source lines (share of samples / of executed instructions)\n\n| samples | instructions | line | source |\n|---|---|---|---|\n")
+        for k, v in samp.most_common(25):
+            o.write("| %.1f %% | %.1f %% | %s:%d | `%s` |\n" % (100 * v / tss, 100 * inst[k] / ti, k[0], k[1], src[k].strip().replace("|", "\\|")[:100]))
+
+
+if __name__ == "__main__":
+    shutil.copy(os.path.join(OUT, "launches_r1.csv"), os.path.join(PROF, "r1_launches_arm_table.csv"))
+    ncu_md()
+    bench_md()
+    print("profiles/ regenerated")
