@@ -1514,6 +1514,173 @@ __device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
     __syncwarp();
 }
 
+// The same algorithm for taller systems (rows > 64): the matrix stays in the scratch slot (column major, L1/L2) and
+// every step makes a few passes over the rows with one accumulator per column, so the reductions are again two
+// interleaved shuffle trees per step instead of one tree per column as in the generic solver.  The step loop is rolled
+// (columns are addressed in memory, so a run-time column index costs nothing).
+template <int NC>
+__device__ __noinline__ void colpiv_qr_solve_mem(int wb, int rows, int x_off) {
+    const Frame& fr = frame();
+    const int lane = lane_id();
+    double* ws = wsd(wb);
+    double* A = reinterpret_cast<double*>(scratch_slot() + fr.a.sl.jstore);
+    const int ld = fr.a.sl.ldj;
+    double* bcol = A + (size_t)NC * ld;
+    double* rdiag = ws + fr.a.wl.qr;  // 1 / R(k,k)
+    const int size = rows < NC ? rows : NC;
+    const double eps = DBL_EPSILON;
+    double threshold_helper = 0.0;
+    int nonzero_pivots = size;
+    unsigned transp = 0u;
+    bool near_cut = false;
+#pragma unroll 1
+    for (int k = 0; k < size; k++) {
+        // ---- pass 1: squares below row k of the columns k .. NC-1, and their row-k entries ------------------
+        double sq[NC], dk[NC];
+#pragma unroll
+        for (int j = 0; j < NC; j++) sq[j] = 0.0;
+        for (int r = k + 1 + lane; r < rows; r += 32) {
+#pragma unroll
+            for (int j = 0; j < NC; j++)
+                if (j >= k) {
+                    const double v = A[(size_t)j * ld + r];
+                    sq[j] += v * v;
+                }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int j = 0; j < NC; j++) sq[j] += __shfl_xor_sync(FKS_FULL, sq[j], o);
+#pragma unroll
+        for (int j = 0; j < NC; j++) dk[j] = (j >= k) ? A[(size_t)j * ld + k] : 0.0;
+        if (k == 0) {
+            double mx = 0.0;
+#pragma unroll
+            for (int j = 0; j < NC; j++) mx = fmax(mx, dk[j] * dk[j] + sq[j]);
+            threshold_helper = (mx * (eps * eps)) / (double)rows;
+        }
+        int biggest = k;
+        double big_sq = -1.0, tail_sq = 0.0, c0 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NC; j++) {
+            const double n2 = dk[j] * dk[j] + sq[j];
+            if (j >= k && n2 > big_sq) {  // first maximum wins
+                big_sq = n2;
+                biggest = j;
+                tail_sq = sq[j];
+                c0 = dk[j];
+            }
+        }
+        const double cut = threshold_helper * (double)(rows - k);
+        if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
+        if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
+        transp |= (unsigned)biggest << (4 * k);
+        __syncwarp();
+        // ---- swap columns k <-> biggest (all rows: the finished part of R moves too) --------------------------
+        double* ck = A + (size_t)k * ld;
+        if (biggest != k) {
+            double* cb = A + (size_t)biggest * ld;
+            for (int r = lane; r < rows; r += 32) {
+                const double t = ck[r];
+                ck[r] = cb[r];
+                cb[r] = t;
+            }
+        }
+        // ---- makeHouseholderInPlace ---------------------------------------------------------------------------
+        double tau, beta, inv_denom = 0.0;
+        const bool zero_tail = tail_sq <= DBL_MIN;
+        if (zero_tail) {
+            tau = 0.0;
+            beta = c0;
+        } else {
+            beta = sqrt(c0 * c0 + tail_sq);
+            if (c0 >= 0.0) beta = -beta;
+            inv_denom = c0 - beta;
+            tau = (beta - c0) / beta;
+        }
+        __syncwarp();
+        const bool apply_b = nonzero_pivots > k;
+        // ---- pass 2: scale the tail and form the dot products with the trailing columns and the right-hand side --
+        double dt[NC + 1];
+#pragma unroll
+        for (int j = 0; j <= NC; j++) dt[j] = 0.0;
+        for (int r = k + 1 + lane; r < rows; r += 32) {
+            const double v = zero_tail ? 0.0 : ck[r] / inv_denom;
+            ck[r] = v;
+#pragma unroll
+            for (int j = 0; j < NC; j++)
+                if (j > k) dt[j] += v * A[(size_t)j * ld + r];
+            dt[NC] += v * bcol[r];
+        }
+        if (lane == 0) {
+            rdiag[k] = 1.0 / beta;
+            ck[k] = beta;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int j = 0; j <= NC; j++) dt[j] += __shfl_xor_sync(FKS_FULL, dt[j], o);
+        __syncwarp();
+        // ---- pass 3: apply the reflector ----------------------------------------------------------------------
+        if (rows - k == 1) {
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < NC; j++)
+                    if (j > k) A[(size_t)j * ld + k] *= (1.0 - tau);
+                if (apply_b) bcol[k] *= (1.0 - tau);
+            }
+        } else if (tau != 0.0) {
+            double tmp[NC + 1];
+#pragma unroll
+            for (int j = 0; j < NC; j++) tmp[j] = (j > k) ? dt[j] + A[(size_t)j * ld + k] : 0.0;
+            tmp[NC] = dt[NC] + bcol[k];
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < NC; j++)
+                    if (j > k) A[(size_t)j * ld + k] -= tau * tmp[j];
+                if (apply_b) bcol[k] -= tau * tmp[NC];
+            }
+            for (int r = k + 1 + lane; r < rows; r += 32) {
+                const double tv = tau * ck[r];
+#pragma unroll
+                for (int j = 0; j < NC; j++)
+                    if (j > k) A[(size_t)j * ld + r] -= tv * tmp[j];
+                if (apply_b) bcol[r] -= tv * tmp[NC];
+            }
+        }
+        __syncwarp();
+    }
+    if (near_cut && lane == 0) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
+    if (lane < NC) ws[x_off + lane] = 0.0;
+    __syncwarp();
+    if (lane == 0 && nonzero_pivots > 0) {
+        double y[NC];
+#pragma unroll
+        for (int i = NC - 1; i >= 0; i--) {
+            y[i] = 0.0;
+            if (i < nonzero_pivots) {
+                double sacc = bcol[i];
+#pragma unroll
+                for (int j = i + 1; j < NC; j++)
+                    if (j < nonzero_pivots) sacc -= A[(size_t)j * ld + i] * y[j];
+                y[i] = sacc * rdiag[i];
+            }
+        }
+        unsigned long long perm = 0xFEDCBA9876543210ull;
+        for (int k = 0; k < size; k++) {
+            const int t = (int)((transp >> (4 * k)) & 0xFu);
+            const unsigned long long pk = (perm >> (4 * k)) & 0xFull, pt = (perm >> (4 * t)) & 0xFull;
+            perm &= ~((0xFull << (4 * k)) | (0xFull << (4 * t)));
+            perm |= (pt << (4 * k)) | (pk << (4 * t));
+        }
+#pragma unroll
+        for (int i = 0; i < NC; i++)
+            if (i < nonzero_pivots) ws[x_off + (int)((perm >> (4 * i)) & 0xFull)] = y[i];
+    }
+    __syncwarp();
+}
+
 // actuator noise of the next `count` microsteps, one truncated-normal draw per axis in axis order
 __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned step, unsigned micro0, int count,
                                         unsigned long long tape_pos, unsigned long long tape_end) {
@@ -2012,17 +2179,17 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 colpiv_qr_solve_reg<6, 2>(wb, rows, wl.raw);
             } else if (rows <= 64 && KIND == FKS_ROBOT_LINKED && D == 7) {
                 colpiv_qr_solve_reg<7, 2>(wb, rows, wl.raw);
-            } else if (rows <= 128 && KIND == FKS_ROBOT_SE2) {
-                colpiv_qr_solve_reg<3, 4>(wb, rows, wl.raw);
-            } else if (rows <= 128 && KIND == FKS_ROBOT_SE3) {
-                colpiv_qr_solve_reg<6, 4>(wb, rows, wl.raw);
-            } else if (rows <= 128 && KIND == FKS_ROBOT_LINKED && D == 7) {
-                colpiv_qr_solve_reg<7, 4>(wb, rows, wl.raw);
+            } else if (KIND == FKS_ROBOT_SE2) {
+                colpiv_qr_solve_mem<3>(wb, rows, wl.raw);
+            } else if (KIND == FKS_ROBOT_SE3) {
+                colpiv_qr_solve_mem<6>(wb, rows, wl.raw);
+            } else if (KIND == FKS_ROBOT_LINKED && D == 7) {
+                colpiv_qr_solve_mem<7>(wb, rows, wl.raw);
             } else {
                 colpiv_qr_solve(wb, rows, D, wl.raw);
             }
 #ifdef FKS_PHASE_TIMERS
-            if (rows <= 128) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
+            if (rows <= 64) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
 #endif
             // motion estimate of the raw correction (spcs:1630) in the same solver slot: one lock-step round per
             // resolver iteration instead of two
