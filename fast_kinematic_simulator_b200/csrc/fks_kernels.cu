@@ -1514,7 +1514,7 @@ __device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
     __syncwarp();
 }
 
-// The same algorithm for taller systems (rows > 64): the matrix stays in the scratch slot (column major, L1/L2) and
+// The same algorithm for taller systems (rows > 128): the matrix stays in the scratch slot (column major, L1/L2) and
 // every step makes a few passes over the rows with one accumulator per column, so the reductions are again two
 // interleaved shuffle trees per step instead of one tree per column as in the generic solver.  The step loop is rolled
 // (columns are addressed in memory, so a run-time column index costs nothing).
@@ -2179,6 +2179,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 colpiv_qr_solve_reg<6, 2>(wb, rows, wl.raw);
             } else if (rows <= 64 && KIND == FKS_ROBOT_LINKED && D == 7) {
                 colpiv_qr_solve_reg<7, 2>(wb, rows, wl.raw);
+            } else if (rows <= 128 && KIND == FKS_ROBOT_SE2) {
+                colpiv_qr_solve_reg<3, 4>(wb, rows, wl.raw);
+            } else if (rows <= 128 && KIND == FKS_ROBOT_SE3) {
+                colpiv_qr_solve_reg<6, 4>(wb, rows, wl.raw);
+            } else if (rows <= 128 && KIND == FKS_ROBOT_LINKED && D == 7) {
+                colpiv_qr_solve_reg<7, 4>(wb, rows, wl.raw);
             } else if (KIND == FKS_ROBOT_SE2) {
                 colpiv_qr_solve_mem<3>(wb, rows, wl.raw);
             } else if (KIND == FKS_ROBOT_SE3) {
