@@ -295,3 +295,43 @@ WORKLOADS = {
 
 def make(name, **kw):
     return WORKLOADS[name](**kw)
+
+
+def gantry(n_particles=128, seed=1003):
+    """A small linked robot with every joint type the reference's linked model supports: two PRISMATIC axes (x, y), a FIXED
+    mounting joint, and a REVOLUTE + CONTINUOUS wrist carrying a bar of points.  Exercises the prismatic / fixed FK and Jacobian
+    paths that the 7-DoF arm does not."""
+    res = 0.05
+    rng = np.random.Generator(np.random.MT19937(seed))
+    obstacles = [
+        (make_transform((0.0, 0.0, -0.05)), (1.5, 1.5, 0.05), 1),        # floor
+        (make_transform((0.9, 0.0, 0.3)), (0.1, 0.6, 0.3), 2),           # a wall the bar is pushed into
+    ]
+    L = 6
+    bar = np.array([(0.0, 0.0, z) for z in np.linspace(0.02, 0.3, 8)] + [(x, 0.0, 0.3) for x in np.linspace(-0.15, 0.15, 7)])
+    cube = np.array([(x, y, z) for x in (-0.04, 0.04) for y in (-0.04, 0.04) for z in (0.0, 0.08)])
+    pts, plink = [], []
+    for l in range(L):
+        p = bar if l == L - 1 else cube
+        pts.append(p)
+        plink += [l] * len(p)
+    pts = np.concatenate(pts)
+    joints = [
+        dict(parent=0, child=1, type=capi.JOINT_PRISMATIC, transform=make_transform((0.0, 0.0, 0.25)), axis=(1.0, 0.0, 0.0), lower=-1.0, upper=1.0),
+        dict(parent=1, child=2, type=capi.JOINT_PRISMATIC, transform=make_transform((0.0, 0.0, 0.1)), axis=(0.0, 1.0, 0.0), lower=-0.2, upper=0.2),
+        dict(parent=2, child=3, type=capi.JOINT_FIXED, transform=make_transform((0.0, 0.0, 0.1), _rot((1, 0, 0), 0.1)), axis=(0.0, 0.0, 1.0), lower=0.0, upper=0.0),
+        dict(parent=3, child=4, type=capi.JOINT_REVOLUTE, transform=make_transform((0.0, 0.0, 0.1)), axis=(0.0, 1.0, 0.0), lower=-1.0, upper=1.0),
+        dict(parent=4, child=5, type=capi.JOINT_CONTINUOUS, transform=make_transform((0.0, 0.0, 0.1)), axis=(0.0, 0.0, 1.0), lower=-np.pi, upper=np.pi),
+    ]
+    allowed = np.ones((L, L), np.uint8)
+    axes = [_axis(1.0, kp=2.0), _axis(1.0, kp=2.0), _axis(1.0, kp=2.0), _axis(2.0, kp=2.0)]
+    robot = RobotDescription(capi.ROBOT_LINKED, pts, np.array(plink, np.int32), axes, n_links=L, joints=joints,
+                             base_transform=make_transform((0.011, 0.007, 0.063)), allowed_self_collision=allowed)  # off the voxel lattice
+    start = np.array([0.0, 0.0, 0.2, 3.0])
+    target = np.array([0.9, 0.3, 0.9, -2.9])   # x drives the bar into the wall, y runs into its upper limit, the wrist wraps through pi
+    starts = start[None, :] + rng.normal(0.0, 0.02, (n_particles, 4))
+    return Workload("gantry", capi.ROBOT_LINKED, obstacles, res, robot, starts, target.reshape(1, 4),
+                    "linked robot with prismatic, fixed, revolute and continuous joints pushed into a wall")
+
+
+WORKLOADS["gantry"] = gantry

@@ -1,1 +1,1 @@
-for w in 32 14 12 16; do echo "== FKS_WARPS_PER_BLOCK=$w"; FKS_WARPS_PER_BLOCK=$w timeout 300 python tests/gpu_perf.py 2>&1 | grep -vE "^$|n=   2368|n=  16384|n=    128|phases|per call|arm_free"; done
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -15

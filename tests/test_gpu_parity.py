@@ -132,3 +132,37 @@ def test_philox_matches_oracle_statistically():
     ref = orc.forward_simulate(w.starts, w.targets, True, capi.NOISE_PHILOX)
     assert np.array_equal(gpu.n_microsteps, ref["n_microsteps"])
     assert np.max(np.abs(gpu.configs - ref["cfg"])) < 1e-9
+
+
+def test_gantry_parity_all_joint_types():
+    """PRISMATIC + FIXED + REVOLUTE (limit reached) + CONTINUOUS (wraps through pi) joints, wall contact."""
+    w = W.gantry(128)
+    rep, gpu, ref, sens = parity.run_parity(w, 128)
+    _assert_parity(rep, sens, 0.5)
+    assert gpu.did_contact.mean() > 0.9 and np.array_equal(gpu.did_contact, (ref["flags"] & 1) != 0)
+    # the y axis target lies beyond the prismatic limit: the joint saturates at +0.2
+    assert np.all(gpu.configs[:, 1] <= 0.2 + 1e-12) and np.all(np.abs(gpu.configs[:, 3]) <= np.pi + 1e-12)
+
+
+@pytest.mark.parametrize("name,n,dist", [("se2_arena", 64, 1.5), ("se3_narrow_passage", 128, 0.5), ("arm_free", 64, 0.35), ("gantry", 64, 0.8)])
+def test_shortcut_distance_parity(name, n, dist):
+    """simulation_shortcut_distance > 0: ComputeConfigurationDistanceTo runs on the device after every step (spcs:898-902)."""
+    sp = capi.default_solver_params()
+    sp.simulation_shortcut_distance = dist
+    w = W.make(name, n_particles=n)
+    rep, gpu, ref, sens = parity.run_parity(w, n, solver_params=sp)
+    _assert_parity(rep, sens)
+    assert ((gpu.flags & capi.FLAG_ENDED_BY_SHORTCUT) != 0).any()
+    assert np.array_equal(gpu.n_steps[sens == 0], ref["n_steps"][sens == 0])
+
+
+def test_recovered_resolves_counter():
+    sp = capi.default_solver_params()
+    sp.failed_resolves_end_motion = 0
+    sp.max_resolver_iterations = 1
+    w = W.se3_narrow_passage(256)
+    rep, gpu, ref, sens = parity.run_parity(w, 256, solver_params=sp)
+    _assert_parity(rep, sens)
+    assert rep["oracle_stats"]["recovered_unsuccessful_resolves"] > 0
+    if len(rep["bad_sensitive"]) == 0:
+        assert rep["gpu_stats"] == rep["oracle_stats"]
