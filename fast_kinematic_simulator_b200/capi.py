@@ -165,6 +165,7 @@ EXPORTS = (
     "fks_forward_simulate",
     "fks_reverse_simulate",
     "fks_forward_simulate_device",
+    "fks_check_config_collision",
     "fks_get_statistics",
     "fks_reset_statistics",
     "fks_sim_launch_count",
@@ -202,6 +203,7 @@ lib.fks_forward_simulate_device.argtypes = [
     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
     C.c_uint64, C.c_void_p, C.c_void_p,
 ]
+lib.fks_check_config_collision.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
 lib.fks_get_statistics.argtypes = [C.c_void_p, P(C.c_uint64)]
 lib.fks_reset_statistics.argtypes = [C.c_void_p]
 lib.fks_sim_launch_count.argtypes = [C.c_void_p]

@@ -681,6 +681,41 @@ int fks_forward_simulate_device(fks_sim* s, const double* d_starts, const double
                               first_particle_id, d_results, (cudaStream_t)cuda_stream);
 }
 
+int fks_check_config_collision(fks_sim* s, const double* configs, size_t n, double inflation_ratio, uint8_t* out) {
+    if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_check_config_collision: null simulator");
+    if (n == 0) return FKS_OK;
+    if (!configs || !out || std::isnan(inflation_ratio)) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_check_config_collision: bad argument");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_check_config_collision: cudaSetDevice failed");
+    const size_t stride = (size_t)s->robot->stride;
+    int rc;
+    if ((rc = ensure(&s->d_starts, &s->cap_starts, n * stride)) != FKS_OK) return rc;
+    if ((rc = ensure(&s->d_results, &s->cap_results, n)) != FKS_OK) return rc;
+    FKS_CUDA(cudaMemcpyAsync(s->d_starts, configs, n * stride * 8, cudaMemcpyHostToDevice, s->stream));
+    LaunchArgs a = s->plan;
+    a.env = s->env->dev;
+    a.sp = s->sp;
+    a.robot = s->robot->d_robot;
+    a.pxy = s->robot->d_pxy;
+    a.pzl = s->robot->d_pzl;
+    a.starts = s->d_starts;
+    a.scratch = s->d_scratch;
+    a.n_particles = n;
+    a.cfg_stride = s->robot->stride;
+    const size_t per_sm = (n + (size_t)s->num_sms - 1) / (size_t)s->num_sms;
+    const int wpb = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->plan.warps_per_block, per_sm));
+    a.warps_per_block = wpb;
+    a.sync_off = a.warps_off + wpb * a.wl.total * 8;
+    const size_t dyn_smem = (size_t)a.sync_off + 16;
+    const int grid = (int)std::min<size_t>((size_t)s->grid_max, (n + (size_t)wpb - 1) / (size_t)wpb);
+    rc = launch_check_config(s->robot->host.kind, a, grid, dyn_smem, s->stream, inflation_ratio, (unsigned char*)s->d_results);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "check_config kernel launch");
+    s->launches++;
+    FKS_CUDA(cudaMemcpyAsync(out, s->d_results, n, cudaMemcpyDeviceToHost, s->stream));
+    FKS_CUDA(cudaStreamSynchronize(s->stream));
+    return FKS_OK;
+}
+
 int fks_get_statistics(fks_sim* s, uint64_t* out) {
     if (!s || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_get_statistics: null argument");
     DeviceGuard guard(s->device);

@@ -236,6 +236,7 @@ int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem,
                     const void* l2_window_base, size_t l2_window_bytes);
 // fills args.wl / pts_off / warps_off / warps_per_block and returns the dynamic shared memory size
 size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block);
+int launch_check_config(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream, double inflation_ratio, unsigned char* out);
 int launch_fp64_peak(double* out, int grid, int iters, void* stream);
 int launch_gather(const float* data, unsigned long long n_mask, float* out, int grid, int iters, void* stream);
 

@@ -497,8 +497,9 @@ __device__ __forceinline__ unsigned active_links(const DevEnv& e, const DevRobot
 #endif
 constexpr int kCandShared = FKS_CAND_SHARED;  // candidate points of collect_corrections kept in shared memory (<= 32)
 
-// CheckEnvironmentCollision (spcs:921-981) of the CURRENT state (G and T[X]); collision_threshold = 0.0 (spcs:424)
-__device__ __noinline__ bool check_env(int wb, int X, int use_cull) {
+// CheckEnvironmentCollision (spcs:921-981) of the CURRENT state (G and T[X]); collision_threshold = 0.0 on the simulation
+// path (spcs:424), inflation_ratio * resolution for CheckConfigCollision (spcs:1403)
+__device__ __noinline__ bool check_env(int wb, int X, int use_cull, double collision_threshold) {
     const Frame& fr = frame();
     const DevEnv& e = fr.a.env;
     const WarpLayout& wl = fr.a.wl;
@@ -508,13 +509,13 @@ __device__ __noinline__ bool check_env(int wb, int X, int use_cull) {
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
     const double res = e.sdf_res;
-    const double thr = 0.0 - (fr.a.sp.check_tolerance * res);
+    const double thr = collision_threshold - (fr.a.sp.check_tolerance * res);
     const double thr_deep = thr - res;
     const float oob = e.oob;
     bool hit = false;
     // points of culled links cannot collide (and an out-of-bounds value below the threshold disables culling)
     const DevRobot& rb = fr.rb;
-    unsigned links = (!use_cull || !e.cull || (double)oob < thr) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, 0.0);
+    unsigned links = (!use_cull || !e.cull || (double)oob < thr) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, thr > 0.0 ? thr : 0.0);
     // walk the runs of consecutive active links (one contiguous point range each), kBatch x 32 points -- kBatch
     // independent gathers per lane -- at a time
     while (links) {
@@ -971,7 +972,7 @@ __device__ __forceinline__ bool collect_self(int wb, int Xprev, int Xcur) {
 // CheckCollision (spcs:1418-1436): bit 0 = in collision, bit 1 = self-collision map non-empty
 template <int KIND>
 __device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur, int use_cull) {
-    const bool envc = check_env(wb, Xcur, use_cull);
+    const bool envc = check_env(wb, Xcur, use_cull, 0.0);
     const bool has_self = (KIND == FKS_ROBOT_LINKED) ? collect_self(wb, Xprev, Xcur) : false;
     return ((envc || has_self) ? 1u : 0u) | (has_self ? 2u : 0u);
 }
@@ -2234,6 +2235,112 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 }
 
 // ------------------------------------------------------------------------------------------------
+// CheckConfigCollision (spcs:1398-1416), the planner-side static query, batched: one warp per configuration.
+//   environment: CheckEnvironmentCollision with threshold inflation_ratio * map resolution (spcs:1403,1405)
+//   self:        CheckSelfCollisions (spcs:1324-1396): two points of links whose pair is not allowed share a cell of
+//                edge (inflation_ratio + 1) * map resolution (spcs:1404) -- same capsule broad phase, same cell keys
+// ------------------------------------------------------------------------------------------------
+namespace {
+__device__ __noinline__ bool self_collision_bool(int wb, int X, double check_resolution) {
+    const Frame& fr = frame();
+    const DevRobot& rb = fr.rb;
+    const DevEnv& e = fr.a.env;
+    const WarpLayout& wl = fr.a.wl;
+    if (rb.n_pairs == 0) return false;  // spcs:1327-1338
+    const int lane = lane_id();
+    const int P = fr.a.P;
+    const double* ws = wsd(wb);
+    const double* T = ws + wl.T + X * wl.L12;
+    const double* caps = ws + wl.caps;
+    const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
+    const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch_slot() + fr.a.sl.keys);
+    const double diag = 1.7320508075688772 * check_resolution * (1.0 + 1e-6) + 1e-9;
+    bool found = false;
+    bool keys_ready = false;
+    const int nch = (rb.n_pairs + 31) >> 5;
+    for (int ch = 0; ch < nch && !found; ch++) {
+        const int q = ch * 32 + lane;
+        bool hit = false;
+        if (q < rb.n_pairs) {
+            const int a = rb.pair_a[q], b = rb.pair_b[q];
+            const double d2 = segment_distance_sq(caps + 6 * a, caps + 6 * a + 3, caps + 6 * b, caps + 6 * b + 3);
+            const double reach = rb.cap_radius[a] + rb.cap_radius[b] + diag;
+            hit = d2 <= reach * reach;
+        }
+        unsigned m = __ballot_sync(FKS_FULL, hit);
+        if (m && !keys_ready) {
+            // cell keys of every point at the check resolution (LocationToExtendedGridIndex, spcs:1173-1181,1360)
+            for (int p = lane; p < P; p += 32) {
+                double wx, wy, wz;
+                apply_T(T + 12 * pzl[p].link, pxy[p].x, pxy[p].y, pzl[p].z, wx, wy, wz);
+                const double gx = e.inv_origin[0] * wx + e.inv_origin[1] * wy + e.inv_origin[2] * wz + e.inv_origin[3];
+                const double gy = e.inv_origin[4] * wx + e.inv_origin[5] * wy + e.inv_origin[6] * wz + e.inv_origin[7];
+                const double gz = e.inv_origin[8] * wx + e.inv_origin[9] * wy + e.inv_origin[10] * wz + e.inv_origin[11];
+                const long long kx = (long long)(gx / check_resolution), ky = (long long)(gy / check_resolution), kz = (long long)(gz / check_resolution);
+                keys[p] = ((unsigned long long)kx & 0x1FFFFFull) | (((unsigned long long)ky & 0x1FFFFFull) << 21) |
+                          (((unsigned long long)kz & 0x1FFFFFull) << 42);
+            }
+            __syncwarp();
+            keys_ready = true;
+        }
+        while (m && !found) {
+            const int qq = ch * 32 + (__ffs(m) - 1);
+            m &= m - 1u;
+            const int la = rb.pair_a[qq], lb = rb.pair_b[qq];
+            const int b0 = rb.link_begin[lb], b1 = rb.link_begin[lb + 1];
+            for (int base = rb.link_begin[la]; base < rb.link_begin[la + 1] && !found; base += 32) {
+                const int p = base + lane;
+                const bool valid = p < rb.link_begin[la + 1];
+                const unsigned long long kp = valid ? keys[p] : 0ull;
+                bool h = false;
+                for (int j = b0; j < b1; j++) h = h || (keys[j] == kp);
+                found = __any_sync(FKS_FULL, h && valid);
+            }
+        }
+    }
+    return found;
+}
+}  // namespace
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) check_config_kernel(const __grid_constant__ LaunchArgs args, double inflation_ratio,
+                                                                                       unsigned char* out) {
+    {
+        Frame* f = reinterpret_cast<Frame*>(smem_raw);
+        const unsigned* src = reinterpret_cast<const unsigned*>(&args);
+        unsigned* dst = reinterpret_cast<unsigned*>(&f->a);
+        for (int i = threadIdx.x; i < (int)(sizeof(LaunchArgs) / 4); i += blockDim.x) dst[i] = src[i];
+        const unsigned* rsrc = reinterpret_cast<const unsigned*>(args.robot);
+        unsigned* rdst = reinterpret_cast<unsigned*>(&f->rb);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevRobot) / 4); i += blockDim.x) rdst[i] = rsrc[i];
+        double2* pxy = reinterpret_cast<double2*>(smem_raw + args.pts_off);
+        PointZL* pzl = reinterpret_cast<PointZL*>(pxy + args.P);
+        for (int i = threadIdx.x; i < args.P; i += blockDim.x) {
+            pxy[i] = args.pxy[i];
+            pzl[i] = args.pzl[i];
+        }
+    }
+    __syncthreads();
+    const Frame& fr = frame();
+    const LaunchArgs& a = fr.a;
+    const int lane = lane_id();
+    const int wb = a.warps_off + (threadIdx.x >> 5) * a.wl.total * 8;
+    double* ws = wsd(wb);
+    const double map_res = a.env.map_res;
+    const unsigned long long warps_total = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.n_particles; i += warps_total) {
+        if (lane < a.cfg_stride) ws[a.wl.cfg + lane] = a.starts[(size_t)i * a.cfg_stride + lane];
+        __syncwarp();
+        kinematics<KIND>(wb, 0, 1);  // current_robot->SetPosition(config) (spcs:1401)
+        const bool envc = check_env(wb, 0, 1, inflation_ratio * map_res);
+        const bool selfc = (KIND == FKS_ROBOT_LINKED) ? self_collision_bool(wb, 0, (inflation_ratio + 1.0) * map_res) : false;
+        if (lane == 0) out[i] = (envc || selfc) ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // roofline micro-benchmarks: FP64 FMA throughput and random 4-byte gather rate
 // ------------------------------------------------------------------------------------------------
 __global__ void fp64_peak_kernel(double* out, int iters) {
@@ -2334,6 +2441,28 @@ int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem,
     cfg.numAttrs = nattr;
     void* params[1] = {const_cast<LaunchArgs*>(&args)};
     return (int)cudaLaunchKernelExC(&cfg, fn, params);
+}
+
+int launch_check_config(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream, double inflation_ratio, unsigned char* out) {
+    const int threads = 32 * args.warps_per_block;
+    cudaError_t err;
+    switch (kind) {
+        case FKS_ROBOT_SE2:
+            if ((err = cudaFuncSetAttribute(check_config_kernel<FKS_ROBOT_SE2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem)) != cudaSuccess) return (int)err;
+            check_config_kernel<FKS_ROBOT_SE2><<<grid, threads, dyn_smem, (cudaStream_t)stream>>>(args, inflation_ratio, out);
+            break;
+        case FKS_ROBOT_SE3:
+            if ((err = cudaFuncSetAttribute(check_config_kernel<FKS_ROBOT_SE3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem)) != cudaSuccess) return (int)err;
+            check_config_kernel<FKS_ROBOT_SE3><<<grid, threads, dyn_smem, (cudaStream_t)stream>>>(args, inflation_ratio, out);
+            break;
+        case FKS_ROBOT_LINKED:
+            if ((err = cudaFuncSetAttribute(check_config_kernel<FKS_ROBOT_LINKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem)) != cudaSuccess) return (int)err;
+            check_config_kernel<FKS_ROBOT_LINKED><<<grid, threads, dyn_smem, (cudaStream_t)stream>>>(args, inflation_ratio, out);
+            break;
+        default:
+            return (int)cudaErrorInvalidValue;
+    }
+    return (int)cudaGetLastError();
 }
 
 int launch_fp64_peak(double* out, int grid, int iters, void* stream) {

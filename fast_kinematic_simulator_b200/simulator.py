@@ -287,6 +287,13 @@ class GpuParticleContactSimulator:
                                               int(bool(allow_contacts)), int(noise_mode), ptr(d_tape), ptr(d_tape_offsets),
                                               int(first_particle_id), ptr(d_results), int(stream) if stream else None))
 
+    def check_config_collision(self, configs, inflation_ratio=0.0):
+        """CheckConfigCollision (spcs.hpp:1398-1416) for a batch of configurations -> bool array."""
+        configs = _as_f64(configs).reshape(-1, self.config_stride)
+        out = np.zeros(configs.shape[0], dtype=np.uint8)
+        check(lib.fks_check_config_collision(self._h, configs.ctypes.data, configs.shape[0], float(inflation_ratio), out.ctypes.data))
+        return out.astype(bool)
+
     def get_statistics(self):
         out = (C.c_uint64 * capi.NUM_STATS)()
         check(lib.fks_get_statistics(self._h, out))

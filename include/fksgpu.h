@@ -248,6 +248,13 @@ int fks_forward_simulate_device(fks_sim* sim, const double* d_starts, const doub
                                 const uint64_t* d_tape_offsets, uint64_t first_particle_id,
                                 void* d_results, void* cuda_stream);
 
+/* CheckConfigCollision (spcs.hpp:1398-1416), batched: out_collides[i] = 1 when configuration i collides with the
+ * environment inflated by inflation_ratio cells (CheckEnvironmentCollision, spcs.hpp:921-981 with threshold
+ * inflation_ratio * resolution) or with itself (CheckSelfCollisions, spcs.hpp:1324-1396, cells of
+ * (inflation_ratio + 1) * resolution).  HOST buffers: configs n * cfg_stride doubles, out_collides n bytes. */
+int fks_check_config_collision(fks_sim* sim, const double* configs, size_t n_configs, double inflation_ratio,
+                               uint8_t* out_collides);
+
 /* GetStatistics / ResetStatistics (spcs.hpp:488-512); out has FKS_NUM_STATS entries.
  * Synchronises the simulator's stream. */
 int fks_get_statistics(fks_sim* sim, uint64_t* out);

@@ -120,6 +120,22 @@ public:
         return ForwardSimulateRobots(std::vector<Configuration>(1, start), std::vector<Configuration>(1, target), allow_contacts)[0];
     }
 
+    // spcs.hpp:1398: planner-side static query (environment inflated by inflation_ratio cells, self collisions)
+    bool CheckConfigCollision(const Configuration& config, double inflation_ratio) {
+        std::vector<double> flat((size_t)stride_);
+        ConfigTraits<Configuration>::Flatten(config, flat.data(), stride_);
+        uint8_t out = 0;
+        Check(fks_check_config_collision(sim_, flat.data(), 1, inflation_ratio, &out));
+        return out != 0;
+    }
+    std::vector<uint8_t> CheckConfigCollisions(const std::vector<Configuration>& configs, double inflation_ratio) {
+        std::vector<double> flat(configs.size() * (size_t)stride_);
+        for (size_t i = 0; i < configs.size(); i++) ConfigTraits<Configuration>::Flatten(configs[i], flat.data() + i * (size_t)stride_, stride_);
+        std::vector<uint8_t> out(configs.size(), 0);
+        Check(fks_check_config_collision(sim_, flat.data(), configs.size(), inflation_ratio, out.data()));
+        return out;
+    }
+
     // spcs.hpp:488-500, same keys
     std::map<std::string, double> GetStatistics() {
         uint64_t s[FKS_NUM_STATS];

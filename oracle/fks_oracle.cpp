@@ -1053,6 +1053,41 @@ struct Sim {
         }
     }
 
+    // CheckSelfCollisions + CheckPointsForSelfCollision (spcs:1277-1396): true when some cell of edge check_resolution
+    // holds points of two links whose pair is not allowed
+    bool check_self_bool(const Robot& cur, double check_resolution) const {
+        const int L = cur.L;
+        if (L == 1) return false;
+        if (L == 2 && cur.mdl->allowed[0 * L + 1]) return false;
+        std::map<SelfKey, std::vector<int>> cells;  // cell -> links of its points
+        for (int l = 0; l < L; l++)
+            for (int p = cur.mdl->link_begin[(size_t)l]; p < cur.mdl->link_begin[(size_t)l + 1]; p++) {
+                const V3 pw = iso_apply(cur.link_T[(size_t)l], cur.mdl->points[(size_t)p]);
+                const V3 g = iso_apply(env.inv_origin, pw);
+                const SelfKey key = {(int64_t)(g.x / check_resolution), (int64_t)(g.y / check_resolution), (int64_t)(g.z / check_resolution)};
+                cells[key].push_back(l);
+            }
+        for (auto& kv : cells) {
+            const std::vector<int>& links = kv.second;
+            if (links.size() <= 1) continue;
+            for (int a : links)
+                for (int b : links)
+                    if (a != b && !cur.mdl->allowed[(size_t)a * L + b]) return true;
+        }
+        return false;
+    }
+
+    // CheckConfigCollision (spcs:1398-1416)
+    bool check_config_collision(const double* config, double inflation_ratio) const {
+        Robot robot = proto;
+        robot.set_position(config, nullptr);
+        const double environment_collision_distance_threshold = inflation_ratio * env.d.map_resolution;
+        const double self_collision_check_resolution = (inflation_ratio + 1.0) * env.d.map_resolution;
+        const bool env_collision = check_env(robot, environment_collision_distance_threshold, nullptr);
+        const bool self_collision = check_self_bool(robot, self_collision_check_resolution);
+        return env_collision || self_collision;
+    }
+
     // CheckCollision (spcs:1418-1436)
     bool check_collision(const Robot& prev, const Robot& cur, double time_interval, SelfMap* self, uint32_t* sens) const {
         const bool envc = check_env(cur, 0.0 /*contact_distance_threshold_, spcs:424*/, sens);
@@ -1383,6 +1418,13 @@ int oracle_forward_simulate(oracle_sim* o, const double* starts, const double* t
     for (int t = 0; t < T; t++)
         for (int k = 0; k < FKS_NUM_STATS; k++) s.stats[k] += tstats[(size_t)t][(size_t)k];
     return FKS_OK;
+}
+
+// CheckConfigCollision (spcs:1398-1416) for n configurations
+void oracle_check_config_collision(const oracle_sim* o, const double* configs, size_t n, double inflation_ratio, uint8_t* out) {
+    const int stride = o->s.proto.cfg_stride();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) out[i] = o->s.check_config_collision(configs + (size_t)i * stride, inflation_ratio) ? 1 : 0;
 }
 
 uint64_t oracle_tape_total(const oracle_sim* o) {

@@ -34,6 +34,8 @@ def load():
     lib.oracle_config_stride.argtypes = [C.c_void_p]
     lib.oracle_forward_simulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                             C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    lib.oracle_check_config_collision.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
+    lib.oracle_check_config_collision.restype = None
     lib.oracle_tape_total.argtypes = [C.c_void_p]
     lib.oracle_tape_total.restype = C.c_uint64
     lib.oracle_copy_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -121,6 +123,12 @@ class OracleSimulator:
         if rc != 0:
             raise ValueError("oracle_forward_simulate failed with code %d" % rc)
         return out
+
+    def check_config_collision(self, configs, inflation_ratio=0.0):
+        configs = _f64(configs).reshape(-1, self.stride)
+        out = np.zeros(configs.shape[0], dtype=np.uint8)
+        lib().oracle_check_config_collision(self._h, configs.ctypes.data, configs.shape[0], float(inflation_ratio), out.ctypes.data)
+        return out.astype(bool)
 
     def statistics(self):
         out = np.zeros(11, dtype=np.uint64)
