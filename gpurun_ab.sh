@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -12
+timeout 600 python tests/gpu_perf_check_config.py
