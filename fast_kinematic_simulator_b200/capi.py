@@ -174,6 +174,9 @@ EXPORTS = (
     "fks_built_env_desc",
     "fks_built_env_occupancy",
     "fks_built_env_destroy",
+    "fks_env_build_device",
+    "fks_env_build_timings",
+    "fks_env_download",
     "fks_measure_fp64_peak",
     "fks_measure_gather_rate",
 )
@@ -217,6 +220,9 @@ lib.fks_built_env_occupancy.argtypes = [C.c_void_p]
 lib.fks_built_env_occupancy.restype = P(C.c_uint8)
 lib.fks_built_env_destroy.argtypes = [C.c_void_p]
 lib.fks_built_env_destroy.restype = None
+lib.fks_env_build_device.argtypes = [C.c_int, P(Obstacle), C.c_size_t, C.c_double, P(C.c_void_p)]
+lib.fks_env_build_timings.argtypes = [C.c_void_p, P(C.c_double), C.c_int]
+lib.fks_env_download.argtypes = [C.c_void_p, P(C.c_void_p)]
 lib.fks_measure_fp64_peak.argtypes = [C.c_int, P(C.c_double)]
 lib.fks_measure_gather_rate.argtypes = [C.c_int, C.c_size_t, P(C.c_double)]
 

@@ -15,12 +15,24 @@
 #include <vector>
 
 #include "fks_device_types.h"
+#include "fks_internal.h"
 
 using namespace fksdev;
 
 namespace fks_host {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+// keep the SDF resident in L2 when it fits the persisting carve-out (the current device is env->device)
+void finish_env_l2_window(fks_env* env) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, env->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+        const size_t want = std::min<size_t>(env->sdf_bytes, (size_t)prop.persistingL2CacheMaxSize);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess && env->sdf_bytes <= (size_t)prop.persistingL2CacheMaxSize)
+            env->l2_window_bytes = std::min<size_t>(env->sdf_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    }
+    cudaGetLastError();
+}
 }  // namespace fks_host
 
 namespace {
@@ -72,16 +84,6 @@ int ensure(T** ptr, size_t* cap, size_t need) {
 }
 
 }  // namespace
-
-struct fks_env {
-    int device;
-    DevEnv dev;
-    float* d_sdf;
-    unsigned long long* d_keys;
-    double* d_entries;
-    size_t sdf_bytes;
-    size_t l2_window_bytes;
-};
 
 struct fks_robot {
     int device;
@@ -210,6 +212,13 @@ int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
     }
     rc = upload(&env->d_keys, keys.data(), 2 * cap);
     if (rc == FKS_OK) rc = upload(&env->d_entries, entries.data(), entries.size());
+    // ordered view kept for fks_env_download
+    static_assert(sizeof(long long) == sizeof(int64_t), "cell index width");
+    const uint32_t zero_start = 0;
+    if (rc == FKS_OK) rc = upload(&env->d_cell_index, reinterpret_cast<const long long*>(desc->normal_cell_index), ncell_n);
+    if (rc == FKS_OK) rc = upload(&env->d_cell_start, ncell_n ? desc->normal_cell_start : &zero_start, ncell_n + 1);
+    env->n_normal_cells = (long long)ncell_n;
+    env->n_entries = nentries;
     if (rc != FKS_OK) { fks_env_destroy(env); return rc; }
 
     DevEnv& d = env->dev;
@@ -251,14 +260,7 @@ int fks_env_create(int device, const fks_env_desc* desc, fks_env** out) {
     d.nh_mask = (unsigned long long)(cap - 1);
     d.normal_entries = env->d_entries;
 
-    // keep the SDF resident in L2 when it fits the persisting carve-out
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-        const size_t want = std::min<size_t>(env->sdf_bytes, (size_t)prop.persistingL2CacheMaxSize);
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess && env->sdf_bytes <= (size_t)prop.persistingL2CacheMaxSize)
-            env->l2_window_bytes = std::min<size_t>(env->sdf_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-    }
-    cudaGetLastError();
+    fks_host::finish_env_l2_window(env);
     *out = env;
     return FKS_OK;
 }
@@ -269,6 +271,9 @@ void fks_env_destroy(fks_env* env) {
     cudaFree(env->d_sdf);
     cudaFree(env->d_keys);
     cudaFree(env->d_entries);
+    cudaFree(env->d_cell_index);
+    cudaFree(env->d_cell_start);
+    cudaFree(env->d_occupancy);
     delete env;
 }
 

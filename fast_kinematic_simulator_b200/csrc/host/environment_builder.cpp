@@ -13,6 +13,7 @@
 // This is product host code (the workloads and the C++ adapter use it); it is NOT part of oracle/.
 
 #include "fksgpu.h"
+#include "../fks_internal.h"
 
 #include <algorithm>
 #include <cmath>
@@ -23,10 +24,6 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
-
-namespace fks_host {
-void set_last_error(const std::string& msg);
-}
 
 namespace {
 
@@ -176,15 +173,6 @@ NormalEntry make_entry(const double* normal, const double* direction) {
 
 }  // namespace
 
-struct fks_built_env {
-    fks_env_desc desc;
-    std::vector<float> sdf;
-    std::vector<uint8_t> occupancy;
-    std::vector<int64_t> normal_cell_index;
-    std::vector<uint32_t> normal_cell_start;
-    std::vector<double> normal_entries;
-};
-
 namespace {
 
 // sdf_tools SignedDistanceField::GetGradient(x,y,z, enable_edge_gradients=true) (call site envb.cpp:272):
@@ -211,26 +199,12 @@ void sdf_gradient(const float* sdf, const Grid& g, int64_t x, int64_t y, int64_t
 
 }  // namespace
 
-extern "C" int fks_build_environment(const fks_obstacle* obstacles, size_t n_obstacles, double resolution,
-                                     fks_built_env** out) {
-    if (!out || resolution <= 0.0 || (n_obstacles > 0 && !obstacles)) {
-        fks_host::set_last_error("fks_build_environment: invalid argument");
-        return FKS_ERR_INVALID_ARGUMENT;
-    }
-    for (size_t i = 0; i < n_obstacles; i++) {
-        if (obstacles[i].object_id == 0) {  // envb.hpp:35,41 assert(in_object_id > 0)
-            fks_host::set_last_error("fks_build_environment: obstacle object_id must be > 0");
-            return FKS_ERR_INVALID_ARGUMENT;
-        }
-    }
-    fks_built_env* env = new (std::nothrow) fks_built_env();
-    if (!env) return FKS_ERR_OUT_OF_MEMORY;
-    Grid g;
-    g.res = resolution;
+// Grid bounds and cell counts of BuildEnvironment (envb.cpp:49-160).
+int fks_host::compute_grid_geometry(const fks_obstacle* obstacles, size_t n_obstacles, double resolution,
+                                    fks_host::GridGeometry* g) {
     const double res = resolution;
     const double eff = resolution * 0.5;  // envb.cpp:23
-
-    // ---- BuildEnvironment (envb.cpp:49-160) ---------------------------------------------------
+    g->res = resolution;
     double x_min = 0, y_min = 0, z_min = 0, x_max = 0, y_max = 0, z_max = 0;
     double x_size = 10.0, y_size = 10.0, z_size = 10.0;
     if (n_obstacles == 0) {
@@ -285,15 +259,50 @@ extern "C" int fks_build_environment(const fks_obstacle* obstacles, size_t n_obs
     }
     const double ident[12] = {1, 0, 0, x_min, 0, 1, 0, y_min, 0, 0, 1, z_min};
     const double ident_inv[12] = {1, 0, 0, -x_min, 0, 1, 0, -y_min, 0, 0, 1, -z_min};
-    std::memcpy(g.origin, ident, sizeof(ident));
-    std::memcpy(g.inv_origin, ident_inv, sizeof(ident_inv));
-    g.nx = (int64_t)std::ceil(x_size / res);  // VoxelGrid ctor: ceil(size / cell_size)
-    g.ny = (int64_t)std::ceil(y_size / res);
-    g.nz = (int64_t)std::ceil(z_size / res);
-    if (g.nx <= 0 || g.ny <= 0 || g.nz <= 0 || g.nx > 4096 || g.ny > 4096 || g.nz > 4096) {
-        delete env;
+    std::memcpy(g->origin, ident, sizeof(ident));
+    std::memcpy(g->inv_origin, ident_inv, sizeof(ident_inv));
+    g->nx = (int64_t)std::ceil(x_size / res);  // VoxelGrid ctor: ceil(size / cell_size)
+    g->ny = (int64_t)std::ceil(y_size / res);
+    g->nz = (int64_t)std::ceil(z_size / res);
+    if (g->nx <= 0 || g->ny <= 0 || g->nz <= 0 || g->nx > 4096 || g->ny > 4096 || g->nz > 4096) {
         fks_host::set_last_error("fks_build_environment: grid dimensions out of range");
         return FKS_ERR_INVALID_ARGUMENT;
+    }
+    return FKS_OK;
+}
+
+extern "C" int fks_build_environment(const fks_obstacle* obstacles, size_t n_obstacles, double resolution,
+                                     fks_built_env** out) {
+    if (!out || resolution <= 0.0 || (n_obstacles > 0 && !obstacles)) {
+        fks_host::set_last_error("fks_build_environment: invalid argument");
+        return FKS_ERR_INVALID_ARGUMENT;
+    }
+    for (size_t i = 0; i < n_obstacles; i++) {
+        if (obstacles[i].object_id == 0) {  // envb.hpp:35,41 assert(in_object_id > 0)
+            fks_host::set_last_error("fks_build_environment: obstacle object_id must be > 0");
+            return FKS_ERR_INVALID_ARGUMENT;
+        }
+    }
+    fks_built_env* env = new (std::nothrow) fks_built_env();
+    if (!env) return FKS_ERR_OUT_OF_MEMORY;
+    Grid g;
+    g.res = resolution;
+    const double res = resolution;
+    const double eff = resolution * 0.5;  // envb.cpp:23
+
+    // ---- BuildEnvironment (envb.cpp:49-160) ---------------------------------------------------
+    {
+        fks_host::GridGeometry gg;
+        const int rc = fks_host::compute_grid_geometry(obstacles, n_obstacles, resolution, &gg);
+        if (rc != FKS_OK) {
+            delete env;
+            return rc;
+        }
+        std::memcpy(g.origin, gg.origin, sizeof(g.origin));
+        std::memcpy(g.inv_origin, gg.inv_origin, sizeof(g.inv_origin));
+        g.nx = gg.nx;
+        g.ny = gg.ny;
+        g.nz = gg.nz;
     }
     const int64_t ncells = g.nx * g.ny * g.nz;
     env->occupancy.assign((size_t)ncells, 0);
@@ -428,6 +437,6 @@ extern "C" int fks_build_environment(const fks_obstacle* obstacles, size_t n_obs
 
 extern "C" const fks_env_desc* fks_built_env_desc(const fks_built_env* env) { return env ? &env->desc : nullptr; }
 extern "C" const uint8_t* fks_built_env_occupancy(const fks_built_env* env) {
-    return env ? env->occupancy.data() : nullptr;
+    return (env && !env->occupancy.empty()) ? env->occupancy.data() : nullptr;
 }
 extern "C" void fks_built_env_destroy(fks_built_env* env) { delete env; }

@@ -52,7 +52,7 @@ class BuiltEnvironment:
         self.resolution = float(d.sdf_resolution)
         self.sdf = np.ctypeslib.as_array(d.sdf, shape=(n,)).reshape(self.shape)
         occ = lib.fks_built_env_occupancy(handle)
-        self.occupancy = np.ctypeslib.as_array(occ, shape=(n,)).reshape(self.shape)
+        self.occupancy = np.ctypeslib.as_array(occ, shape=(n,)).reshape(self.shape) if occ else None
         self.origin = np.array(list(d.origin))
         self.inverse_origin = np.array(list(d.inverse_origin))
         nc = int(d.n_normal_cells)
@@ -82,15 +82,32 @@ class BuiltEnvironment:
 def build_complete_environment(obstacles, resolution):
     """obstacles: iterable of (pose12, half_extents3, object_id) -- OBSTACLE_CONFIG
     (simulator_environment_builder.hpp:25-49)."""
+    arr, n = _obstacle_array(obstacles)
+    h = C.c_void_p()
+    check(lib.fks_build_environment(arr, n, float(resolution), C.byref(h)))
+    return BuiltEnvironment(h)
+
+
+def _obstacle_array(obstacles):
     obstacles = list(obstacles)
     arr = (capi.Obstacle * max(len(obstacles), 1))()
     for i, (pose, ext, oid) in enumerate(obstacles):
         arr[i].pose = (C.c_double * 12)(*[float(v) for v in pose])
         arr[i].extents = (C.c_double * 3)(*[float(v) for v in ext])
         arr[i].object_id = int(oid)
+    return arr, len(obstacles)
+
+
+BUILD_PHASES = ("total", "rasterize", "edt_z", "edt_y", "edt_x_sdf", "normals_mark", "normals_emit", "distance_field_check")
+
+
+def build_complete_environment_on_device(obstacles, resolution, device=0):
+    """BuildCompleteEnvironment (simulator_environment_builder.cpp:470-476) computed by CUDA kernels straight into a
+    device environment (fks_env_build_device): no host copy of the occupancy grid, SDF or normal table."""
+    arr, n = _obstacle_array(obstacles)
     h = C.c_void_p()
-    check(lib.fks_build_environment(arr, len(obstacles), float(resolution), C.byref(h)))
-    return BuiltEnvironment(h)
+    check(lib.fks_env_build_device(int(device), arr, n, float(resolution), C.byref(h)))
+    return GpuEnvironment(None, device, _handle=h)
 
 
 class RobotDescription:
@@ -159,12 +176,28 @@ class RobotDescription:
 class GpuEnvironment:
     """Device copy of what the simulator copies at construction (spcs.hpp:420): SDF + normals."""
 
-    def __init__(self, built_env, device=0):
+    def __init__(self, built_env, device=0, _handle=None):
         self.built = built_env
         self.device = device
+        if _handle is not None:  # built on the device (build_complete_environment_on_device)
+            self._h = _handle
+            return
         self._h = C.c_void_p()
         desc = built_env.desc if isinstance(built_env, BuiltEnvironment) else built_env
         check(lib.fks_env_create(device, C.byref(desc), C.byref(self._h)))
+
+    def download(self):
+        """Host copy of the device environment (fks_env_download) as a BuiltEnvironment."""
+        h = C.c_void_p()
+        check(lib.fks_env_download(self._h, C.byref(h)))
+        return BuiltEnvironment(h)
+
+    @property
+    def build_timings_ms(self):
+        """Device time of each phase of the device builder (zeros for uploaded environments)."""
+        out = (C.c_double * len(BUILD_PHASES))()
+        check(lib.fks_env_build_timings(self._h, out, len(BUILD_PHASES)))
+        return {k: float(out[i]) for i, k in enumerate(BUILD_PHASES)}
 
     def close(self):
         if self._h:
@@ -325,7 +358,7 @@ class GpuParticleContactSimulator:
 def _make(kind, built_env, robot_description, solver_params, simulation_controller_frequency, prng_seed, debug_level, device):
     if robot_description.kind != kind:
         raise ValueError("robot description kind does not match the factory")
-    env = GpuEnvironment(built_env, device)
+    env = built_env if isinstance(built_env, GpuEnvironment) else GpuEnvironment(built_env, device)
     robot = GpuRobot(robot_description, device)
     return GpuParticleContactSimulator(env, robot, solver_params, simulation_controller_frequency, prng_seed, debug_level)
 

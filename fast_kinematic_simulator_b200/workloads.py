@@ -48,12 +48,19 @@ class Workload:
             self._env = build_complete_environment(self.obstacles, self.resolution)
         return self._env
 
-    def make_simulator(self, device=0, solver_params=None, seed=PRNG_SEED):
+    def device_environment(self, device=0):
+        """BuildCompleteEnvironment on the GPU (fks_env_build_device): no host copy of the grids."""
+        from . import simulator as S
+
+        return S.build_complete_environment_on_device(self.obstacles, self.resolution, device)
+
+    def make_simulator(self, device=0, solver_params=None, seed=PRNG_SEED, build_on_device=False):
         from . import simulator as S
 
         fn = {capi.ROBOT_SE2: S.make_se2_simulator, capi.ROBOT_SE3: S.make_se3_simulator,
               capi.ROBOT_LINKED: S.make_linked_simulator}[self.kind]
-        return fn(self.environment(), self.robot, solver_params, CONTROLLER_HZ, seed, 0, device)
+        env = self.device_environment(device) if build_on_device else self.environment()
+        return fn(env, self.robot, solver_params, CONTROLLER_HZ, seed, 0, device)
 
     def subset(self, n, offset=0):
         t = self.targets if self.targets.shape[0] == 1 else self.targets[offset:offset + n]

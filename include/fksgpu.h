@@ -287,6 +287,22 @@ const uint8_t* fks_built_env_occupancy(const fks_built_env* env);
 void fks_built_env_destroy(fks_built_env* env);
 
 /* -------------------------------------------------------------------------------------------
+ * Environment builder on the device: the same BuildCompleteEnvironment
+ * (simulator_environment_builder.cpp:470-476: BuildEnvironment :49-160, ExtractSignedDistanceField :473,
+ * BuildSurfaceNormalsGrid :258-468) computed by CUDA kernels straight into a device environment -- occupancy
+ * rasterisation, exact Euclidean distance transform, float SDF, surface-normal table and its hash -- with no host
+ * copy of the grids.  Results are bit-identical to fks_build_environment + fks_env_create.
+ * fks_env_build_timings: out_ms[0] = total device time of the build, [1] rasterise, [2] z pass, [3] y pass,
+ * [4] x pass + SDF, [5] surface marking, [6] normal count/scan/emit, [7] distance-field check (milliseconds).
+ * fks_env_download: copies a device environment back into host arrays (any fks_env; occupancy only when the
+ * environment was built on the device, else fks_built_env_occupancy returns NULL).
+ * ----------------------------------------------------------------------------------------- */
+int fks_env_build_device(int device, const fks_obstacle* obstacles, size_t n_obstacles, double resolution,
+                         fks_env** out);
+int fks_env_build_timings(const fks_env* env, double* out_ms, int n);
+int fks_env_download(const fks_env* env, fks_built_env** out);
+
+/* -------------------------------------------------------------------------------------------
  * Device micro-benchmarks used for the roofline denominators: dependent-free DFMA
  * throughput (FLOP/s) and random 4-byte gather rate (gathers/s) over a `bytes`-sized array.
  * ----------------------------------------------------------------------------------------- */

@@ -64,7 +64,27 @@ def load():
     lib.oracle_philox_raw.restype = None
     lib.oracle_env_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oracle_robot_kinematics.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_build_environment.argtypes = [C.c_void_p, C.c_size_t, C.c_double]
+    lib.oracle_build_environment.restype = C.c_void_p
+    lib.oracle_env_desc.argtypes = [C.c_void_p]
+    lib.oracle_env_desc.restype = C.POINTER(_EnvDesc)
+    lib.oracle_env_occupancy.argtypes = [C.c_void_p]
+    lib.oracle_env_occupancy.restype = C.POINTER(C.c_uint8)
+    lib.oracle_env_destroy.argtypes = [C.c_void_p]
+    lib.oracle_env_destroy.restype = None
     return lib
+
+
+class _Obstacle(C.Structure):  # fks_obstacle (include/fksgpu.h)
+    _fields_ = [("pose", C.c_double * 12), ("extents", C.c_double * 3), ("object_id", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class _EnvDesc(C.Structure):  # fks_env_desc (include/fksgpu.h)
+    _fields_ = [("origin", C.c_double * 12), ("inverse_origin", C.c_double * 12), ("map_resolution", C.c_double),
+                ("sdf_resolution", C.c_double), ("nx", C.c_int64), ("ny", C.c_int64), ("nz", C.c_int64),
+                ("sdf", C.POINTER(C.c_float)), ("oob_value", C.c_float), ("_pad", C.c_int32), ("n_normal_cells", C.c_int64),
+                ("normal_cell_index", C.POINTER(C.c_int64)), ("normal_cell_start", C.POINTER(C.c_uint32)),
+                ("normal_entries", C.POINTER(C.c_double))]
 
 
 _lib = None
@@ -75,6 +95,39 @@ def lib():
     if _lib is None:
         _lib = load()
     return _lib
+
+
+def build_environment(obstacles, resolution):
+    """oracle_build_environment: scalar restatement of BuildCompleteEnvironment (simulator_environment_builder.cpp:470-476).
+    obstacles: iterable of (pose12, half_extents3, object_id).  Returns numpy copies of every array."""
+    obstacles = list(obstacles)
+    arr = (_Obstacle * max(len(obstacles), 1))()
+    for i, (pose, ext, oid) in enumerate(obstacles):
+        arr[i].pose = (C.c_double * 12)(*[float(v) for v in pose])
+        arr[i].extents = (C.c_double * 3)(*[float(v) for v in ext])
+        arr[i].object_id = int(oid)
+    h = lib().oracle_build_environment(arr, len(obstacles), float(resolution))
+    try:
+        d = lib().oracle_env_desc(h).contents
+        shape = (int(d.nx), int(d.ny), int(d.nz))
+        n = shape[0] * shape[1] * shape[2]
+        nc = int(d.n_normal_cells)
+        out = {
+            "shape": shape,
+            "origin": np.array(list(d.origin)),
+            "inverse_origin": np.array(list(d.inverse_origin)),
+            "resolution": float(d.sdf_resolution),
+            "sdf": np.ctypeslib.as_array(d.sdf, shape=(n,)).reshape(shape).copy(),
+            "occupancy": np.ctypeslib.as_array(lib().oracle_env_occupancy(h), shape=(n,)).reshape(shape).copy(),
+            "normal_cell_index": np.ctypeslib.as_array(d.normal_cell_index, shape=(nc,)).copy() if nc else np.zeros(0, np.int64),
+            "normal_cell_start": np.ctypeslib.as_array(d.normal_cell_start, shape=(nc + 1,)).copy(),
+        }
+        ne = int(out["normal_cell_start"][-1])
+        out["normal_entries"] = (np.ctypeslib.as_array(d.normal_entries, shape=(ne * 7,)).reshape(ne, 7).copy() if ne
+                                 else np.zeros((0, 7)))
+        return out
+    finally:
+        lib().oracle_env_destroy(h)
 
 
 def _f64(a):
