@@ -66,6 +66,28 @@ private:
     fks_built_env* built_;
 };
 
+// The same environment built by CUDA kernels directly in device memory (fks_env_build_device): no host grids.
+class DeviceEnvironment {
+public:
+    // BuildCompleteEnvironment (simulator_environment_builder.cpp:470-476) on `device`
+    DeviceEnvironment(const std::vector<fks_obstacle>& obstacles, double resolution, int device = 0) : env_(nullptr) {
+        Check(fks_env_build_device(device, obstacles.data(), obstacles.size(), resolution, &env_));
+    }
+    ~DeviceEnvironment() { fks_env_destroy(env_); }
+    DeviceEnvironment(const DeviceEnvironment&) = delete;
+    DeviceEnvironment& operator=(const DeviceEnvironment&) = delete;
+    fks_env* Handle() const { return env_; }
+    // milliseconds of device time: total, rasterise, z / y / x passes, surface marking, normal emit, distance-field check
+    std::vector<double> BuildTimingsMs() const {
+        std::vector<double> ms(8, 0.0);
+        Check(fks_env_build_timings(env_, ms.data(), (int)ms.size()));
+        return ms;
+    }
+
+private:
+    fks_env* env_;
+};
+
 template <typename Configuration>
 struct ConfigTraits;  // Flatten(config, double*) / Unflatten(const double*, stride) -> config
 
@@ -90,6 +112,22 @@ public:
             Check(fks_env_create(device, &environment, &env_));
             Check(fks_robot_create(device, &robot, &robot_));
             Check(fks_sim_create(env_, robot_, &solver_config, simulation_controller_frequency, prng_seed, debug_level, &sim_));
+        } catch (...) {
+            Release();
+            throw;
+        }
+        stride_ = fks_robot_config_stride(robot_);
+        record_ = fks_sim_result_stride(sim_);
+    }
+    // same, in an environment that already lives on the device (shared, must outlive the simulator)
+    GpuParticleContactSimulator(const std::shared_ptr<DeviceEnvironment>& environment, const fks_robot_desc& robot,
+                                const fks_solver_params& solver_config, double simulation_controller_frequency, uint64_t prng_seed,
+                                int32_t debug_level, int device = 0)
+        : shared_env_(environment), env_(nullptr), robot_(nullptr), sim_(nullptr) {
+        if (!environment) throw std::invalid_argument("fksgpu: null device environment");
+        try {
+            Check(fks_robot_create(device, &robot, &robot_));
+            Check(fks_sim_create(environment->Handle(), robot_, &solver_config, simulation_controller_frequency, prng_seed, debug_level, &sim_));
         } catch (...) {
             Release();
             throw;
@@ -196,6 +234,7 @@ private:
         env_ = nullptr;
     }
 
+    std::shared_ptr<DeviceEnvironment> shared_env_;  // set when the environment is not owned (env_ stays null)
     fks_env* env_;
     fks_robot* robot_;
     fks_sim* sim_;
@@ -209,6 +248,12 @@ typedef std::shared_ptr<GpuSimulator> GpuSimulatorPtr;
 
 // fast_kinematic_simulator.hpp:18-22, same argument order (grid + SDF + surface normals = one fks_env_desc)
 inline GpuSimulatorPtr MakeGpuSimulator(int kind, const fks_env_desc& environment, const fks_robot_desc& robot,
+                                        const fks_solver_params& solver_config, double simulation_controller_frequency,
+                                        uint64_t prng_seed, int32_t debug_level) {
+    if (robot.kind != kind) throw std::invalid_argument("fksgpu: robot description does not match the factory");
+    return GpuSimulatorPtr(new GpuSimulator(environment, robot, solver_config, simulation_controller_frequency, prng_seed, debug_level));
+}
+inline GpuSimulatorPtr MakeGpuSimulator(int kind, const std::shared_ptr<DeviceEnvironment>& environment, const fks_robot_desc& robot,
                                         const fks_solver_params& solver_config, double simulation_controller_frequency,
                                         uint64_t prng_seed, int32_t debug_level) {
     if (robot.kind != kind) throw std::invalid_argument("fksgpu: robot description does not match the factory");
