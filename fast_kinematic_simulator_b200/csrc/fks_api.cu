@@ -541,9 +541,9 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     const size_t scratch_bytes = (size_t)s->grid_max * wpb * s->plan.sl.total;
     if ((err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_scratch, scratch_bytes)) != cudaSuccess ||
-        (err = cudaMalloc((void**)&s->d_stats, 32 * sizeof(unsigned long long))) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_stats, 64 * sizeof(unsigned long long))) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_counter, sizeof(unsigned int))) != cudaSuccess ||
-        (err = cudaMemset(s->d_stats, 0, 32 * sizeof(unsigned long long))) != cudaSuccess) {
+        (err = cudaMemset(s->d_stats, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) {
         fks_sim_destroy(s);
         return cuda_fail(err, "fks_sim_create: allocation");
     }
@@ -733,7 +733,7 @@ int fks_reset_statistics(fks_sim* s) {
     if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_reset_statistics: null argument");
     DeviceGuard guard(s->device);
     FKS_CUDA(cudaDeviceSynchronize());
-    FKS_CUDA(cudaMemset(s->d_stats, 0, 32 * sizeof(uint64_t)));
+    FKS_CUDA(cudaMemset(s->d_stats, 0, 64 * sizeof(uint64_t)));
     return FKS_OK;
 }
 
@@ -744,7 +744,7 @@ int fks_debug_phase_cycles(fks_sim* s, uint64_t* out16) {
     if (!s || !out16) return FKS_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(s->device);
     FKS_CUDA(cudaDeviceSynchronize());
-    FKS_CUDA(cudaMemcpy(out16, s->d_stats + 16, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    FKS_CUDA(cudaMemcpy(out16, s->d_stats + 16, 48 * sizeof(uint64_t), cudaMemcpyDeviceToHost));  // 48 values
     return FKS_OK;
 }
 

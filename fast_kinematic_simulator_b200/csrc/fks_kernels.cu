@@ -1343,51 +1343,73 @@ __device__ __noinline__ void colpiv_qr_solve(int wb, int rows, int cols, int x_o
     __syncwarp();
 }
 
-// Register-resident variant of the same solve for the common small systems: rows <= 32 * R, NC columns known
-// at compile time (3 / 6 / 7: the reference's three robots).  Lane l keeps rows l, l + 32, ... of all NC columns
-// and of the right-hand side in registers; rows beyond `rows` are zero, which leaves every Householder quantity
-// unchanged.  The critical path per Householder step is two interleaved shuffle trees, one square root and one
-// division:
-//   * tree 1 sums, for every not-yet-eliminated column, the squares of the rows below the diagonal row k; with
-//     the diagonal-row entries broadcast from lane k this gives all residual column norms (pivot selection, rank
-//     cut) AND the tail norm of whichever column is picked.  Eigen keeps these norms by LAPACK-style downdating
-//     (a division and a square root per column per step, recomputed when they lose half their digits); the direct
-//     sums here are the exact quantities those approximate, so the pivot order only differs on ties that the
-//     oracle reports as SENS_PIVOT_TIE / SENS_RANK_CUT;
-//   * tree 2 forms the dot products of the reflector with all trailing columns and the right-hand side.
-// Column swaps are register selects; reflectors are applied to the right-hand side as they are formed (only those
-// below the rank cut, as Eigen's solve does).  The step loop is fully unrolled on purpose: a rolled variant (pivot
-// column rotated to register 0, finished rows of R parked in shared memory) is 3.5x smaller but measured 15 % slower
-// on the contact workloads (profiles/r1_v1_free_running.md).
+// ---- the solver of the reference's three robots (NC = 3 / 6 / 7 columns known at compile time) -----------------------------
+// Register-resident column-pivoted Householder QR, rows <= 32 R held R per lane (row lane + 32 s in slot s).  Rows beyond
+// `rows` are zero, which leaves every Householder quantity unchanged.  Per step: tree 1 sums the squares of every column
+// over the rows from the diagonal row on -- the residual column norms Eigen tracks by LAPACK-style downdating; the direct
+// sums are the exact quantities those approximate, so the pivot order only differs on ties the oracle reports as
+// SENS_PIVOT_TIE / SENS_RANK_CUT -- then the pivot, the reflector, and tree 2 = the reflector's dot products with all
+// columns and the right-hand side (reflectors are applied to the right-hand side as they are formed, only those below the
+// rank cut, as Eigen's solve does).
+// The step loop is a REAL loop over ONE copy of the step.  An earlier version unrolled it (column swaps as register
+// renames): ~9 000 instructions, 147 KB of straight-line code per (NC, R) pair, against a 32 KB instruction cache shared
+// by a dozen solver warps at different places -- ncu showed 61 % of its stall samples on instruction fetch.  What was
+// compile-time because of the step index is data here:
+//   * columns are never swapped: column j stays in registers a[.][j] and `pos` holds its position in Eigen's permuted
+//     order (candidates are the columns with pos >= k; ties go to the smallest position, as Eigen's scan over k .. NC-1 does);
+//   * the pivot column is read through a select chain on the run-time pivot index;
+//   * trees and updates run over all NC (+1) columns with the finished ones masked out.
+// Same speed on the arm workloads, 5-10 % faster on SE(3), a sixth of the code (profiles/r1_kernel_experiments.md).
+//
+// Tall systems (rows > 64) are first folded, 64 rows at a time, into an NC x (NC + 1) triangle by UNPIVOTED reflections
+// (reduce_only: pivot = step index, triangle written back over the last NC rows of the chunk, returns the new first row):
+// [A | c] -> Q^T [A | c] = [R | d ; 0 | *].  An orthogonal transformation from the left changes neither the Gram matrix of
+// the columns nor the least-squares problem, so the column-pivoted QR of the folded system (triangle + remaining rows)
+// makes the same pivot choices, rank decision (rows_thr = the ORIGINAL row count enters Eigen's threshold) and solution as
+// the one of the full system up to round-off -- the same class of difference as the summation order of the trees.  This
+// replaced a four-slot register variant (spilled at 64 registers) and a memory-resident one for > 128 rows.
+template <int NC>
+__device__ __forceinline__ double select_col(int p, const double (&v)[NC + 1]) {
+    double r = v[0];
+#pragma unroll
+    for (int j = 1; j < NC; j++) r = (p == j) ? v[j] : r;
+    return r;
+}
+
+// R = row slots per lane (rows <= 32 R).  Register budget at 64 registers per thread: the matrix (2 R (NC + 1) registers),
+// ONE transient array of NC + 1 sums, and the positions packed four bits each in one register -- nothing spills.  To get
+// there the sums run over the rows FROM the diagonal row on (not below it): tree 1 gives the residual column norms
+// directly and beta = -sign(c0) sqrt(norm) for the pivot column;
+// tree 2 uses the full Householder vector (1 on the diagonal row), so it needs no separate broadcast of row k.
 template <int NC, int R>
-__device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
+__device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int rows_thr, bool reduce_only) {
     const Frame& fr = frame();
     const int lane = lane_id();
     double* ws = wsd(wb);
-    const double* A = reinterpret_cast<const double*>(scratch_slot() + fr.a.sl.jstore);
+    double* A = reinterpret_cast<double*>(scratch_slot() + fr.a.sl.jstore) + row0;
     const int ld = fr.a.sl.ldj;
-    double a[R][NC + 1];  // slot s holds row lane + 32 s; column index NC = right-hand side
+    double a[R][NC + 1];  // slot s holds row lane + 32 s; column NC = right-hand side
 #pragma unroll
     for (int sl = 0; sl < R; sl++)
 #pragma unroll
         for (int c = 0; c <= NC; c++) a[sl][c] = (lane + 32 * sl < rows) ? A[(size_t)c * ld + lane + 32 * sl] : 0.0;
     const int size = rows < NC ? rows : NC;
-    const double eps = DBL_EPSILON;
-    double threshold_helper = 0.0;
+    double threshold_helper = 0.0, rdiag_mine = 0.0;
     int nonzero_pivots = size;
-    unsigned transp = 0u;
+    unsigned order = 0u;        // 4 bits per step: the column picked at step k
+    unsigned pos = 0x76543210u; // 4 bits per column: its position in the permuted order
     bool near_cut = false;
-    double rdiag[NC];  // 1 / R(k,k)
+#pragma unroll 1
+    for (int k = 0; k < size; k++) {
+        const bool from_diag = lane >= k;  // slot-0 rows not yet finished (rows above the diagonal row belong to R)
+        int p = k;
+        double nsq_p;
+        {
+            // ---- tree 1: squared residual norms (rows >= k) of every column ---------------------------------------
+            double sq[NC + 1];
 #pragma unroll
-    for (int k = 0; k < NC; k++) {
-        rdiag[k] = 0.0;
-        if (k < size) {
-            // ---- tree 1: squares below row k of every remaining column -------------------------------------
-            const bool below = lane > k;  // slot 0 rows below the diagonal (higher slots always are)
-            double sq[NC];
-#pragma unroll
-            for (int j = k; j < NC; j++) {
-                double v = below ? a[0][j] * a[0][j] : 0.0;
+            for (int j = 0; j < NC; j++) {
+                double v = from_diag ? a[0][j] * a[0][j] : 0.0;
 #pragma unroll
                 for (int sl = 1; sl < R; sl++) v += a[sl][j] * a[sl][j];
                 sq[j] = v;
@@ -1395,292 +1417,116 @@ __device__ __noinline__ void colpiv_qr_solve_reg(int wb, int rows, int x_off) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int j = k; j < NC; j++) sq[j] += __shfl_xor_sync(FKS_FULL, sq[j], o);
-            double dk[NC], nsq[NC];  // entry of row k, squared residual norm (rows >= k)
+                for (int j = 0; j < NC; j++) sq[j] += __shfl_xor_sync(FKS_FULL, sq[j], o);
+            if (!reduce_only) {
+                if (k == 0) {  // Eigen: colNormsUpdated.maxCoeff()
+                    double mx = 0.0;
 #pragma unroll
-            for (int j = k; j < NC; j++) {
-                dk[j] = __shfl_sync(FKS_FULL, a[0][j], k);
-                nsq[j] = dk[j] * dk[j] + sq[j];
-            }
-            if (k == 0) {  // threshold from the largest initial column norm (Eigen: colNormsUpdated.maxCoeff())
-                double mx = 0.0;
-#pragma unroll
-                for (int j = 0; j < NC; j++) mx = fmax(mx, nsq[j]);
-                threshold_helper = (mx * (eps * eps)) / (double)rows;
-            }
-            int biggest = k;
-            double big_sq = nsq[k];
-#pragma unroll
-            for (int j = k + 1; j < NC; j++)
-                if (nsq[j] > big_sq) {
-                    big_sq = nsq[j];
-                    biggest = j;
+                    for (int j = 0; j < NC; j++) mx = fmax(mx, sq[j]);
+                    threshold_helper = (mx * (DBL_EPSILON * DBL_EPSILON)) / (double)rows_thr;
                 }
-            const double cut = threshold_helper * (double)(rows - k);
-            if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
-            if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
-            transp |= (unsigned)biggest << (4 * k);
-            // ---- swap columns k <-> biggest (registers, runtime `biggest`) ----------------------------------
-            double tail_sq = sq[k], c0 = dk[k];
+                double big_sq = -1.0;
+                int best_pos = NC;
 #pragma unroll
-            for (int j = k + 1; j < NC; j++)
-                if (j == biggest) {
-                    tail_sq = sq[j];
-                    c0 = dk[j];
-#pragma unroll
-                    for (int sl = 0; sl < R; sl++) {
-                        const double t = a[sl][k];
-                        a[sl][k] = a[sl][j];
-                        a[sl][j] = t;
+                for (int j = 0; j < NC; j++) {
+                    const int pj = (int)((pos >> (4 * j)) & 0xFu);
+                    if (pj >= k && (sq[j] > big_sq || (sq[j] == big_sq && pj < best_pos))) {
+                        big_sq = sq[j];
+                        best_pos = pj;
+                        p = j;
                     }
                 }
-            // ---- makeHouseholderInPlace on col(k).tail(rows - k) ---------------------------------------------
-            double tau, beta;
-            if (tail_sq <= DBL_MIN) {
-                tau = 0.0;
-                beta = c0;
-                if (below) a[0][k] = 0.0;
+                const double cut = threshold_helper * (double)(rows_thr - k);
+                if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
+                if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
+                // the column that sat at position k takes the pivot's old position, the pivot takes position k
 #pragma unroll
-                for (int sl = 1; sl < R; sl++) a[sl][k] = 0.0;
-            } else {
-                beta = sqrt(c0 * c0 + tail_sq);
-                if (c0 >= 0.0) beta = -beta;
-                const double denom = c0 - beta;
-                if (below) a[0][k] = a[0][k] / denom;
-#pragma unroll
-                for (int sl = 1; sl < R; sl++) a[sl][k] = a[sl][k] / denom;
-                tau = (beta - c0) / beta;
+                for (int j = 0; j < NC; j++)
+                    if ((int)((pos >> (4 * j)) & 0xFu) == k) pos = (pos & ~(0xFu << (4 * j))) | ((unsigned)best_pos << (4 * j));
+                pos = (pos & ~(0xFu << (4 * p))) | ((unsigned)k << (4 * p));
             }
-            rdiag[k] = 1.0 / beta;
-            if (lane == k) a[0][k] = beta;
-            const bool apply_b = nonzero_pivots > k;  // Eigen's solve applies the first nonzero_pivots reflectors to c
-            // ---- applyHouseholderOnTheLeft to the trailing columns (and the right-hand side) -----------------
-            if (rows - k == 1) {
-                if (lane == k) {
-#pragma unroll
-                    for (int j = k + 1; j < NC; j++) a[0][j] *= (1.0 - tau);
-                    if (apply_b) a[0][NC] *= (1.0 - tau);
-                }
-            } else if (tau != 0.0) {
-                double dt[NC + 1];
-#pragma unroll
-                for (int j = k + 1; j <= NC; j++) {
-                    double v = below ? a[0][k] * a[0][j] : 0.0;
-#pragma unroll
-                    for (int sl = 1; sl < R; sl++) v += a[sl][k] * a[sl][j];
-                    dt[j] = v;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int j = k + 1; j <= NC; j++) dt[j] += __shfl_xor_sync(FKS_FULL, dt[j], o);
-#pragma unroll
-                for (int j = k + 1; j <= NC; j++) {
-                    if (j == NC && !apply_b) continue;
-                    const double tmp = dt[j] + __shfl_sync(FKS_FULL, a[0][j], k);
-                    if (lane == k) a[0][j] -= tau * tmp;
-                    else if (below) a[0][j] -= (tau * a[0][k]) * tmp;
-#pragma unroll
-                    for (int sl = 1; sl < R; sl++) a[sl][j] -= (tau * a[sl][k]) * tmp;
-                }
-            }
+            nsq_p = select_col<NC>(p, sq);
         }
-    }
-    if (near_cut && lane == 0) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
-    // back substitution on the leading nz x nz upper triangle: lane i owns row i
-    double y[NC];
-    double sres = a[0][NC];
+        order |= (unsigned)p << (4 * k);
+        // ---- makeHouseholderInPlace on the pivot column ----------------------------------------------------------
+        double v[R];
 #pragma unroll
-    for (int j = NC - 1; j >= 0; j--) {
-        y[j] = 0.0;
-        if (j < nonzero_pivots) {
-            y[j] = __shfl_sync(FKS_FULL, sres * rdiag[j], j);
-            sres -= a[0][j] * y[j];
-        }
-    }
-    if (lane < NC) ws[x_off + lane] = 0.0;
-    __syncwarp();
-    if (lane == 0) {
-        unsigned long long perm = 0xFEDCBA9876543210ull;
-        for (int k = 0; k < size; k++) {
-            const int t = (int)((transp >> (4 * k)) & 0xFu);
-            const unsigned long long pk = (perm >> (4 * k)) & 0xFull, pt = (perm >> (4 * t)) & 0xFull;
-            perm &= ~((0xFull << (4 * k)) | (0xFull << (4 * t)));
-            perm |= (pt << (4 * k)) | (pk << (4 * t));
-        }
+        for (int sl = 0; sl < R; sl++) v[sl] = select_col<NC>(p, a[sl]);
+        const double c0 = __shfl_sync(FKS_FULL, v[0], k);
+        // Eigen skips the reflection when the tail's squared norm is <= DBL_MIN.  nsq_p - c0^2 would lose a tail below
+        // ~1e-8 |c0| to cancellation, so the test is made on the entries themselves.
+        bool tail_entry = lane > k && v[0] != 0.0;
 #pragma unroll
-        for (int i = 0; i < NC; i++)
-            if (i < nonzero_pivots) ws[x_off + (int)((perm >> (4 * i)) & 0xFull)] = y[i];
-    }
-    __syncwarp();
-}
-
-// The same algorithm for taller systems (rows > 128): the matrix stays in the scratch slot (column major, L1/L2) and
-// every step makes a few passes over the rows with one accumulator per column, so the reductions are again two
-// interleaved shuffle trees per step instead of one tree per column as in the generic solver.  The step loop is rolled
-// (columns are addressed in memory, so a run-time column index costs nothing).
-template <int NC>
-__device__ __noinline__ void colpiv_qr_solve_mem(int wb, int rows, int x_off) {
-    const Frame& fr = frame();
-    const int lane = lane_id();
-    double* ws = wsd(wb);
-    double* A = reinterpret_cast<double*>(scratch_slot() + fr.a.sl.jstore);
-    const int ld = fr.a.sl.ldj;
-    double* bcol = A + (size_t)NC * ld;
-    double* rdiag = ws + fr.a.wl.qr;  // 1 / R(k,k)
-    const int size = rows < NC ? rows : NC;
-    const double eps = DBL_EPSILON;
-    double threshold_helper = 0.0;
-    int nonzero_pivots = size;
-    unsigned transp = 0u;
-    bool near_cut = false;
-#pragma unroll 1
-    for (int k = 0; k < size; k++) {
-        // ---- pass 1: squares below row k of the columns k .. NC-1, and their row-k entries ------------------
-        double sq[NC], dk[NC];
-#pragma unroll
-        for (int j = 0; j < NC; j++) sq[j] = 0.0;
-        for (int r = k + 1 + lane; r < rows; r += 32) {
-#pragma unroll
-            for (int j = 0; j < NC; j++)
-                if (j >= k) {
-                    const double v = A[(size_t)j * ld + r];
-                    sq[j] += v * v;
-                }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int j = 0; j < NC; j++) sq[j] += __shfl_xor_sync(FKS_FULL, sq[j], o);
-#pragma unroll
-        for (int j = 0; j < NC; j++) dk[j] = (j >= k) ? A[(size_t)j * ld + k] : 0.0;
-        if (k == 0) {
-            double mx = 0.0;
-#pragma unroll
-            for (int j = 0; j < NC; j++) mx = fmax(mx, dk[j] * dk[j] + sq[j]);
-            threshold_helper = (mx * (eps * eps)) / (double)rows;
-        }
-        int biggest = k;
-        double big_sq = -1.0, tail_sq = 0.0, c0 = 0.0;
-#pragma unroll
-        for (int j = 0; j < NC; j++) {
-            const double n2 = dk[j] * dk[j] + sq[j];
-            if (j >= k && n2 > big_sq) {  // first maximum wins
-                big_sq = n2;
-                biggest = j;
-                tail_sq = sq[j];
-                c0 = dk[j];
-            }
-        }
-        const double cut = threshold_helper * (double)(rows - k);
-        if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
-        if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
-        transp |= (unsigned)biggest << (4 * k);
-        __syncwarp();
-        // ---- swap columns k <-> biggest (all rows: the finished part of R moves too) --------------------------
-        double* ck = A + (size_t)k * ld;
-        if (biggest != k) {
-            double* cb = A + (size_t)biggest * ld;
-            for (int r = lane; r < rows; r += 32) {
-                const double t = ck[r];
-                ck[r] = cb[r];
-                cb[r] = t;
-            }
-        }
-        // ---- makeHouseholderInPlace ---------------------------------------------------------------------------
-        double tau, beta, inv_denom = 0.0;
-        const bool zero_tail = tail_sq <= DBL_MIN;
-        if (zero_tail) {
-            tau = 0.0;
-            beta = c0;
-        } else {
-            beta = sqrt(c0 * c0 + tail_sq);
+        for (int sl = 1; sl < R; sl++) tail_entry = tail_entry || v[sl] != 0.0;
+        double tau = 0.0, beta = c0;
+        if (__any_sync(FKS_FULL, tail_entry)) {
+            beta = sqrt(nsq_p);
             if (c0 >= 0.0) beta = -beta;
-            inv_denom = c0 - beta;
+            const double inv_denom = 1.0 / (c0 - beta);
+            v[0] = (lane > k) ? v[0] * inv_denom : 0.0;
+#pragma unroll
+            for (int sl = 1; sl < R; sl++) v[sl] *= inv_denom;
             tau = (beta - c0) / beta;
         }
-        __syncwarp();
-        const bool apply_b = nonzero_pivots > k;
-        // ---- pass 2: scale the tail and form the dot products with the trailing columns and the right-hand side --
-        double dt[NC + 1];
+        if (lane == k) {
+            v[0] = 1.0;
+            rdiag_mine = 1.0 / beta;
 #pragma unroll
-        for (int j = 0; j <= NC; j++) dt[j] = 0.0;
-        for (int r = k + 1 + lane; r < rows; r += 32) {
-            const double v = zero_tail ? 0.0 : ck[r] / inv_denom;
-            ck[r] = v;
-#pragma unroll
-            for (int j = 0; j < NC; j++)
-                if (j > k) dt[j] += v * A[(size_t)j * ld + r];
-            dt[NC] += v * bcol[r];
+            for (int j = 0; j < NC; j++) a[0][j] = (j == p) ? beta : a[0][j];
         }
-        if (lane == 0) {
-            rdiag[k] = 1.0 / beta;
-            ck[k] = beta;
-        }
+        const bool apply_b = reduce_only || nonzero_pivots > k;  // Eigen's solve applies the first nonzero_pivots reflectors to c
+        // ---- applyHouseholderOnTheLeft to the remaining columns and the right-hand side ----------------------------
+        // (a single remaining row, rows - k == 1, is the same formula with an empty tail: a -= tau * a)
+        if (tau != 0.0) {
+            double dt[NC + 1];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+            for (int j = 0; j <= NC; j++) {
+                double t = (lane >= k) ? v[0] * a[0][j] : 0.0;
 #pragma unroll
-            for (int j = 0; j <= NC; j++) dt[j] += __shfl_xor_sync(FKS_FULL, dt[j], o);
-        __syncwarp();
-        // ---- pass 3: apply the reflector ----------------------------------------------------------------------
-        if (rows - k == 1) {
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < NC; j++)
-                    if (j > k) A[(size_t)j * ld + k] *= (1.0 - tau);
-                if (apply_b) bcol[k] *= (1.0 - tau);
+                for (int sl = 1; sl < R; sl++) t += v[sl] * a[sl][j];
+                dt[j] = t;
             }
-        } else if (tau != 0.0) {
-            double tmp[NC + 1];
 #pragma unroll
-            for (int j = 0; j < NC; j++) tmp[j] = (j > k) ? dt[j] + A[(size_t)j * ld + k] : 0.0;
-            tmp[NC] = dt[NC] + bcol[k];
-            __syncwarp();
-            if (lane == 0) {
+            for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                for (int j = 0; j < NC; j++)
-                    if (j > k) A[(size_t)j * ld + k] -= tau * tmp[j];
-                if (apply_b) bcol[k] -= tau * tmp[NC];
-            }
-            for (int r = k + 1 + lane; r < rows; r += 32) {
-                const double tv = tau * ck[r];
+                for (int j = 0; j <= NC; j++) dt[j] += __shfl_xor_sync(FKS_FULL, dt[j], o);
 #pragma unroll
-                for (int j = 0; j < NC; j++)
-                    if (j > k) A[(size_t)j * ld + r] -= tv * tmp[j];
-                if (apply_b) bcol[r] -= tv * tmp[NC];
+            for (int j = 0; j <= NC; j++) {
+                const bool active = (j == NC) ? apply_b : ((int)((pos >> (4 * (j < NC ? j : 0))) & 0xFu) > k);
+                if (active) {
+                    const double tmp = tau * dt[j];
+                    if (lane >= k) a[0][j] -= v[0] * tmp;
+#pragma unroll
+                    for (int sl = 1; sl < R; sl++) a[sl][j] -= v[sl] * tmp;
+                }
             }
         }
+    }
+    if (reduce_only) {  // R == 2, a full chunk of 64 rows
+        __syncwarp();   // every lane has read its rows before the last NC of them are overwritten
+        if (lane < NC) {
+#pragma unroll
+            for (int c = 0; c <= NC; c++) A[(size_t)c * ld + (64 - NC) + lane] = (c < lane) ? 0.0 : a[0][c];
+        }
         __syncwarp();
+        return row0 + 64 - NC;
     }
     if (near_cut && lane == 0) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
+    // back substitution on the leading nz x nz triangle (lane i owns row i), unknowns written in column order
     if (lane < NC) ws[x_off + lane] = 0.0;
     __syncwarp();
-    if (lane == 0 && nonzero_pivots > 0) {
-        double y[NC];
-#pragma unroll
-        for (int i = NC - 1; i >= 0; i--) {
-            y[i] = 0.0;
-            if (i < nonzero_pivots) {
-                double sacc = bcol[i];
-#pragma unroll
-                for (int j = i + 1; j < NC; j++)
-                    if (j < nonzero_pivots) sacc -= A[(size_t)j * ld + i] * y[j];
-                y[i] = sacc * rdiag[i];
-            }
-        }
-        unsigned long long perm = 0xFEDCBA9876543210ull;
-        for (int k = 0; k < size; k++) {
-            const int t = (int)((transp >> (4 * k)) & 0xFu);
-            const unsigned long long pk = (perm >> (4 * k)) & 0xFull, pt = (perm >> (4 * t)) & 0xFull;
-            perm &= ~((0xFull << (4 * k)) | (0xFull << (4 * t)));
-            perm |= (pt << (4 * k)) | (pk << (4 * t));
-        }
-#pragma unroll
-        for (int i = 0; i < NC; i++)
-            if (i < nonzero_pivots) ws[x_off + (int)((perm >> (4 * i)) & 0xFull)] = y[i];
+    double sres = a[0][NC];
+#pragma unroll 1
+    for (int i = nonzero_pivots - 1; i >= 0; i--) {
+        const int pc = (int)((order >> (4 * i)) & 0xFu);
+        const double yi = __shfl_sync(FKS_FULL, sres * rdiag_mine, i);
+        sres -= select_col<NC>(pc, a[0]) * yi;
+        if (lane == 0) ws[x_off + pc] = yi;
     }
     __syncwarp();
+    return 0;
 }
+
 
 // actuator noise of the next `count` microsteps, one truncated-normal draw per axis in axis order
 __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned step, unsigned micro0, int count,
@@ -1788,6 +1634,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #ifdef FKS_PHASE_TIMERS
     long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tqr[4] = {0, 0, 0, 0};
+    long long textra[4] = {0, 0, 0, 0};  // super-cycles, sum of solver warps, group-1 extra rounds, estimate clocks
     long long t0 = clock64(), t1;
 #define FKS_TICK(i) { t1 = clock64(); tacc[i] += t1 - t0; t0 = t1; }
 #else
@@ -2133,6 +1980,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         if (round == 0) {
             n_solvers = __syncthreads_count(want_solve) >> 5;  // full barrier; the count is in threads
             FKS_TICK(5)
+#ifdef FKS_PHASE_TIMERS
+            textra[0] += 1;
+            textra[1] += n_solvers;
+#endif
             if (n_solvers == 0) break;         // nobody solves: next super-cycle
             counted_solver = want_solve;
             if (want_solve) break;             // group 2 goes to collect + solve
@@ -2141,7 +1992,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         }
         // group 1 only: another round while group 2 is still busy (decision made uniform by the barrier reduction)
         const bool keep = (*g2_done < (unsigned)n_solvers) && (round < 16);
-        if (!named_barrier_or(1, bar_threads, keep)) break;
+        const bool go_on = named_barrier_or(1, bar_threads, keep);
+        FKS_TICK(1)
+#ifdef FKS_PHASE_TIMERS
+        textra[2] += 1;
+#endif
+        if (!go_on) break;
         }  // rounds
         // =========================== phase C: collect corrections (spcs:1627) ==========================
         if (counted_solver) {
@@ -2168,40 +2024,31 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 wv->flags |= FKS_FLAG_EMPTY_JACOBIAN;
                 if (lane < D) ws[wl.raw + lane] = 0.0;
                 __syncwarp();
-            } else if (rows <= 32 && KIND == FKS_ROBOT_SE2) {
-                colpiv_qr_solve_reg<3, 1>(wb, rows, wl.raw);
-            } else if (rows <= 32 && KIND == FKS_ROBOT_SE3) {
-                colpiv_qr_solve_reg<6, 1>(wb, rows, wl.raw);
-            } else if (rows <= 32 && KIND == FKS_ROBOT_LINKED && D == 7) {
-                colpiv_qr_solve_reg<7, 1>(wb, rows, wl.raw);
-            } else if (rows <= 64 && KIND == FKS_ROBOT_SE2) {
-                colpiv_qr_solve_reg<3, 2>(wb, rows, wl.raw);
-            } else if (rows <= 64 && KIND == FKS_ROBOT_SE3) {
-                colpiv_qr_solve_reg<6, 2>(wb, rows, wl.raw);
-            } else if (rows <= 64 && KIND == FKS_ROBOT_LINKED && D == 7) {
-                colpiv_qr_solve_reg<7, 2>(wb, rows, wl.raw);
-            } else if (rows <= 128 && KIND == FKS_ROBOT_SE2) {
-                colpiv_qr_solve_reg<3, 4>(wb, rows, wl.raw);
-            } else if (rows <= 128 && KIND == FKS_ROBOT_SE3) {
-                colpiv_qr_solve_reg<6, 4>(wb, rows, wl.raw);
-            } else if (rows <= 128 && KIND == FKS_ROBOT_LINKED && D == 7) {
-                colpiv_qr_solve_reg<7, 4>(wb, rows, wl.raw);
-            } else if (KIND == FKS_ROBOT_SE2) {
-                colpiv_qr_solve_mem<3>(wb, rows, wl.raw);
-            } else if (KIND == FKS_ROBOT_SE3) {
-                colpiv_qr_solve_mem<6>(wb, rows, wl.raw);
-            } else if (KIND == FKS_ROBOT_LINKED && D == 7) {
-                colpiv_qr_solve_mem<7>(wb, rows, wl.raw);
-            } else {
+            } else if (KIND == FKS_ROBOT_LINKED && D != 7) {
                 colpiv_qr_solve(wb, rows, D, wl.raw);
+            } else {
+                constexpr int NCK = KIND == FKS_ROBOT_SE2 ? 3 : (KIND == FKS_ROBOT_SE3 ? 6 : 7);
+                if (rows <= 32) {
+                    qr_rolled<NCK, 1>(wb, rows, wl.raw, 0, rows, false);
+                } else {
+                    int row0 = 0;
+                    while (rows - row0 > 64) row0 = qr_rolled<NCK, 2>(wb, 64, 0, row0, 0, true);
+                    qr_rolled<NCK, 2>(wb, rows - row0, wl.raw, row0, rows, false);
+                }
             }
 #ifdef FKS_PHASE_TIMERS
             if (rows <= 64) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
 #endif
             // motion estimate of the raw correction (spcs:1630) in the same solver slot: one lock-step round per
             // resolver iteration instead of two
+#ifdef FKS_PHASE_TIMERS
+            const long long te0 = clock64();
+#endif
             apply_control<KIND>(wb, cur, 2, wl.raw, -1, 0);
             m_result = max_motion(wb, cur, 2);
+#ifdef FKS_PHASE_TIMERS
+            textra[3] += clock64() - te0;
+#endif
             {  // spcs:1681-1689
                 const double step_fraction = fmax(m_result / allowed_microstep_distance, 1.0);
                 if (lane < D) ws[wl.stepv + lane] = (ws[wl.raw + lane] / step_fraction) * fabs(wv->scaling);
@@ -2225,6 +2072,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
     {
         for (int i = 0; i < 12; i++) atomicAdd(a.stats + 16 + i, (unsigned long long)tacc[i]);
         for (int i = 0; i < 4; i++) atomicAdd(a.stats + 28 + i, (unsigned long long)tqr[i]);
+        for (int i = 0; i < 4; i++) atomicAdd(a.stats + 32 + i, (unsigned long long)textra[i]);
     }
 #endif
     __syncwarp();

@@ -35,15 +35,20 @@ def run(name, n, free=False, reps=3):
         s["total_microsteps"] / best * 1e3, int(((rec["flags"] & 2) != 0).sum()), int((rec["flags"] & 1).sum())), flush=True)
     import ctypes as C
     if hasattr(capi.lib, "fks_debug_phase_cycles"):
-        ph = (C.c_uint64 * 16)()
+        ph = (C.c_uint64 * 48)()
         capi.lib.fks_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
         capi.lib.fks_debug_phase_cycles(sim._h, ph)
         tot = float(sum(ph[:10])) or 1.0
         if sum(ph[:10]):
-            names = ["A apply", "bar1", "B measure", "bar2", "T trans", "bar3", "C collect", "bar4", "D solve", "bar5"]
-            print("    phases: " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(names, ph)), flush=True)
-            print("    per call: collect %.0f clk (n=%d), qr<=64rows %.0f clk (n=%d), qr>64rows %.0f clk (n=%d)" % (
-                ph[10] / max(ph[11], 1), ph[11], ph[12] / max(ph[13], 1), ph[13], ph[14] / max(ph[15], 1), ph[15]), flush=True)
+            names = ["A apply", "group-1 barrier", "B measure", "-", "T trans", "full barrier", "C collect", "solver barrier", "D solve+estimate", "end barrier"]
+            print("    warp clocks: " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(names, ph)), flush=True)
+            print("    per call: collect %.0f clk (n=%d), qr<=64rows %.0f clk (n=%d), qr>64rows %.0f clk (n=%d), estimate %.0f clk" % (
+                ph[10] / max(ph[11], 1), ph[11], ph[12] / max(ph[13], 1), ph[13], ph[14] / max(ph[15], 1), ph[15],
+                ph[19] / max(ph[11], 1)), flush=True)
+            nw = 148 * 32  # counters are summed over all warps
+            sc = ph[16] / nw
+            print("    super-cycles per CTA %.0f (%.0f clk each), solver warps per super-cycle %.1f, group-1 extra rounds per warp %.0f" % (
+                sc, tot / nw / max(sc, 1), ph[17] / max(ph[16], 1), ph[18] / nw), flush=True)
     sim.close()
 
 
