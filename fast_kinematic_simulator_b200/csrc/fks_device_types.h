@@ -224,6 +224,7 @@ struct LaunchArgs {
 struct Frame {
     LaunchArgs a;
     DevRobot rb;
+    double gbase[12];  // (1 / sdf_res) * inverse_origin * base: root of the world->voxel chain (linked robots)
 };
 
 // launch interface implemented in fks_kernels.cu

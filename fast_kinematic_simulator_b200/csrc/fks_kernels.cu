@@ -337,17 +337,25 @@ __device__ __noinline__ void kinematics(int wb, int X, int derive) {
 #pragma unroll
             for (int i = 0; i < 12; i++) M[12 * j + i] = Mj[i];
         }
+        // chain T_child = T_parent * M_j on lanes 0..11; lanes 12..23 run the SAME recurrence from the root
+        // (1 / res) * inverse_origin * base, which yields the world->voxel transforms G_l = (1 / res) * inverse_origin * T_l
+        // in the same instructions (they were a separate pass of 3 x 12 L products)
+        double* G = ws + wl.G;
         if (lane < 12) T[lane] = rb.base[lane];
+        else if (lane < 24 && derive) G[lane - 12] = fr.gbase[lane - 12];
         __syncwarp();
-        const int r = lane >> 2, cc = lane & 3;
+        const int e12 = lane < 12 ? lane : lane - 12;
+        const int r = e12 >> 2, cc = e12 & 3;
+        double* chain = lane < 12 ? T : G;
+        const bool in_chain = lane < 12 || (lane < 24 && derive);
         for (int j = 0; j < rb.J; j++) {
             const DevJoint& jd = rb.joints[j];
-            if (lane < 12) {
-                const double* Tp = T + 12 * jd.parent;
+            if (in_chain) {
+                const double* Tp = chain + 12 * jd.parent;
                 const double* Mj = M + 12 * j;
                 double v = Tp[4 * r + 0] * Mj[cc] + Tp[4 * r + 1] * Mj[4 + cc] + Tp[4 * r + 2] * Mj[8 + cc];
                 if (cc == 3) v += Tp[4 * r + 3];
-                T[12 * jd.child + lane] = v;
+                chain[12 * jd.child + e12] = v;
             }
             __syncwarp();
         }
@@ -355,6 +363,7 @@ __device__ __noinline__ void kinematics(int wb, int X, int derive) {
     if (derive) {
         const DevEnv& e = fr.a.env;
         double* G = ws + wl.G;
+        if (KIND != FKS_ROBOT_LINKED)
         for (int el = lane; el < wl.L12; el += 32) {
             const int l = el / 12, rc = el - 12 * l, r = rc >> 2, cc = rc & 3;
             const double* Tl = T + 12 * l;
@@ -1603,6 +1612,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             pxy[i] = args.pxy[i];
             pzl[i] = args.pzl[i];
         }
+        if (threadIdx.x < 12) {  // root of the world->voxel chain of the linked robot (kinematics)
+            const int r = threadIdx.x >> 2, c = threadIdx.x & 3;
+            const double* io = args.env.inv_origin;
+            const double* bs = args.robot->base;
+            double v = io[4 * r + 0] * bs[c] + io[4 * r + 1] * bs[4 + c] + io[4 * r + 2] * bs[8 + c];
+            if (c == 3) v += io[4 * r + 3];
+            f->gbase[threadIdx.x] = v * args.env.inv_sdf_res;
+        }
         if (threadIdx.x < 4) reinterpret_cast<unsigned*>(smem_raw + args.sync_off)[threadIdx.x] = 0u;
     }
     __syncthreads();
@@ -2167,6 +2184,14 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) check_config
         for (int i = threadIdx.x; i < args.P; i += blockDim.x) {
             pxy[i] = args.pxy[i];
             pzl[i] = args.pzl[i];
+        }
+        if (threadIdx.x < 12) {  // root of the world->voxel chain of the linked robot (kinematics)
+            const int r = threadIdx.x >> 2, c = threadIdx.x & 3;
+            const double* io = args.env.inv_origin;
+            const double* bs = args.robot->base;
+            double v = io[4 * r + 0] * bs[c] + io[4 * r + 1] * bs[4 + c] + io[4 * r + 2] * bs[8 + c];
+            if (c == 3) v += io[4 * r + 3];
+            f->gbase[threadIdx.x] = v * args.env.inv_sdf_res;
         }
     }
     __syncthreads();
