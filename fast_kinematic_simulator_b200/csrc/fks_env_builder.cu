@@ -428,17 +428,24 @@ struct Temps {
     std::vector<void*> ptrs;
     std::vector<cudaEvent_t> events;
     int prev_device = -1;
+    // temporaries come from the device's stream-ordered pool (no synchronising cudaMalloc / cudaFree inside the build;
+    // up to 256 MiB stays cached in the pool between builds, see fks_env_build_device)
     ~Temps() {
-        for (void* p : ptrs) cudaFree(p);
+        for (void* p : ptrs) cudaFreeAsync(p, 0);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         if (prev_device >= 0) cudaSetDevice(prev_device);
     }
     template <typename T>
     cudaError_t alloc(T** p, size_t n) {
         *p = nullptr;
-        cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+        cudaError_t e = pooled_alloc((void**)p, std::max<size_t>(n, 1) * sizeof(T), 0);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
+    }
+    // small blocks from the stream-ordered pool, large ones (which would make the pool grow and shrink by hundreds of MB
+    // on every build) from cudaMalloc; cudaFree / cudaFreeAsync accept both kinds
+    static cudaError_t pooled_alloc(void** p, size_t bytes, cudaStream_t st) {
+        return bytes <= (64u << 20) ? cudaMallocAsync(p, bytes, st) : cudaMalloc(p, bytes);
     }
 };
 
@@ -522,6 +529,12 @@ extern "C" int fks_env_build_device(int device, const fks_obstacle* obstacles, s
     cudaDeviceProp prop;
     FKS_TRY(cudaGetDeviceProperties(&prop, device));
     const int sms = prop.multiProcessorCount;
+    {
+        cudaMemPool_t pool;
+        unsigned long long keep = 256ull << 20;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaGetLastError();
+    }
     cudaStream_t st = 0;
     for (int i = 0; i < 8; i++) {
         cudaEvent_t e;
@@ -597,12 +610,13 @@ extern "C" int fks_env_build_device(int device, const fks_obstacle* obstacles, s
     FKS_TRY(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
     FKS_TRY(cudaStreamSynchronize(st));
     const size_t n_normal_cells = (size_t)(total >> 32), n_entries = (size_t)(total & 0xffffffffull);
+    // the table arrays also come from the stream-ordered pool (fks_env_destroy releases them with cudaFree, which accepts both)
     size_t cap = 2;
     while (cap < 2 * n_normal_cells) cap <<= 1;
-    FKS_TRY(cudaMalloc((void**)&env->d_keys, 2 * cap * sizeof(unsigned long long)));
-    FKS_TRY(cudaMalloc((void**)&env->d_entries, std::max<size_t>(n_entries, 1) * 6 * sizeof(double)));
-    FKS_TRY(cudaMalloc((void**)&env->d_cell_index, std::max<size_t>(n_normal_cells, 1) * sizeof(long long)));
-    FKS_TRY(cudaMalloc((void**)&env->d_cell_start, (n_normal_cells + 1) * sizeof(unsigned)));
+    FKS_TRY(Temps::pooled_alloc((void**)&env->d_keys, 2 * cap * sizeof(unsigned long long), st));
+    FKS_TRY(Temps::pooled_alloc((void**)&env->d_entries, std::max<size_t>(n_entries, 1) * 6 * sizeof(double), st));
+    FKS_TRY(Temps::pooled_alloc((void**)&env->d_cell_index, std::max<size_t>(n_normal_cells, 1) * sizeof(long long), st));
+    FKS_TRY(Temps::pooled_alloc((void**)&env->d_cell_start, (n_normal_cells + 1) * sizeof(unsigned), st));
     FKS_TRY(cudaMemsetAsync(env->d_keys, 0, 2 * cap * sizeof(unsigned long long), st));
     FKS_TRY(cudaMemsetAsync(env->d_entries, 0, std::max<size_t>(n_entries, 1) * 6 * sizeof(double), st));
     normals_emit_kernel<<<(unsigned)n_blocks, kScanThreads, 0, st>>>(d_obs, g, env->d_sdf, d_winner, d_count, d_block_sums, env->d_cell_index,
