@@ -2029,7 +2029,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #endif
             if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
             FKS_TICK(6)
-            named_barrier(2, 32 * n_solvers);
+            // the solvers of this super-cycle agree on ONE copy of the QR code: the two-slot copy if any of them has more than
+            // 32 rows, else the one-slot copy -- two copies live at once cost more in instruction fetch than the second row
+            // slot costs the small systems (A/B in profiles/r1_kernel_experiments.md)
+            const bool any_tall = named_barrier_or(2, 32 * n_solvers, rows > 32);
             FKS_TICK(7)
             // ======================= phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
 #ifdef FKS_PHASE_TIMERS
@@ -2045,7 +2048,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 colpiv_qr_solve(wb, rows, D, wl.raw);
             } else {
                 constexpr int NCK = KIND == FKS_ROBOT_SE2 ? 3 : (KIND == FKS_ROBOT_SE3 ? 6 : 7);
-                if (rows <= 32) {
+                if (!any_tall) {
                     qr_rolled<NCK, 1>(wb, rows, wl.raw, 0, rows, false);
                 } else {
                     int row0 = 0;
