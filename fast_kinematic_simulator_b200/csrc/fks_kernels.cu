@@ -1377,6 +1377,44 @@ __device__ __noinline__ void colpiv_qr_solve(int wb, int rows, int cols, int x_o
 // makes the same pivot choices, rank decision (rows_thr = the ORIGINAL row count enters Eigen's threshold) and solution as
 // the one of the full system up to round-off -- the same class of difference as the summation order of the trees.  This
 // replaced a four-slot register variant (spilled at 64 registers) and a memory-resident one for > 128 rows.
+// Sum of N (4 or 8) per-lane values over the warp by a HALVING butterfly: at each of the first log2(N) levels a lane keeps
+// one half of its values and sends the other half to its partner, so the level costs N/2, N/4, ... exchanges instead of N;
+// the remaining levels are plain butterflies on the single value left.  Lane l ends with the total of value fold_index(l);
+// fold_lane(j) is a lane that holds the total of value j.  9 exchanges for 8 values instead of 40.
+template <int N>
+__device__ __forceinline__ int fold_index(int lane) {
+    return N == 8 ? (((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1) : (((lane >> 4) & 1) << 1) | ((lane >> 3) & 1);
+}
+template <int N>
+__device__ __forceinline__ int fold_lane(int j) {
+    return N == 8 ? ((j & 4) << 2) | ((j & 2) << 2) | ((j & 1) << 2) : ((j & 2) << 3) | ((j & 1) << 3);
+}
+template <int N>
+__device__ __forceinline__ double warp_fold(const double (&v)[N], int lane) {
+    double w[N / 2];
+    {
+        const bool hi = (lane & 16) != 0;
+#pragma unroll
+        for (int j = 0; j < N / 2; j++) w[j] = (hi ? v[j + N / 2] : v[j]) + __shfl_xor_sync(FKS_FULL, hi ? v[j] : v[j + N / 2], 16);
+    }
+    double x[N / 4];
+    {
+        const bool hi = (lane & 8) != 0;
+#pragma unroll
+        for (int j = 0; j < N / 4; j++) x[j] = (hi ? w[j + N / 4] : w[j]) + __shfl_xor_sync(FKS_FULL, hi ? w[j] : w[j + N / 4], 8);
+    }
+    double y;
+    if (N == 8) {
+        const bool hi = (lane & 4) != 0;
+        y = (hi ? x[N / 4 - 1] : x[0]) + __shfl_xor_sync(FKS_FULL, hi ? x[0] : x[N / 4 - 1], 4);
+    } else {
+        y = x[0] + __shfl_xor_sync(FKS_FULL, x[0], 4);
+    }
+    y += __shfl_xor_sync(FKS_FULL, y, 2);
+    y += __shfl_xor_sync(FKS_FULL, y, 1);
+    return y;
+}
+
 template <int NC>
 __device__ __forceinline__ double select_col(int p, const double (&v)[NC + 1]) {
     double r = v[0];
@@ -1408,43 +1446,46 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
     unsigned order = 0u;        // 4 bits per step: the column picked at step k
     unsigned pos = 0x76543210u; // 4 bits per column: its position in the permuted order
     bool near_cut = false;
+    constexpr int NF = (NC + 1 <= 4) ? 4 : 8;  // width of the folded reductions
 #pragma unroll 1
     for (int k = 0; k < size; k++) {
         const bool from_diag = lane >= k;  // slot-0 rows not yet finished (rows above the diagonal row belong to R)
         int p = k;
         double nsq_p;
         {
-            // ---- tree 1: squared residual norms (rows >= k) of every column ---------------------------------------
-            double sq[NC + 1];
+            // ---- tree 1: squared residual norms (rows >= k) of every column, folded: this lane gets column fold_index --
+            double sq[NF];
 #pragma unroll
-            for (int j = 0; j < NC; j++) {
-                double v = from_diag ? a[0][j] * a[0][j] : 0.0;
+            for (int j = 0; j < NF; j++) {
+                double v = 0.0;
+                if (j < NC) {
+                    v = from_diag ? a[0][j] * a[0][j] : 0.0;
 #pragma unroll
-                for (int sl = 1; sl < R; sl++) v += a[sl][j] * a[sl][j];
+                    for (int sl = 1; sl < R; sl++) v += a[sl][j] * a[sl][j];
+                }
                 sq[j] = v;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int j = 0; j < NC; j++) sq[j] += __shfl_xor_sync(FKS_FULL, sq[j], o);
+            double y = warp_fold<NF>(sq, lane);
             if (!reduce_only) {
-                if (k == 0) {  // Eigen: colNormsUpdated.maxCoeff()
-                    double mx = 0.0;
+                // arg-max over the columns not yet chosen (position >= k), ties to the smallest position (Eigen's scan order):
+                // three more exchange levels between the lane groups that hold different columns
+                int col = fold_index<NF>(lane);
+                int pcol = col < NC ? (int)((pos >> (4 * col)) & 0xFu) : -1;
+                if (pcol < k) y = -1.0;
 #pragma unroll
-                    for (int j = 0; j < NC; j++) mx = fmax(mx, sq[j]);
-                    threshold_helper = (mx * (DBL_EPSILON * DBL_EPSILON)) / (double)rows_thr;
-                }
-                double big_sq = -1.0;
-                int best_pos = NC;
-#pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const int pj = (int)((pos >> (4 * j)) & 0xFu);
-                    if (pj >= k && (sq[j] > big_sq || (sq[j] == big_sq && pj < best_pos))) {
-                        big_sq = sq[j];
-                        best_pos = pj;
-                        p = j;
+                for (int o = 16; o >= (NF == 8 ? 4 : 8); o >>= 1) {
+                    const double oy = __shfl_xor_sync(FKS_FULL, y, o);
+                    const int oc = __shfl_xor_sync(FKS_FULL, col, o), op = __shfl_xor_sync(FKS_FULL, pcol, o);
+                    if (oy > y || (oy == y && op < pcol)) {
+                        y = oy;
+                        col = oc;
+                        pcol = op;
                     }
                 }
+                p = col;
+                const double big_sq = y;
+                const int best_pos = pcol;
+                if (k == 0) threshold_helper = (big_sq * (DBL_EPSILON * DBL_EPSILON)) / (double)rows_thr;  // Eigen: colNormsUpdated.maxCoeff()
                 const double cut = threshold_helper * (double)(rows_thr - k);
                 if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
                 if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
@@ -1453,8 +1494,10 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
                 for (int j = 0; j < NC; j++)
                     if ((int)((pos >> (4 * j)) & 0xFu) == k) pos = (pos & ~(0xFu << (4 * j))) | ((unsigned)best_pos << (4 * j));
                 pos = (pos & ~(0xFu << (4 * p))) | ((unsigned)k << (4 * p));
+                nsq_p = big_sq;
+            } else {
+                nsq_p = __shfl_sync(FKS_FULL, y, fold_lane<NF>(k));
             }
-            nsq_p = select_col<NC>(p, sq);
         }
         order |= (unsigned)p << (4 * k);
         // ---- makeHouseholderInPlace on the pivot column ----------------------------------------------------------
@@ -1487,23 +1530,24 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
         // ---- applyHouseholderOnTheLeft to the remaining columns and the right-hand side ----------------------------
         // (a single remaining row, rows - k == 1, is the same formula with an empty tail: a -= tau * a)
         if (tau != 0.0) {
-            double dt[NC + 1];
+            double dt[NF];
 #pragma unroll
-            for (int j = 0; j <= NC; j++) {
-                double t = (lane >= k) ? v[0] * a[0][j] : 0.0;
+            for (int j = 0; j < NF; j++) {
+                double t = 0.0;
+                if (j <= NC) {
+                    t = (lane >= k) ? v[0] * a[0][j] : 0.0;
 #pragma unroll
-                for (int sl = 1; sl < R; sl++) t += v[sl] * a[sl][j];
+                    for (int sl = 1; sl < R; sl++) t += v[sl] * a[sl][j];
+                }
                 dt[j] = t;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                for (int j = 0; j <= NC; j++) dt[j] += __shfl_xor_sync(FKS_FULL, dt[j], o);
+            const double folded = warp_fold<NF>(dt, lane);
 #pragma unroll
             for (int j = 0; j <= NC; j++) {
                 const bool active = (j == NC) ? apply_b : ((int)((pos >> (4 * (j < NC ? j : 0))) & 0xFu) > k);
+                const double dtj = __shfl_sync(FKS_FULL, folded, fold_lane<NF>(j));
                 if (active) {
-                    const double tmp = tau * dt[j];
+                    const double tmp = tau * dtj;
                     if (lane >= k) a[0][j] -= v[0] * tmp;
 #pragma unroll
                     for (int sl = 1; sl < R; sl++) a[sl][j] -= v[sl] * tmp;
