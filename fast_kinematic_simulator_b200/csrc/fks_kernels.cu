@@ -576,21 +576,23 @@ __device__ __noinline__ double max_motion(int wb, int Xa, int Xb) {
     const Frame& fr = frame();
     const WarpLayout& wl = fr.a.wl;
     const int lane = lane_id();
-    const double* ws = wsd(wb);
+    double* ws = wsd(wb);
     const double* Ta = ws + wl.T + Xa * wl.L12;
-    const double* Tb = ws + wl.T + Xb * wl.L12;
+    double* Tb = ws + wl.T + Xb * wl.L12;
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
     const int P = fr.a.P;
+    // T_b p - T_a p = (T_b - T_a) [p; 1]: the difference of the link transforms is formed once (in place: state Xb is the
+    // scratch state of the motion estimates and is not read again), which halves the work per point
+    for (int el = lane; el < wl.L12; el += 32) Tb[el] = Tb[el] - Ta[el];
+    __syncwarp();
     double mx = 0.0;
 #pragma unroll 2
     for (int p = lane; p < P; p += 32) {
         const double2 xy = pxy[p];
         const PointZL zl = pzl[p];
-        double ax, ay, az, bx, by, bz;
-        apply_T(Ta + 12 * zl.link, xy.x, xy.y, zl.z, ax, ay, az);
-        apply_T(Tb + 12 * zl.link, xy.x, xy.y, zl.z, bx, by, bz);
-        const double dx = bx - ax, dy = by - ay, dz = bz - az;
+        double dx, dy, dz;
+        apply_T(Tb + 12 * zl.link, xy.x, xy.y, zl.z, dx, dy, dz);
         const double sq = dx * dx + dy * dy + dz * dz;
         if (sq > mx) mx = sq;
     }
@@ -1511,18 +1513,20 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
 #pragma unroll
         for (int sl = 1; sl < R; sl++) tail_entry = tail_entry || v[sl] != 0.0;
         double tau = 0.0, beta = c0;
-        if (__any_sync(FKS_FULL, tail_entry)) {
+        const bool has_tail = __any_sync(FKS_FULL, tail_entry);
+        if (has_tail) {
             beta = sqrt(nsq_p);
             if (c0 >= 0.0) beta = -beta;
             const double inv_denom = 1.0 / (c0 - beta);
             v[0] = (lane > k) ? v[0] * inv_denom : 0.0;
 #pragma unroll
             for (int sl = 1; sl < R; sl++) v[sl] *= inv_denom;
-            tau = (beta - c0) / beta;
         }
+        const double inv_beta = 1.0 / beta;  // 1 / R(k,k); tau = (beta - c0) / beta through the same reciprocal
+        if (has_tail) tau = (beta - c0) * inv_beta;
         if (lane == k) {
             v[0] = 1.0;
-            rdiag_mine = 1.0 / beta;
+            rdiag_mine = inv_beta;
 #pragma unroll
             for (int j = 0; j < NC; j++) a[0][j] = (j == p) ? beta : a[0][j];
         }
