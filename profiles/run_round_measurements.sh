@@ -19,4 +19,6 @@ done
 python bench.py --particles 1048576 --steps 2 --warmup 3 --no-cpu-baseline > $O/bench_r1_arm_1m.json 2>> $O/bench_r1.err
 python tests/gpu_perf_env_builder.py > $O/env_builder_r1.log 2>&1
 python tests/gpu_perf_check_config.py > $O/check_config_perf.log 2>&1
+python tests/gpu_big_parity.py > $O/big_parity.log 2>&1
+python tests/gpu_perf.py > $O/gpu_perf_r1.log 2>&1
 echo done
