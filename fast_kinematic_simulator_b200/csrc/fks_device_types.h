@@ -98,7 +98,8 @@ struct WarpVars {
     unsigned long long pid, tape_pos, tape_end;
     double scaling;
     unsigned step, micro, number_microsteps, resolver_iterations, flags, n_micro_total, n_iter_total, n_steps;
-    int collided, any_resolve_failed, step_collided, step_failed, step_stopped, _pad;
+    int collided, any_resolve_failed, step_collided, step_failed, step_stopped;
+    int pend_rows, pend_row0, _pad;  // a tall stacked system folded in the previous solver slot waits for its final solve (pend_rows > 0)
 };
 constexpr int kWarpVarsDoubles = (int)((sizeof(WarpVars) + 7) / 8);
 

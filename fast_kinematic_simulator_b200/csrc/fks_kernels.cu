@@ -1776,6 +1776,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             wv->tape_pos = a.tape_off[wv->pid];
                             wv->tape_end = a.tape_off[wv->pid + 1];
                         }
+                        wv->pend_rows = 0;
                         wv->collided = wv->any_resolve_failed = false;
                         wv->flags = wv->n_micro_total = wv->n_iter_total = wv->n_steps = 0u;
                         wv->step = 0u;
@@ -2070,22 +2071,33 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #ifdef FKS_PHASE_TIMERS
             const long long tc0 = clock64();
 #endif
-            rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
+            // A tall system (more than 64 rows) takes two solver slots: this one collects and folds it to <= 64 rows, the
+            // next one solves it.  The slowest solver warp gates the CTA, and with a dozen solvers per slot one of them is
+            // tall in 3 slots of 4 -- a fold pass AND a solve pass in the same slot made every slot as long as the tall ones.
+            int row0 = 0;
+            const bool resumed = wv->pend_rows > 0;
+            if (resumed) {
+                rows = wv->pend_rows;
+                row0 = wv->pend_row0;
+            } else {
+                rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
+                if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
+            }
 #ifdef FKS_PHASE_TIMERS
             tacc[10] += clock64() - tc0;
             tacc[11] += 1;
 #endif
-            if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
             FKS_TICK(6)
             // the solvers of this super-cycle agree on ONE copy of the QR code: the two-slot copy if any of them has more than
             // 32 rows, else the one-slot copy -- two copies live at once cost more in instruction fetch than the second row
             // slot costs the small systems (A/B in profiles/r1_kernel_experiments.md)
-            const bool any_tall = named_barrier_or(2, 32 * n_solvers, rows > 32);
+            const bool any_tall = named_barrier_or(2, 32 * n_solvers, rows - row0 > 32);
             FKS_TICK(7)
             // ======================= phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
 #ifdef FKS_PHASE_TIMERS
             const long long tq0 = clock64();
 #endif
+            bool deferred = false;
             if (rows == 0) {
                 // Eigen would return an empty vector and ApplyControlInput would assert; documented device
                 // behaviour: zero correction wv->step
@@ -2096,12 +2108,15 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 colpiv_qr_solve(wb, rows, D, wl.raw);
             } else {
                 constexpr int NCK = KIND == FKS_ROBOT_SE2 ? 3 : (KIND == FKS_ROBOT_SE3 ? 6 : 7);
-                if (!any_tall) {
-                    qr_rolled<NCK, 1>(wb, rows, wl.raw, 0, rows, false);
-                } else {
-                    int row0 = 0;
+                if (rows - row0 > 64) {  // tall and not folded yet: fold now, solve in the next slot
                     while (rows - row0 > 64) row0 = qr_rolled<NCK, 2>(wb, 64, 0, row0, 0, true);
-                    qr_rolled<NCK, 2>(wb, rows - row0, wl.raw, row0, rows, false);
+                    wv->pend_rows = rows;  // every lane stores the same value
+                    wv->pend_row0 = row0;
+                    deferred = true;
+                } else {
+                    if (!any_tall) qr_rolled<NCK, 1>(wb, rows - row0, wl.raw, row0, rows, false);
+                    else qr_rolled<NCK, 2>(wb, rows - row0, wl.raw, row0, rows, false);
+                    wv->pend_rows = 0;
                 }
             }
 #ifdef FKS_PHASE_TIMERS
@@ -2109,6 +2124,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #endif
             // motion estimate of the raw correction (spcs:1630) in the same solver slot: one lock-step round per
             // resolver iteration instead of two
+            if (!deferred) {
 #ifdef FKS_PHASE_TIMERS
             const long long te0 = clock64();
 #endif
@@ -2126,6 +2142,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             measure = M_CHECK;
             after = AF_RESOLVE_CHECK;
             want_solve = false;
+            }  // a deferred warp keeps want_solve: it is a solver of the next slot again and skips the rounds until then
             __syncwarp();
             if (lane == 0) atomicAdd(const_cast<unsigned*>(g2_done), 1u);
         }
