@@ -1625,6 +1625,14 @@ __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned
 // instruction fetch: ~200 KB of SASS walked by 16 warps at unrelated places against a 32 KB instruction
 // cache.  In lock step the working set of a phase is a few KB.
 // ------------------------------------------------------------------------------------------------
+// Resolver iterations a solver warp may chain inside one solver slot, each followed by a PRIVATE round (apply the correction,
+// check, transition) instead of waiting for round 0 of the next super-cycle.  0 = leave the slot right after the solve.
+// Measured (profiles/r1_kernel_experiments.md): chaining 2 / 4 / 8 iterations makes the arm 20-85 % slower (solver warps
+// drift apart in a 60 KB code region: instruction fetch), one private round gains 12 % on SE(2) (small kernel) and loses
+// 3-6 % on the arm -> 1 for SE(2), 0 otherwise.
+#ifndef FKS_SLOT_ITERATIONS
+#define FKS_SLOT_ITERATIONS(kind) ((kind) == FKS_ROBOT_SE2 ? 1 : 0)
+#endif
 namespace {
 enum { OP_NONE = 0, OP_KIN = 1, OP_APPLY = 2 };
 enum { M_NONE = 0, M_MOTION = 1, M_CHECK = 2 };
@@ -1714,7 +1722,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
     bool want_solve = false;
     for (;;) {
         int bar_id = 0, bar_threads = 32 * n_warps, n_solvers = 0;
-        bool counted_solver = false;
+        bool counted_solver = false, any_tall = false;
+        int slot_iter = 0;
+        constexpr int kSlotIters = FKS_SLOT_ITERATIONS(KIND);
         for (int round = 0;; round++) {
         // =========================== phase A: advance a kinematic state ===============================
         if (!want_solve) {
@@ -2043,30 +2053,40 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         }
         }  // if (!want_solve): end of phase T
         FKS_TICK(4)
-        if (round == 0) {
-            n_solvers = __syncthreads_count(want_solve) >> 5;  // full barrier; the count is in threads
-            FKS_TICK(5)
-#ifdef FKS_PHASE_TIMERS
-            textra[0] += 1;
-            textra[1] += n_solvers;
-#endif
-            if (n_solvers == 0) break;         // nobody solves: next super-cycle
-            counted_solver = want_solve;
-            if (want_solve) break;             // group 2 goes to collect + solve
-            bar_id = 1;                        // group 1 keeps going on its own barrier
-            bar_threads = 32 * (n_warps - n_solvers);
-        }
-        // group 1 only: another round while group 2 is still busy (decision made uniform by the barrier reduction)
-        const bool keep = (*g2_done < (unsigned)n_solvers) && (round < 16);
-        const bool go_on = named_barrier_or(1, bar_threads, keep);
-        FKS_TICK(1)
-#ifdef FKS_PHASE_TIMERS
-        textra[2] += 1;
-#endif
-        if (!go_on) break;
-        }  // rounds
-        // =========================== phase C: collect corrections (spcs:1627) ==========================
         if (counted_solver) {
+            // A solver warp has just run a PRIVATE round (kSlotIters > 0): the phases above applied its correction step, checked it
+            // and made the transition.  Still in collision and iterations left in this slot -> the next resolver iteration right
+            // away; resolved (or budget used) -> out, the pending operation runs in round 0 of the next super-cycle.
+            if (!want_solve || slot_iter >= kSlotIters) break;
+        } else {
+            if (round == 0) {
+                n_solvers = __syncthreads_count(want_solve) >> 5;  // full barrier; the count is in threads
+                FKS_TICK(5)
+#ifdef FKS_PHASE_TIMERS
+                textra[0] += 1;
+                textra[1] += n_solvers;
+#endif
+                if (n_solvers == 0) break;         // nobody solves: next super-cycle
+                counted_solver = want_solve;       // group 2 goes to collect + solve (below)
+                if (!counted_solver) {
+                    bar_id = 1;                    // group 1 keeps going on its own barrier
+                    bar_threads = 32 * (n_warps - n_solvers);
+                }
+            }
+            if (!counted_solver) {
+                // group 1 only: another round while group 2 is still busy (decision made uniform by the barrier reduction)
+                const bool keep = (*g2_done < (unsigned)n_solvers) && (round < 16 * (kSlotIters > 1 ? kSlotIters : 1));
+                const bool go_on = named_barrier_or(1, bar_threads, keep);
+                FKS_TICK(1)
+#ifdef FKS_PHASE_TIMERS
+                textra[2] += 1;
+#endif
+                if (!go_on) break;
+                continue;
+            }
+        }
+        // =========================== solver slot: phase C, collect corrections (spcs:1627) ==============
+        {
             int rows = 0;
 #ifdef FKS_PHASE_TIMERS
             const long long tc0 = clock64();
@@ -2091,7 +2111,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             // the solvers of this super-cycle agree on ONE copy of the QR code: the two-slot copy if any of them has more than
             // 32 rows, else the one-slot copy -- two copies live at once cost more in instruction fetch than the second row
             // slot costs the small systems (A/B in profiles/r1_kernel_experiments.md)
-            const bool any_tall = named_barrier_or(2, 32 * n_solvers, rows - row0 > 32);
+            // (only the first iteration of a slot is common to all of its solvers; later ones keep the choice unless they
+            // turn out tall themselves)
+            if (slot_iter == 0) any_tall = named_barrier_or(2, 32 * n_solvers, rows - row0 > 32);
+            else any_tall = any_tall || (rows - row0 > 32);
             FKS_TICK(7)
             // ======================= phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
 #ifdef FKS_PHASE_TIMERS
@@ -2143,6 +2166,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             after = AF_RESOLVE_CHECK;
             want_solve = false;
             }  // a deferred warp keeps want_solve: it is a solver of the next slot again and skips the rounds until then
+            slot_iter++;
+            if (deferred || kSlotIters == 0) break;  // folded: the solve comes in the next super-cycle's slot
+        }
+        }  // rounds
+        if (counted_solver) {
             __syncwarp();
             if (lane == 0) atomicAdd(const_cast<unsigned*>(g2_done), 1u);
         }
