@@ -1373,7 +1373,7 @@ __device__ __noinline__ void colpiv_qr_solve(int wb, int rows, int cols, int x_o
 // Same speed on the arm workloads, 5-10 % faster on SE(3), a sixth of the code (profiles/r1_kernel_experiments.md).
 //
 // Tall systems (rows > 64) are first folded, 64 rows at a time, into an NC x (NC + 1) triangle by UNPIVOTED reflections
-// (reduce_only: pivot = step index, triangle written back over the last NC rows of the chunk, returns the new first row):
+// (template flag reduce_only: pivot = step index, triangle written back over the last NC rows of the chunk, returns the new first row):
 // [A | c] -> Q^T [A | c] = [R | d ; 0 | *].  An orthogonal transformation from the left changes neither the Gram matrix of
 // the columns nor the least-squares problem, so the column-pivoted QR of the folded system (triangle + remaining rows)
 // makes the same pivot choices, rank decision (rows_thr = the ORIGINAL row count enters Eigen's threshold) and solution as
@@ -1430,8 +1430,8 @@ __device__ __forceinline__ double select_col(int p, const double (&v)[NC + 1]) {
 // there the sums run over the rows FROM the diagonal row on (not below it): tree 1 gives the residual column norms
 // directly and beta = -sign(c0) sqrt(norm) for the pivot column;
 // tree 2 uses the full Householder vector (1 on the diagonal row), so it needs no separate broadcast of row k.
-template <int NC, int R>
-__device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int rows_thr, bool reduce_only) {
+template <int NC, int R, bool reduce_only>
+__device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int rows_thr) {
     const Frame& fr = frame();
     const int lane = lane_id();
     double* ws = wsd(wb);
@@ -1443,7 +1443,7 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
 #pragma unroll
         for (int c = 0; c <= NC; c++) a[sl][c] = (lane + 32 * sl < rows) ? A[(size_t)c * ld + lane + 32 * sl] : 0.0;
     const int size = rows < NC ? rows : NC;
-    double threshold_helper = 0.0, rdiag_mine = 0.0;
+    double threshold_helper = -1.0, rdiag_mine = 0.0;
     int nonzero_pivots = size;
     unsigned order = 0u;        // 4 bits per step: the column picked at step k
     unsigned pos = 0x76543210u; // 4 bits per column: its position in the permuted order
@@ -1487,7 +1487,9 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
                 p = col;
                 const double big_sq = y;
                 const int best_pos = pcol;
-                if (k == 0) threshold_helper = (big_sq * (DBL_EPSILON * DBL_EPSILON)) / (double)rows_thr;  // Eigen: colNormsUpdated.maxCoeff()
+                // Eigen: colNormsUpdated.maxCoeff() before the first step (tested on the value, not on k == 0, so that the
+                // compiler does not peel the first iteration off the loop: that doubled the code)
+                if (threshold_helper < 0.0) threshold_helper = (big_sq * (DBL_EPSILON * DBL_EPSILON)) / (double)rows_thr;
                 const double cut = threshold_helper * (double)(rows_thr - k);
                 if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
                 if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
@@ -2132,13 +2134,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             } else {
                 constexpr int NCK = KIND == FKS_ROBOT_SE2 ? 3 : (KIND == FKS_ROBOT_SE3 ? 6 : 7);
                 if (rows - row0 > 64) {  // tall and not folded yet: fold now, solve in the next slot
-                    while (rows - row0 > 64) row0 = qr_rolled<NCK, 2>(wb, 64, 0, row0, 0, true);
+                    while (rows - row0 > 64) row0 = qr_rolled<NCK, 2, true>(wb, 64, 0, row0, 0);
                     wv->pend_rows = rows;  // every lane stores the same value
                     wv->pend_row0 = row0;
                     deferred = true;
                 } else {
-                    if (!any_tall) qr_rolled<NCK, 1>(wb, rows - row0, wl.raw, row0, rows, false);
-                    else qr_rolled<NCK, 2>(wb, rows - row0, wl.raw, row0, rows, false);
+                    if (!any_tall) qr_rolled<NCK, 1, false>(wb, rows - row0, wl.raw, row0, rows);
+                    else qr_rolled<NCK, 2, false>(wb, rows - row0, wl.raw, row0, rows);
                     wv->pend_rows = 0;
                 }
             }
