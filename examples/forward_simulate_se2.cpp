@@ -47,6 +47,18 @@ int main() {
         int differ = 0;
         for (size_t i = 0; i < results.size(); i++)
             if (results[i].result_config != results2[i].result_config || results[i].n_microsteps != results2[i].n_microsteps) differ++;
+        // one particle with the step trace of the reference (ForwardSimulateRobot, enable_tracing = true)
+        fksgpu::ForwardSimulationStepTrace<std::vector<double>> trace;
+        auto traced = sim2->ForwardSimulateRobot(starts[0], target[0], true, trace, true);
+        size_t micro = 0, configs = 0;
+        for (const auto& rs : trace.resolver_steps) {
+            micro += rs.contact_resolver_steps.size();
+            for (const auto& cs : rs.contact_resolver_steps) configs += cs.contact_resolution_steps.size();
+        }
+        if (trace.resolver_steps.size() != traced.n_steps || micro != traced.n_microsteps ||
+            configs < (size_t)traced.n_microsteps + traced.n_resolver_iterations)
+            differ++;
+        std::printf("trace: %zu controller steps, %zu microsteps, %zu configurations\n", trace.resolver_steps.size(), micro, configs);
         std::printf("%zu particles, %d outside the expected band, collision_resolves %.0f, %d differ in the device-built environment (built in %.3f ms)\n%s\n",
                     results.size(), bad, stats["collision_resolves"], differ, denv->BuildTimingsMs()[0], (bad == 0 && differ == 0) ? "ok" : "FAILED");
         return (bad == 0 && differ == 0) ? 0 : 1;

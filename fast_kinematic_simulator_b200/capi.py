@@ -40,6 +40,7 @@ FLAG_EMPTY_JACOBIAN = 1 << 11
 FLAG_TAPE_EXHAUSTED = 1 << 12
 FLAG_NEAR_RANK_CUT = 1 << 13
 FLAG_J_SPILLED = 1 << 14
+TRACE_CONTROL_INPUT, TRACE_CONTROL_INPUT_STEP, TRACE_POST_ACTION, TRACE_RESOLUTION_STEP, TRACE_RETURNED_PREVIOUS = range(5)
 NUM_STATS = 11
 STAT_NAMES = (
     "successful_resolves",
@@ -166,6 +167,8 @@ EXPORTS = (
     "fks_reverse_simulate",
     "fks_forward_simulate_device",
     "fks_check_config_collision",
+    "fks_sim_trace_stride",
+    "fks_forward_simulate_traced",
     "fks_get_statistics",
     "fks_reset_statistics",
     "fks_sim_launch_count",
@@ -207,6 +210,10 @@ lib.fks_forward_simulate_device.argtypes = [
     C.c_uint64, C.c_void_p, C.c_void_p,
 ]
 lib.fks_check_config_collision.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
+lib.fks_sim_trace_stride.argtypes = [C.c_void_p]
+lib.fks_sim_trace_stride.restype = C.c_size_t
+lib.fks_forward_simulate_traced.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, P(NoiseTape), C.c_uint64, C.c_void_p,
+                                            C.c_void_p, C.c_size_t, P(C.c_size_t)]
 lib.fks_get_statistics.argtypes = [C.c_void_p, P(C.c_uint64)]
 lib.fks_reset_statistics.argtypes = [C.c_void_p]
 lib.fks_sim_launch_count.argtypes = [C.c_void_p]

@@ -116,6 +116,10 @@ struct fks_sim {
     size_t cap_starts, cap_targets, cap_tape, cap_tape_off, cap_results;
     uint64_t launches;
     std::string info;
+    // set by fks_forward_simulate_traced around its launch, null otherwise
+    char* d_trace;
+    unsigned int* d_trace_count;
+    unsigned int trace_capacity;
 };
 
 extern "C" {
@@ -501,6 +505,9 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     s->d_results = nullptr;
     s->cap_starts = s->cap_targets = s->cap_tape = s->cap_tape_off = s->cap_results = 0;
     s->launches = 0;
+    s->d_trace = nullptr;
+    s->d_trace_count = nullptr;
+    s->trace_capacity = 0;
     const double freq = std::fabs(simulation_controller_frequency);  // spcs.hpp:426
     s->sp.interval = 1.0 / simulation_controller_frequency;          // spcs.hpp:427 (sign kept)
     s->sp.shortcut_distance = params->simulation_shortcut_distance;
@@ -530,6 +537,10 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
         cudaGetLastError();
     }
     s->plan.cull_mode = 1;
+    s->plan.trace = nullptr;
+    s->plan.trace_count = nullptr;
+    s->plan.trace_capacity = 0;
+    s->plan.trace_width = 0;
     if (const char* ev = std::getenv("FKS_CULL")) s->plan.cull_mode = std::atoi(ev);  // developer knob
     if (rc != 0) { delete s; return cuda_fail((cudaError_t)rc, "fks_sim_create: kernel attributes"); }
     if (s->kinfo.max_blocks_per_sm < 1) { delete s; return fail(FKS_ERR_UNSUPPORTED, "fks_sim_create: robot does not fit one CTA's shared memory"); }
@@ -605,6 +616,10 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
     a.noise_mode = noise_mode;
     a.cfg_stride = s->robot->stride;
     a.rec_stride = (int)fks_sim_result_stride(s);
+    a.trace = s->d_trace;
+    a.trace_count = s->d_trace_count;
+    a.trace_capacity = s->trace_capacity;
+    a.trace_width = std::max(s->robot->stride, s->robot->host.D);
     // small batches: fewer warps per CTA so that the particles spread over all SMs (one warp per particle)
     const size_t per_sm = (n + (size_t)s->num_sms - 1) / (size_t)s->num_sms;
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->plan.warps_per_block, per_sm));
@@ -665,6 +680,50 @@ int fks_forward_simulate(fks_sim* s, const double* starts, const double* targets
     FKS_CUDA(cudaMemcpyAsync(results, s->d_results, n * rec, cudaMemcpyDeviceToHost, s->stream));
     FKS_CUDA(cudaStreamSynchronize(s->stream));
     return FKS_OK;
+}
+
+size_t fks_sim_trace_stride(const fks_sim* s) {
+    return s ? sizeof(fks_trace_header) + (size_t)std::max(s->robot->stride, s->robot->host.D) * 8 : 0;
+}
+
+// ForwardSimulateRobot(..., trace, enable_tracing = true, ...) (spcs.hpp:824-829) for one particle
+int fks_forward_simulate_traced(fks_sim* s, const double* start, const double* target, int allow_contacts, int noise_mode,
+                                const fks_noise_tape* tape, uint64_t particle_id, void* result, void* trace_records,
+                                size_t trace_capacity, size_t* n_records) {
+    if (!s || !n_records || (trace_capacity > 0 && !trace_records) || trace_capacity > 0x7fffffffull)
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate_traced: bad argument");
+    *n_records = 0;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_forward_simulate_traced: cudaSetDevice failed");
+    const size_t rec = fks_sim_trace_stride(s);
+    char* d_trace = nullptr;
+    unsigned int* d_count = nullptr;
+    FKS_CUDA(cudaMalloc((void**)&d_trace, std::max<size_t>(trace_capacity, 1) * rec));
+    cudaError_t e = cudaMalloc((void**)&d_count, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, sizeof(unsigned int), s->stream);
+    int rc = FKS_OK;
+    if (e != cudaSuccess) {
+        rc = cuda_fail(e, "fks_forward_simulate_traced: allocation");
+    } else {
+        s->d_trace = d_trace;
+        s->d_trace_count = d_count;
+        s->trace_capacity = (unsigned int)trace_capacity;
+        rc = fks_forward_simulate(s, start, target, 1, 1, allow_contacts, noise_mode, tape, particle_id, result);
+        s->d_trace = nullptr;
+        s->d_trace_count = nullptr;
+        s->trace_capacity = 0;
+    }
+    if (rc == FKS_OK) {
+        unsigned int count = 0;
+        e = cudaMemcpy(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && trace_capacity)
+            e = cudaMemcpy(trace_records, d_trace, std::min<size_t>(count, trace_capacity) * rec, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "fks_forward_simulate_traced: copy back");
+        else *n_records = count;
+    }
+    cudaFree(d_trace);
+    cudaFree(d_count);
+    return rc;
 }
 
 int fks_reverse_simulate(fks_sim* s, const double* starts, const double* targets, size_t n, size_t n_targets,

@@ -220,6 +220,11 @@ struct LaunchArgs {
     int pts_off, warps_off;          // byte offsets of the point arrays / the warp blocks in dynamic shared memory
     int sync_off;                    // byte offset of the CTA-level synchronisation word
     int cull_mode;                   // link-level SDF culling: 0 never, 1 always, 2 only while the particle is collision free
+    // step trace of a single-particle call (fks_forward_simulate_traced); null on the batch path
+    char* trace;                     // records of trace_stride bytes: fks_trace_header + trace_width doubles
+    unsigned int* trace_count;       // records produced (may exceed the capacity: the excess is not stored)
+    unsigned int trace_capacity;
+    int trace_width;                 // doubles per record = max(cfg_stride, D)
 };
 
 struct Frame {

@@ -64,6 +64,28 @@ __device__ __forceinline__ char* scratch_slot() {
     return a.scratch + (size_t)(blockIdx.x * a.warps_per_block + (threadIdx.x >> 5)) * a.sl.total;
 }
 
+// ForwardSimulationStepTrace (spcs:1583-1617, :1703, :1714, :1778), flat: one record per assignment / push_back of the
+// reference.  Only reached when the call asked for a trace (a.trace != nullptr, one particle).
+__device__ __noinline__ void trace_append(unsigned kind, unsigned step, unsigned micro, unsigned iter, const double* values, int n) {
+    const LaunchArgs& a = frame().a;
+    const int lane = lane_id();
+    unsigned idx = 0u;
+    if (lane == 0) idx = atomicAdd(a.trace_count, 1u);
+    idx = __shfl_sync(FKS_FULL, idx, 0);
+    if (idx >= a.trace_capacity) return;
+    char* rec = a.trace + (size_t)idx * (sizeof(fks_trace_header) + (size_t)a.trace_width * 8);
+    if (lane == 0) {
+        fks_trace_header h;
+        h.kind = kind;
+        h.step = step;
+        h.microstep = micro;
+        h.iteration = iter;
+        *reinterpret_cast<fks_trace_header*>(rec) = h;
+    }
+    double* v = reinterpret_cast<double*>(rec + sizeof(fks_trace_header));
+    for (int i = lane; i < a.trace_width; i += 32) v[i] = i < n ? values[i] : 0.0;
+}
+
 // named barriers over a subset of the CTA's warps (PTX barrier.sync / barrier.red with a thread count)
 __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -1820,6 +1842,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                     }
                     case AF_EST_DU:  // spcs:1569-1575
                         if (m_result > allowed_microstep_distance) wv->flags |= FKS_FLAG_WOULD_ASSERT_MICROSTEP;
+                        if (a.trace) {  // spcs:1583-1588
+                            trace_append(FKS_TRACE_CONTROL_INPUT, wv->step, 0u, 0u, ws + wl.ru, D);
+                            trace_append(FKS_TRACE_CONTROL_INPUT_STEP, wv->step, 0u, 0u, ws + wl.du, D);
+                        }
                         wv->step_collided = wv->step_failed = wv->step_stopped = false;
                         wv->micro = 0u;
                         ev = 2;
@@ -1827,6 +1853,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                     case AF_MICRO_CHECK: {  // spcs:1608-1625
                         const bool in_collision = (cc & 1u) != 0u;
                         if (in_collision) wv->step_collided = true;
+                        if (a.trace) {
+                            trace_append(FKS_TRACE_POST_ACTION, wv->step, wv->micro, 0u, ws + wl.cfg + cur * S, stride);  // spcs:1615-1618
+                            if (in_collision && !a.allow_contacts)
+                                trace_append(FKS_TRACE_RETURNED_PREVIOUS, wv->step, wv->micro, 0u, ws + wl.cfg + prev * S, stride);  // spcs:1778
+                        }
                         if (in_collision && a.allow_contacts) {
                             wv->resolver_iterations = 0u;
                             wv->scaling = sp.initial_step;
@@ -1856,6 +1887,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         const bool in_collision = (cc & 1u) != 0u;
                         wv->resolver_iterations++;
                         wv->n_iter_total++;
+                        if (a.trace) {
+                            __syncwarp();
+                            trace_append(FKS_TRACE_RESOLUTION_STEP, wv->step, wv->micro, wv->resolver_iterations, ws + wl.cfg + cur * S, stride);  // spcs:1703
+                            if (wv->resolver_iterations > sp.max_iters)
+                                trace_append(FKS_TRACE_RETURNED_PREVIOUS, wv->step, wv->micro, wv->resolver_iterations, ws + wl.cfg + prev * S, stride);  // spcs:1714
+                        }
                         if (wv->resolver_iterations > sp.max_iters) {  // spcs:1705-1746
                             if (lane == 0) {
                                 add_stat(wb, FKS_STAT_UNSUCCESSFUL_RESOLVES, 1ull);

@@ -320,6 +320,31 @@ class GpuParticleContactSimulator:
                                               int(bool(allow_contacts)), int(noise_mode), ptr(d_tape), ptr(d_tape_offsets),
                                               int(first_particle_id), ptr(d_results), int(stream) if stream else None))
 
+    def trace_dtype(self):
+        width = (lib.fks_sim_trace_stride(self._h) - 16) // 8
+        return np.dtype([("kind", np.uint32), ("step", np.uint32), ("microstep", np.uint32), ("iteration", np.uint32),
+                         ("values", np.float64, (width,))])
+
+    def forward_simulate_robot_traced(self, start, target, allow_contacts=True, noise_mode=capi.NOISE_PHILOX, tape=None,
+                                      particle_id=0, capacity=65536):
+        """ForwardSimulateRobot with enable_tracing (spcs.hpp:824-829): (SimulationResults of one particle, trace records).
+        The flat records follow the order in which the reference fills ForwardSimulationStepTrace (spcs.hpp:1583-1617,
+        :1703, :1714, :1778); `values` holds n_dof control values or cfg_stride configuration values."""
+        start = _as_f64(start).reshape(1, self.config_stride)
+        target = _as_f64(target).reshape(1, self.config_stride)
+        out = np.empty(1, dtype=self.dtype)
+        rec = np.zeros(capacity, dtype=self.trace_dtype())
+        ctape, keep = (None, None)
+        if tape is not None:
+            ctape, keep = make_tape(*tape)
+        n = C.c_size_t(0)
+        check(lib.fks_forward_simulate_traced(self._h, start.ctypes.data, target.ctypes.data, int(bool(allow_contacts)), int(noise_mode),
+                                              C.byref(ctape) if ctape is not None else None, int(particle_id), out.ctypes.data,
+                                              rec.ctypes.data, capacity, C.byref(n)))
+        if n.value > capacity:
+            raise capi.FksError(capi.ERR_INVALID_ARGUMENT, "trace capacity %d too small for %d records" % (capacity, n.value))
+        return SimulationResults(out), rec[: n.value]
+
     def check_config_collision(self, configs, inflation_ratio=0.0):
         """CheckConfigCollision (spcs.hpp:1398-1416) for a batch of configurations -> bool array."""
         configs = _as_f64(configs).reshape(-1, self.config_stride)

@@ -255,6 +255,30 @@ int fks_forward_simulate_device(fks_sim* sim, const double* d_starts, const doub
 int fks_check_config_collision(fks_sim* sim, const double* configs, size_t n_configs, double inflation_ratio,
                                uint8_t* out_collides);
 
+/* ForwardSimulateRobot with enable_tracing == true (spcs.hpp:824-829; ForwardSimulationStepTrace filled at :1583-1617,
+ * :1703, :1714, :1778) for ONE particle -- SURVEY.md 8(f)-4.  The nested trace of the reference (controller step ->
+ * microstep -> configurations) is returned flat, in the order the reference appends: every record carries its step /
+ * microstep / resolver-iteration indices.  HOST buffers; trace_records holds up to trace_capacity records of
+ * fks_sim_trace_stride() bytes (fks_trace_header followed by max(cfg_stride, n_dof) doubles); *n_records receives the number
+ * the simulation produced (records beyond the capacity are counted but not stored). */
+enum {
+    FKS_TRACE_CONTROL_INPUT = 0,      /* resolver_steps.back().control_input = real_control_input (:1586), n_dof values   */
+    FKS_TRACE_CONTROL_INPUT_STEP = 1, /* .control_input_step (:1587), n_dof values                                         */
+    FKS_TRACE_POST_ACTION = 2,        /* contact_resolution_steps.push_back(post_action_configuration) (:1617), cfg_stride */
+    FKS_TRACE_RESOLUTION_STEP = 3,    /* ... push_back(active_configuration) after a correction step (:1703)               */
+    FKS_TRACE_RETURNED_PREVIOUS = 4   /* ... push_back(previous_configuration): failed resolve (:1714) / no-contact (:1778) */
+};
+typedef struct fks_trace_header {
+    uint32_t kind;      /* FKS_TRACE_* */
+    uint32_t step;      /* controller step (index into resolver_steps) */
+    uint32_t microstep; /* index into contact_resolver_steps of that step */
+    uint32_t iteration; /* resolver iterations completed when the record was made */
+} fks_trace_header;
+size_t fks_sim_trace_stride(const fks_sim* sim);
+int fks_forward_simulate_traced(fks_sim* sim, const double* start, const double* target, int allow_contacts,
+                                int noise_mode, const fks_noise_tape* tape, uint64_t particle_id, void* result,
+                                void* trace_records, size_t trace_capacity, size_t* n_records);
+
 /* GetStatistics / ResetStatistics (spcs.hpp:488-512); out has FKS_NUM_STATS entries.
  * Synchronises the simulator's stream. */
 int fks_get_statistics(fks_sim* sim, uint64_t* out);

@@ -50,6 +50,24 @@ struct SimulationResult {
     uint32_t flags, n_microsteps, n_resolver_iterations, n_steps;
 };
 
+// simple_simulator_interface::ForwardSimulationStepTrace (filled at spcs.hpp:1583-1617, :1703, :1714, :1778): one entry per
+// controller step holding the control input, its per-microstep share, and per microstep the configurations the resolver
+// went through (post-action configuration, every correction step, the returned previous configuration on a stop).
+template <typename Configuration>
+struct ForwardSimulationContactResolverStepTrace {
+    std::vector<Configuration> contact_resolution_steps;
+};
+template <typename Configuration>
+struct ForwardSimulationResolverTrace {
+    std::vector<double> control_input;
+    std::vector<double> control_input_step;
+    std::vector<ForwardSimulationContactResolverStepTrace<Configuration>> contact_resolver_steps;
+};
+template <typename Configuration>
+struct ForwardSimulationStepTrace {
+    std::vector<ForwardSimulationResolverTrace<Configuration>> resolver_steps;
+};
+
 // Environment = what the reference simulator copies at construction (spcs.hpp:420)
 class Environment {
 public:
@@ -118,6 +136,7 @@ public:
         }
         stride_ = fks_robot_config_stride(robot_);
         record_ = fks_sim_result_stride(sim_);
+        dof_ = robot.n_dof;
     }
     // same, in an environment that already lives on the device (shared, must outlive the simulator)
     GpuParticleContactSimulator(const std::shared_ptr<DeviceEnvironment>& environment, const fks_robot_desc& robot,
@@ -134,6 +153,7 @@ public:
         }
         stride_ = fks_robot_config_stride(robot_);
         record_ = fks_sim_result_stride(sim_);
+        dof_ = robot.n_dof;
     }
     ~GpuParticleContactSimulator() { Release(); }
     GpuParticleContactSimulator(const GpuParticleContactSimulator&) = delete;
@@ -156,6 +176,42 @@ public:
     // spcs.hpp:824: single particle
     Result ForwardSimulateRobot(const Configuration& start, const Configuration& target, bool allow_contacts) {
         return ForwardSimulateRobots(std::vector<Configuration>(1, start), std::vector<Configuration>(1, target), allow_contacts)[0];
+    }
+
+    // spcs.hpp:824 with the trace arguments: single particle, trace filled when enable_tracing is set
+    Result ForwardSimulateRobot(const Configuration& start, const Configuration& target, bool allow_contacts,
+                                ForwardSimulationStepTrace<Configuration>& trace, bool enable_tracing) {
+        if (!enable_tracing) return ForwardSimulateRobot(start, target, allow_contacts);
+        std::vector<double> s0((size_t)stride_), t0((size_t)stride_);
+        ConfigTraits<Configuration>::Flatten(start, s0.data(), stride_);
+        ConfigTraits<Configuration>::Flatten(target, t0.data(), stride_);
+        const size_t rec = fks_sim_trace_stride(sim_);
+        std::vector<unsigned char> result(record_), records;
+        size_t capacity = 4096, n = 0;
+        for (;;) {  // grow until the whole trace fits (the simulation is deterministic in the particle id)
+            records.resize(capacity * rec);
+            Check(fks_forward_simulate_traced(sim_, s0.data(), t0.data(), allow_contacts ? 1 : 0, FKS_NOISE_PHILOX, nullptr,
+                                              next_particle_id_, result.data(), records.data(), capacity, &n));
+            if (n <= capacity) break;
+            capacity = n;
+        }
+        next_particle_id_ += 1;
+        for (size_t i = 0; i < n; i++) {
+            fks_trace_header h;
+            std::memcpy(&h, records.data() + i * rec, sizeof(h));
+            const double* v = reinterpret_cast<const double*>(records.data() + i * rec + sizeof(h));
+            if (h.kind == FKS_TRACE_CONTROL_INPUT) {
+                trace.resolver_steps.emplace_back();
+                trace.resolver_steps.back().control_input.assign(v, v + dof_);
+            } else if (h.kind == FKS_TRACE_CONTROL_INPUT_STEP) {
+                trace.resolver_steps.back().control_input_step.assign(v, v + dof_);
+            } else {
+                auto& steps = trace.resolver_steps.back().contact_resolver_steps;
+                if (h.kind == FKS_TRACE_POST_ACTION) steps.emplace_back();
+                steps.back().contact_resolution_steps.push_back(ConfigTraits<Configuration>::Unflatten(v, stride_));
+            }
+        }
+        return Unpack(result.data(), target);
     }
 
     // spcs.hpp:1398: planner-side static query (environment inflated by inflation_ratio cells, self collisions)
@@ -210,19 +266,21 @@ private:
                                                                      FKS_NOISE_PHILOX, nullptr, next_particle_id_, rec.data()));
         next_particle_id_ += n;
         std::vector<Result> out(n);
-        for (size_t i = 0; i < n; i++) {
-            const unsigned char* r = rec.data() + i * record_;
-            fks_result_tail tail;
-            std::memcpy(&tail, r + sizeof(double) * (size_t)stride_, sizeof(tail));
-            out[i].result_config = ConfigTraits<Configuration>::Unflatten(reinterpret_cast<const double*>(r), stride_);
-            out[i].actual_target = targets.size() == 1 ? targets[0] : targets[i];
-            out[i].did_contact = (tail.flags & FKS_FLAG_DID_CONTACT) != 0;  // spcs.hpp:918
-            out[i].outcome_is_nominal = true;                               // always true in the reference (:918)
-            out[i].flags = tail.flags;
-            out[i].n_microsteps = tail.n_microsteps;
-            out[i].n_resolver_iterations = tail.n_resolver_iters;
-            out[i].n_steps = tail.n_steps;
-        }
+        for (size_t i = 0; i < n; i++) out[i] = Unpack(rec.data() + i * record_, targets.size() == 1 ? targets[0] : targets[i]);
+        return out;
+    }
+    Result Unpack(const unsigned char* r, const Configuration& target) const {
+        Result out;
+        fks_result_tail tail;
+        std::memcpy(&tail, r + sizeof(double) * (size_t)stride_, sizeof(tail));
+        out.result_config = ConfigTraits<Configuration>::Unflatten(reinterpret_cast<const double*>(r), stride_);
+        out.actual_target = target;
+        out.did_contact = (tail.flags & FKS_FLAG_DID_CONTACT) != 0;  // spcs.hpp:918
+        out.outcome_is_nominal = true;                               // always true in the reference (:918)
+        out.flags = tail.flags;
+        out.n_microsteps = tail.n_microsteps;
+        out.n_resolver_iterations = tail.n_resolver_iters;
+        out.n_steps = tail.n_steps;
         return out;
     }
     void Release() {
@@ -238,7 +296,7 @@ private:
     fks_env* env_;
     fks_robot* robot_;
     fks_sim* sim_;
-    int stride_ = 0;
+    int stride_ = 0, dof_ = 0;
     size_t record_ = 0;
     uint64_t next_particle_id_ = 0;
 };

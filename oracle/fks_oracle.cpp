@@ -1164,6 +1164,21 @@ struct Sim {
         bool collided, failed;
     };
 
+    // ForwardSimulationStepTrace (filled at spcs:1583-1617, :1703, :1714, :1778), flat: one record per push_back /
+    // assignment of the reference, in its order; layout = fks_trace_header + max(cfg_stride, D) doubles
+    mutable std::vector<char>* trace = nullptr;  // set for a traced single-particle call only
+    void trace_push(uint32_t kind, uint32_t step, uint32_t micro, uint32_t iter, const double* values, int n) const {
+        if (!trace) return;
+        const int width = std::max(proto.cfg_stride(), proto.D);
+        fks_trace_header h = {kind, step, micro, iter};
+        std::vector<double> v((size_t)width, 0.0);
+        for (int i = 0; i < n; i++) v[(size_t)i] = values[i];
+        const size_t at = trace->size();
+        trace->resize(at + sizeof(h) + (size_t)width * 8);
+        std::memcpy(trace->data() + at, &h, sizeof(h));
+        std::memcpy(trace->data() + at + sizeof(h), v.data(), (size_t)width * 8);
+    }
+
     // ResolveForwardSimulation (spcs:1546-1816).  `robot` enters at the step's start configuration and
     // leaves at the resolved configuration (the reference returns it and the caller SetPosition()s).
     StepResult resolve(Robot& robot, const double* control_input, double controller_interval, NoiseSource& noise,
@@ -1187,6 +1202,8 @@ struct Sim {
         SelfMap self;
         std::vector<double> Jrows, corr, Acm, bvec;
         noise.begin_step(robot);
+        trace_push(FKS_TRACE_CONTROL_INPUT, step, 0, 0, real_u, D);        // spcs:1583-1587
+        trace_push(FKS_TRACE_CONTROL_INPUT_STEP, step, 0, 0, du, D);
         for (uint32_t micro = 0; micro < number_microsteps; micro++) {
             (*n_micro_total)++;
             const Robot previous = robot;  // previous_configuration (spcs:1597)
@@ -1195,6 +1212,7 @@ struct Sim {
             robot.apply_control(du, tn, &nan_seen, sens);  // spcs:1599-1601
             bool in_collision = check_collision(previous, robot, controller_interval, &self, sens);  // spcs:1608
             if (in_collision) collided = true;
+            trace_push(FKS_TRACE_POST_ACTION, step, micro, 0, robot.cfg, robot.cfg_stride());  // spcs:1615-1618
             if (in_collision && allow_contacts) {
                 uint32_t resolver_iterations = 0;
                 double scaling = sp.resolve_correction_initial_step_size;
@@ -1235,7 +1253,9 @@ struct Sim {
                     in_collision = check_collision(previous, robot, controller_interval, &self, sens);  // spcs:1694-1698
                     resolver_iterations++;
                     (*n_iter_total)++;
+                    trace_push(FKS_TRACE_RESOLUTION_STEP, step, micro, resolver_iterations, robot.cfg, robot.cfg_stride());  // spcs:1703
                     if (resolver_iterations > sp.max_resolver_iterations) {  // spcs:1705-1746
+                        trace_push(FKS_TRACE_RETURNED_PREVIOUS, step, micro, resolver_iterations, previous.cfg, previous.cfg_stride());  // spcs:1714
                         st[FKS_STAT_UNSUCCESSFUL_RESOLVES]++;
                         if (!self.empty()) st[FKS_STAT_UNSUCCESSFUL_SELF_COLLISION_RESOLVES]++;
                         else st[FKS_STAT_UNSUCCESSFUL_ENV_COLLISION_RESOLVES]++;
@@ -1253,6 +1273,7 @@ struct Sim {
                     }
                 }
             } else if (in_collision && !allow_contacts) {  // spcs:1769-1786
+                trace_push(FKS_TRACE_RETURNED_PREVIOUS, step, micro, 0, previous.cfg, previous.cfg_stride());  // spcs:1778
                 st[FKS_STAT_SUCCESSFUL_RESOLVES]++;
                 robot = previous;
                 if (nan_seen) *flags |= FKS_FLAG_WOULD_ASSERT_NAN;
@@ -1418,6 +1439,42 @@ int oracle_forward_simulate(oracle_sim* o, const double* starts, const double* t
     for (int t = 0; t < T; t++)
         for (int k = 0; k < FKS_NUM_STATS; k++) s.stats[k] += tstats[(size_t)t][(size_t)k];
     return FKS_OK;
+}
+
+// ForwardSimulateRobot with enable_tracing (spcs:824-829) for one particle; returns the number of trace records and copies
+// up to `capacity` of them (fks_trace_header + max(stride, D) doubles each)
+size_t oracle_trace_stride(const oracle_sim* o) { return sizeof(fks_trace_header) + (size_t)std::max(o->s.proto.cfg_stride(), o->s.proto.D) * 8; }
+size_t oracle_forward_simulate_traced(oracle_sim* o, const double* start, const double* target, int allow_contacts, int noise_mode,
+                                      const fks_noise_tape* tape, uint64_t particle_id, void* result, void* records, size_t capacity) {
+    Sim& s = o->s;
+    std::vector<char> buf;
+    s.trace = &buf;
+    NoiseSource ns;
+    ns.mode = noise_mode;
+    ns.tape = nullptr;
+    ns.tape_pos = ns.tape_end = 0;
+    ns.exhausted = false;
+    ns.rng = &s.rngs[0];
+    ns.seed = s.seed;
+    ns.particle_id = particle_id;
+    ns.record = nullptr;
+    if (noise_mode == FKS_NOISE_INJECTED && tape) {
+        ns.tape = tape->draws;
+        ns.tape_pos = tape->offsets[0];
+        ns.tape_end = tape->offsets[1];
+    }
+    double cfg[kMaxDof];
+    fks_result_tail tail;
+    std::vector<uint64_t> st(FKS_NUM_STATS, 0);
+    uint32_t sens = 0;
+    s.simulate_particle(start, target, allow_contacts != 0, ns, cfg, &tail, st.data(), &sens);
+    s.trace = nullptr;
+    const int stride = s.proto.cfg_stride();
+    std::memcpy(result, cfg, (size_t)stride * 8);
+    std::memcpy((char*)result + (size_t)stride * 8, &tail, sizeof(tail));
+    const size_t rec = oracle_trace_stride(o), n = buf.size() / rec;
+    std::memcpy(records, buf.data(), std::min(n, capacity) * rec);
+    return n;
 }
 
 // CheckConfigCollision (spcs:1398-1416) for n configurations

@@ -64,6 +64,11 @@ def load():
     lib.oracle_philox_raw.restype = None
     lib.oracle_env_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oracle_robot_kinematics.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_trace_stride.argtypes = [C.c_void_p]
+    lib.oracle_trace_stride.restype = C.c_size_t
+    lib.oracle_forward_simulate_traced.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
+                                                   C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.oracle_forward_simulate_traced.restype = C.c_size_t
     lib.oracle_build_environment.argtypes = [C.c_void_p, C.c_size_t, C.c_double]
     lib.oracle_build_environment.restype = C.c_void_p
     lib.oracle_env_desc.argtypes = [C.c_void_p]
@@ -176,6 +181,20 @@ class OracleSimulator:
         if rc != 0:
             raise ValueError("oracle_forward_simulate failed with code %d" % rc)
         return out
+
+    def forward_simulate_traced(self, start, target, allow_contacts=True, noise_mode=0, particle_id=0, capacity=65536):
+        """ForwardSimulateRobot with enable_tracing (spcs.hpp:824-829) for one particle -> (result record, trace records)."""
+        start = _f64(start).reshape(-1)
+        target = _f64(target).reshape(-1)
+        width = (lib().oracle_trace_stride(self._h) - 16) // 8
+        dt = np.dtype([("kind", np.uint32), ("step", np.uint32), ("microstep", np.uint32), ("iteration", np.uint32),
+                       ("values", np.float64, (width,))])
+        rec = np.zeros(capacity, dtype=dt)
+        out = np.zeros(1, dtype=self.dtype)
+        n = lib().oracle_forward_simulate_traced(self._h, start.ctypes.data, target.ctypes.data, int(bool(allow_contacts)), int(noise_mode),
+                                                 None, int(particle_id), out.ctypes.data, rec.ctypes.data, capacity)
+        assert n <= capacity
+        return out, rec[:n]
 
     def check_config_collision(self, configs, inflation_ratio=0.0):
         configs = _f64(configs).reshape(-1, self.stride)
