@@ -1675,7 +1675,9 @@ enum {
 };
 }  // namespace
 
-template <int KIND>
+// TRACE = true is the single-particle instantiation that records the step trace (fks_forward_simulate_traced); the batch
+// kernel carries none of it.
+template <int KIND, bool TRACE = false>
 __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_kernel(const __grid_constant__ LaunchArgs args) {
     // ---- stage parameters, robot and points into shared memory, once per CTA ---------------------
     {
@@ -1842,7 +1844,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                     }
                     case AF_EST_DU:  // spcs:1569-1575
                         if (m_result > allowed_microstep_distance) wv->flags |= FKS_FLAG_WOULD_ASSERT_MICROSTEP;
-                        if (a.trace) {  // spcs:1583-1588
+                        if (TRACE) {  // spcs:1583-1588
                             trace_append(FKS_TRACE_CONTROL_INPUT, wv->step, 0u, 0u, ws + wl.ru, D);
                             trace_append(FKS_TRACE_CONTROL_INPUT_STEP, wv->step, 0u, 0u, ws + wl.du, D);
                         }
@@ -1853,7 +1855,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                     case AF_MICRO_CHECK: {  // spcs:1608-1625
                         const bool in_collision = (cc & 1u) != 0u;
                         if (in_collision) wv->step_collided = true;
-                        if (a.trace) {
+                        if (TRACE) {
                             trace_append(FKS_TRACE_POST_ACTION, wv->step, wv->micro, 0u, ws + wl.cfg + cur * S, stride);  // spcs:1615-1618
                             if (in_collision && !a.allow_contacts)
                                 trace_append(FKS_TRACE_RETURNED_PREVIOUS, wv->step, wv->micro, 0u, ws + wl.cfg + prev * S, stride);  // spcs:1778
@@ -1887,7 +1889,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         const bool in_collision = (cc & 1u) != 0u;
                         wv->resolver_iterations++;
                         wv->n_iter_total++;
-                        if (a.trace) {
+                        if (TRACE) {
                             __syncwarp();
                             trace_append(FKS_TRACE_RESOLUTION_STEP, wv->step, wv->micro, wv->resolver_iterations, ws + wl.cfg + cur * S, stride);  // spcs:1703
                             if (wv->resolver_iterations > sp.max_iters)
@@ -2396,11 +2398,11 @@ size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stri
     return off;
 }
 
-static const void* kernel_ptr(int kind) {
+static const void* kernel_ptr(int kind, bool trace = false) {
     switch (kind) {
-        case FKS_ROBOT_SE2: return (const void*)simulate_kernel<FKS_ROBOT_SE2>;
-        case FKS_ROBOT_SE3: return (const void*)simulate_kernel<FKS_ROBOT_SE3>;
-        case FKS_ROBOT_LINKED: return (const void*)simulate_kernel<FKS_ROBOT_LINKED>;
+        case FKS_ROBOT_SE2: return trace ? (const void*)simulate_kernel<FKS_ROBOT_SE2, true> : (const void*)simulate_kernel<FKS_ROBOT_SE2>;
+        case FKS_ROBOT_SE3: return trace ? (const void*)simulate_kernel<FKS_ROBOT_SE3, true> : (const void*)simulate_kernel<FKS_ROBOT_SE3>;
+        case FKS_ROBOT_LINKED: return trace ? (const void*)simulate_kernel<FKS_ROBOT_LINKED, true> : (const void*)simulate_kernel<FKS_ROBOT_LINKED>;
     }
     return nullptr;
 }
@@ -2427,8 +2429,12 @@ int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelI
 int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
                     const void* l2_window_base, size_t l2_window_bytes) {
     const int block_threads = 32 * args.warps_per_block;
-    const void* fn = kernel_ptr(kind);
+    const void* fn = kernel_ptr(kind, args.trace != nullptr);
     if (!fn) return (int)cudaErrorInvalidValue;
+    if (args.trace != nullptr) {  // the tracing instantiation is launched rarely: set its shared-memory limit on the spot
+        const cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+        if (err != cudaSuccess) return (int)err;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)block_threads);
