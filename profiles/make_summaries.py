@@ -155,7 +155,7 @@ def ncu_md():
     stalls = sorted(((sum(f(r, s) for r in d2), s) for s in h2 if s.startswith("stall_") and "Not Issued" not in s), reverse=True)
     r3 = list(csv.reader(ncu("--page", "source", "--csv", "--print-source", "cuda,sass").splitlines()))
     cur = hdr3 = None
-    inst, samp, src = collections.Counter(), collections.Counter(), {}
+    inst, samp, src, allsrc = collections.Counter(), collections.Counter(), {}, {}
     for r in r3:
         if len(r) >= 2 and r[0] == "File Path":
             cur = r[1].split("/")[-1]
@@ -163,6 +163,11 @@ def ncu_md():
         if len(r) > 3 and r[0] == "Line No":
             hdr3 = r
             continue
+        if hdr3 is not None and cur is not None and len(r) >= 3 and r[2] == "-":
+            try:
+                allsrc[(cur, int(r[0]))] = r[1]
+            except ValueError:
+                pass
         if hdr3 is None or len(r) < len(hdr3) or cur is None or r[2] != "-":
             continue
         try:
@@ -191,11 +196,18 @@ def ncu_md():
                 "live, 32 warps), which is still the fastest variant measured (`r1_v1_free_running.md`, `r1_kernel_experiments.md`).\n")
         # per enclosing __device__ function of fks_kernels.cu
         import re
+        # (function headers are taken from the source embedded in the report, so the mapping stays right when the file moves on)
         funcs = []
-        for i, l in enumerate(open(os.path.join(ROOT, "fast_kinematic_simulator_b200", "csrc", "fks_kernels.cu")).read().split("\n"), 1):
-            mm = re.match(r"^(?:static )?__(?:device|global)__ .*?(\w+)\(", l)
+        infile = False
+        for r in csv.reader(ncu("--page", "source", "--csv", "--print-source", "cuda").splitlines()):
+            if len(r) >= 2 and r[0] == "File Name":
+                infile = r[1].endswith("fks_kernels.cu")
+                continue
+            if not infile or len(r) < 2 or not r[0].isdigit():
+                continue
+            mm = re.match(r"^(?:static )?__(?:device|global)__ .*?(\w+)\(", r[1])
             if mm:
-                funcs.append((i, mm.group(1)))
+                funcs.append((int(r[0]), mm.group(1)))
 
         def fn_of(f, line):
             if f != "fks_kernels.cu":
