@@ -1654,6 +1654,10 @@ __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned
 // Measured (profiles/r1_kernel_experiments.md): chaining 2 / 4 / 8 iterations makes the arm 20-85 % slower (solver warps
 // drift apart in a 60 KB code region: instruction fetch), one private round gains 12 % on SE(2) (small kernel) and loses
 // 3-6 % on the arm -> 1 for SE(2), 0 otherwise.
+// Lock-step rounds a CTA runs between two CTA barriers while none of its warps is in contact (0 = a barrier every round).
+#ifndef FKS_FREE_ROUNDS
+#define FKS_FREE_ROUNDS 3
+#endif
 #ifndef FKS_SLOT_ITERATIONS
 #define FKS_SLOT_ITERATIONS(kind) ((kind) == FKS_ROBOT_SE2 ? 1 : 0)
 #endif
@@ -1746,6 +1750,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
     const int n_warps = a.warps_per_block;
     volatile unsigned* g2_done = reinterpret_cast<volatile unsigned*>(smem_raw + a.sync_off);
     bool want_solve = false;
+    int free_rounds = 0, free_streak = 0;  // rounds the next super-cycle runs before its first CTA barrier (free flight only)
     for (;;) {
         int bar_id = 0, bar_threads = 32 * n_warps, n_solvers = 0;
         bool counted_solver = false, any_tall = false;
@@ -2100,7 +2105,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             // away; resolved (or budget used) -> out, the pending operation runs in round 0 of the next super-cycle.
             if (!want_solve || slot_iter >= kSlotIters) break;
         } else {
-            if (round == 0) {
+            if (round < free_rounds) continue;  // free flight: a CTA barrier every (free_rounds + 1) rounds only
+            if (round == free_rounds) {
                 n_solvers = __syncthreads_count(want_solve) >> 5;  // full barrier; the count is in threads
                 FKS_TICK(5)
 #ifdef FKS_PHASE_TIMERS
@@ -2216,6 +2222,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             if (lane == 0) atomicAdd(const_cast<unsigned*>(g2_done), 1u);
         }
         FKS_TICK(8)
+        // (only after several solver-free super-cycles in a row: in the contact regime an occasional empty super-cycle must
+        // not delay the next slot)
+        free_streak = (n_solvers == 0) ? free_streak + 1 : 0;
+        free_rounds = (free_streak >= 4) ? FKS_FREE_ROUNDS : 0;
         const bool all_done = __syncthreads_and(after == AF_DONE && !want_solve);
         FKS_TICK(9)
         if (all_done) break;
