@@ -231,6 +231,9 @@ struct Frame {
     LaunchArgs a;
     DevRobot rb;
     double gbase[12];  // (1 / sdf_res) * inverse_origin * base: root of the world->voxel chain (linked robots)
+    // per disallowed link pair: (half lengths + radii of the two bounding capsules + cell diagonal)^2 -- capsule midpoints
+    // further apart than that cannot bring two points of the links into one cell (self-collision broad phase)
+    double pair_reach_sq[kMaxPairs];
 };
 
 // launch interface implemented in fks_kernels.cu

@@ -987,9 +987,21 @@ __device__ __forceinline__ bool collect_self(int wb, int Xprev, int Xcur) {
         bool hit = false;
         if (q < rb.n_pairs) {
             const int a = rb.pair_a[q], b = rb.pair_b[q];
-            const double d2 = segment_distance_sq(caps + 6 * a, caps + 6 * a + 3, caps + 6 * b, caps + 6 * b + 3);
-            const double reach = rb.cap_radius[a] + rb.cap_radius[b] + diag;
-            hit = d2 <= reach * reach;
+            // midpoints first: the segments are at least |m_a - m_b| - half lengths apart (triangle inequality), so far-apart
+            // links never reach the segment-segment distance -- for an arm away from itself that is every pair, every check
+            const double* ca = caps + 6 * a;
+            const double* cb = caps + 6 * b;
+            const double mx = 0.5 * ((ca[0] + ca[3]) - (cb[0] + cb[3])), my = 0.5 * ((ca[1] + ca[4]) - (cb[1] + cb[4])),
+                         mz = 0.5 * ((ca[2] + ca[5]) - (cb[2] + cb[5]));
+            hit = mx * mx + my * my + mz * mz <= fr.pair_reach_sq[q];
+        }
+        if (__any_sync(FKS_FULL, hit)) {
+            if (hit) {
+                const int a = rb.pair_a[q], b = rb.pair_b[q];
+                const double d2 = segment_distance_sq(caps + 6 * a, caps + 6 * a + 3, caps + 6 * b, caps + 6 * b + 3);
+                const double reach = rb.cap_radius[a] + rb.cap_radius[b] + diag;
+                hit = d2 <= reach * reach;
+            }
         }
         const unsigned m = __ballot_sync(FKS_FULL, hit);
         if (ch == 0) cp[0] = m;
@@ -1706,6 +1718,19 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             if (c == 3) v += io[4 * r + 3];
             f->gbase[threadIdx.x] = v * args.env.inv_sdf_res;
         }
+        for (int q = threadIdx.x; q < args.robot->n_pairs; q += blockDim.x) {  // midpoint pre-test of the self-collision broad phase
+            const DevRobot* r = args.robot;
+            const int la = r->pair_a[q], lb = r->pair_b[q];
+            double ha = 0.0, hb = 0.0;
+            for (int k = 0; k < 3; k++) {
+                const double da = r->cap_p1[la][k] - r->cap_p0[la][k], db = r->cap_p1[lb][k] - r->cap_p0[lb][k];
+                ha += da * da;
+                hb += db * db;
+            }
+            const double diag = 1.7320508075688772 * args.env.map_res * (1.0 + 1e-6) + 1e-9;
+            const double reach = (0.5 * sqrt(ha) + 0.5 * sqrt(hb) + r->cap_radius[la] + r->cap_radius[lb] + diag) * (1.0 + 1e-9);
+            f->pair_reach_sq[q] = reach * reach;
+        }
         if (threadIdx.x < 4) reinterpret_cast<unsigned*>(smem_raw + args.sync_off)[threadIdx.x] = 0u;
     }
     __syncthreads();
@@ -2339,6 +2364,19 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) check_config
             double v = io[4 * r + 0] * bs[c] + io[4 * r + 1] * bs[4 + c] + io[4 * r + 2] * bs[8 + c];
             if (c == 3) v += io[4 * r + 3];
             f->gbase[threadIdx.x] = v * args.env.inv_sdf_res;
+        }
+        for (int q = threadIdx.x; q < args.robot->n_pairs; q += blockDim.x) {  // midpoint pre-test of the self-collision broad phase
+            const DevRobot* r = args.robot;
+            const int la = r->pair_a[q], lb = r->pair_b[q];
+            double ha = 0.0, hb = 0.0;
+            for (int k = 0; k < 3; k++) {
+                const double da = r->cap_p1[la][k] - r->cap_p0[la][k], db = r->cap_p1[lb][k] - r->cap_p0[lb][k];
+                ha += da * da;
+                hb += db * db;
+            }
+            const double diag = 1.7320508075688772 * args.env.map_res * (1.0 + 1e-6) + 1e-9;
+            const double reach = (0.5 * sqrt(ha) + 0.5 * sqrt(hb) + r->cap_radius[la] + r->cap_radius[lb] + diag) * (1.0 + 1e-9);
+            f->pair_reach_sq[q] = reach * reach;
         }
     }
     __syncthreads();
