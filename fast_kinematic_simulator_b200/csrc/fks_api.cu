@@ -456,6 +456,31 @@ int fks_robot_create(int device, const fks_robot_desc* r, fks_robot** out) {
         pzl[(size_t)i].link = plink[(size_t)i];
         pzl[(size_t)i]._pad = 0;
     }
+    // Joint matrix as a function of the joint value (linked robots): M_j(q) = J_t R(q) with Rodrigues' form
+    // R = I + sin q K + (1 - cos q) K^2, K = [axis]x  ->  M_j = J_t + sin q (J_t K) + (1 - cos q) (J_t K^2); prismatic:
+    // M_j = J_t + q [0 | J_t axis].  The two constant 3x4 matrices per joint are formed here once (algebraically the same
+    // entries as Eigen's AngleAxis -> quaternion -> matrix path the reference takes, for any axis length).
+    for (int j = 0; j < h.J; j++) {
+        DevJoint& d = h.joints[j];
+        const double ax = d.axis[0], ay = d.axis[1], az = d.axis[2];
+        double* C1 = d.C1;
+        double* C2 = d.C2;
+        for (int i = 0; i < 12; i++) C1[i] = C2[i] = 0.0;
+        if (d.active < 0) continue;
+        if (d.type == FKS_JOINT_PRISMATIC) {
+            for (int r = 0; r < 3; r++) C1[4 * r + 3] = d.T[4 * r + 0] * ax + d.T[4 * r + 1] * ay + d.T[4 * r + 2] * az;
+        } else {
+            const double K[9] = {0.0, -az, ay, az, 0.0, -ax, -ay, ax, 0.0};
+            double K2[9];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) K2[3 * r + c] = K[3 * r + 0] * K[c] + K[3 * r + 1] * K[3 + c] + K[3 * r + 2] * K[6 + c];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) {
+                    C1[4 * r + c] = d.T[4 * r + 0] * K[c] + d.T[4 * r + 1] * K[3 + c] + d.T[4 * r + 2] * K[6 + c];
+                    C2[4 * r + c] = d.T[4 * r + 0] * K2[c] + d.T[4 * r + 1] * K2[3 + c] + d.T[4 * r + 2] * K2[6 + c];
+                }
+        }
+    }
     int rc = upload(&rob->d_robot, &rob->host, 1);
     if (rc == FKS_OK) rc = upload(&rob->d_pxy, pxy.data(), pxy.size());
     if (rc == FKS_OK) rc = upload(&rob->d_pzl, pzl.data(), pzl.size());

@@ -41,6 +41,9 @@ struct DevJoint {
     double T[12];
     double axis[3];
     double lo, hi, weight;
+    // M_j(q) = T + s1 C1 + s2 C2 with (s1, s2) = (sin q, 1 - cos q) for revolute / continuous joints (C1 = T K, C2 = T K^2,
+    // K = [axis]x: Rodrigues' form of T R(q)), (q, 0) for prismatic ones (C1 = [0 | T axis]); filled by fks_robot_create
+    double C1[12], C2[12];
 };
 
 struct DevRobot {

@@ -325,10 +325,11 @@ __device__ __noinline__ void kinematics(int wb, int X, int derive) {
         __syncwarp();
     } else {
         double* M = ws + wl.M;
-        // one joint per lane: value (wrap / clamp), then M_j = joint_transform * motion(value)
+        // one joint per lane: value (wrap / clamp) and its sine / one-minus-cosine (prismatic: the value itself / 0) ...
+        double* sc = ws + wl.jaxis;  // 2 J doubles; collect_corrections refills jaxis whenever it needs it
         for (int j = lane; j < rb.J; j += 32) {
             const DevJoint& jd = rb.joints[j];
-            double Mj[12];
+            double s1 = 0.0, s2 = 0.0;
             if (jd.active >= 0) {
                 double v = cfg[jd.active];
                 if (jd.type == FKS_JOINT_CONTINUOUS) {
@@ -338,26 +339,23 @@ __device__ __noinline__ void kinematics(int wb, int X, int derive) {
                     else if (v < jd.lo) v = jd.lo;
                 }
                 cfg[jd.active] = v;
-                double R[12];
                 if (jd.type == FKS_JOINT_PRISMATIC) {
-#pragma unroll
-                    for (int i = 0; i < 12; i++) R[i] = (i % 5 == 0) ? 1.0 : 0.0;
-                    R[3] = jd.axis[0] * v;
-                    R[7] = jd.axis[1] * v;
-                    R[11] = jd.axis[2] * v;
+                    s1 = v;
                 } else {
-                    rot_axis(v, jd.axis[0], jd.axis[1], jd.axis[2], R);
+                    double c;
+                    sincos(v, &s1, &c);
+                    s2 = 1.0 - c;
                 }
-                double Jt[12];
-#pragma unroll
-                for (int i = 0; i < 12; i++) Jt[i] = jd.T[i];
-                iso_mul(Jt, R, Mj);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 12; i++) Mj[i] = jd.T[i];
             }
-#pragma unroll
-            for (int i = 0; i < 12; i++) M[12 * j + i] = Mj[i];
+            sc[2 * j] = s1;
+            sc[2 * j + 1] = s2;
+        }
+        __syncwarp();
+        // ... then all lanes build M_j = J_t + s1 (J_t K) + s2 (J_t K^2), one matrix element each (fks_robot_create)
+        for (int el = lane; el < 12 * rb.J; el += 32) {
+            const int j = el / 12, e = el - 12 * j;
+            const DevJoint& jd = rb.joints[j];
+            M[el] = jd.T[e] + sc[2 * j] * jd.C1[e] + sc[2 * j + 1] * jd.C2[e];
         }
         // chain T_child = T_parent * M_j on lanes 0..11; lanes 12..23 run the SAME recurrence from the root
         // (1 / res) * inverse_origin * base, which yields the world->voxel transforms G_l = (1 / res) * inverse_origin * T_l
