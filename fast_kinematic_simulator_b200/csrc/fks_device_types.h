@@ -140,6 +140,9 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     int o = 0;
     w.cfg = o; o += 3 * S;
     w.T = o; o += 3 * w.L12;
+    // kinematics<LINKED> runs the T chain (lanes 0..11) and the G chain (lanes 12..23) in the same instructions: their row loads
+    // must not share banks, so G starts 2 doubles (mod 16 = one bank cycle) after a multiple of 16 from T
+    o += (2 + 16 - (o - w.T) % 16) % 16;
     w.G = o; o += w.L12;
     w.caps = o; o += 6 * L;
     w.M = o; o += 12 * J;

@@ -122,10 +122,14 @@ __device__ __forceinline__ double wrap_angle(double value) {
     return value;
 }
 
+// (T is 16-byte aligned wherever it lives: 128-bit loads halve the shared-memory instructions and wavefronts of the point loops)
 __device__ __forceinline__ void apply_T(const double* T, double x, double y, double z, double& ox, double& oy, double& oz) {
-    ox = T[0] * x + T[1] * y + T[2] * z + T[3];
-    oy = T[4] * x + T[5] * y + T[6] * z + T[7];
-    oz = T[8] * x + T[9] * y + T[10] * z + T[11];
+    const double2 t01 = *reinterpret_cast<const double2*>(T + 0), t23 = *reinterpret_cast<const double2*>(T + 2);
+    const double2 t45 = *reinterpret_cast<const double2*>(T + 4), t67 = *reinterpret_cast<const double2*>(T + 6);
+    const double2 t89 = *reinterpret_cast<const double2*>(T + 8), tab = *reinterpret_cast<const double2*>(T + 10);
+    ox = t01.x * x + t01.y * y + t23.x * z + t23.y;
+    oy = t45.x * x + t45.y * y + t67.x * z + t67.y;
+    oz = t89.x * x + t89.y * y + tab.x * z + tab.y;
 }
 
 // Quaterniond(AngleAxisd(angle, axis)).toRotationMatrix(), translation zero
