@@ -121,7 +121,7 @@ struct WarpLayout {
     int jaxis, jorig;  // 3 * J each
     int target, scfg, act, ru, du, raw, stepv;  // S each
     int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
-    int qr;       // QR bookkeeping: max(4 * S, 64) doubles (the register QR parks R, 1/diag and Q^T c here: NC^2 + 2 NC <= 63)
+    int qr;       // 4 * S doubles: bookkeeping of the generic QR (norms, Householder coefficients, transpositions)
     int cand;     // 32 doubles = 32 candidate records of collect_corrections
     int vars;     // WarpVars (kWarpVarsDoubles) + 2 * S doubles of PID state
     int stats;    // FKS_NUM_STATS u64 counters of this warp
@@ -145,7 +145,7 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     o += (2 + 16 - (o - w.T) % 16) % 16;
     w.G = o; o += w.L12;
     w.caps = o; o += 6 * L;
-    w.M = o; o += 12 * J;
+    w.M = o; o += 16 * J;  // joint matrices, TRANSPOSED and padded: element (row k, column c) of joint j at 16 j + 4 c + k
     w.jaxis = o; o += 3 * J;
     w.jorig = o; o += 3 * J;
     o = (o + 1) & ~1;
@@ -157,7 +157,7 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.raw = o; o += S;
     w.stepv = o; o += S;
     w.tn = o; o += w.noise_batch * S;
-    w.qr = o; o += (4 * S > 64 ? 4 * S : 64);
+    w.qr = o; o += 4 * S;  // generic solver: 3 D doubles + D ints; SE3: the actuated twist
     w.cand = o; o += 32;
     w.vars = o; o += kWarpVarsDoubles + 2 * S;
     w.stats = o; o += FKS_NUM_STATS;

@@ -359,7 +359,7 @@ __device__ __noinline__ void kinematics(int wb, int X, int derive) {
         for (int el = lane; el < 12 * rb.J; el += 32) {
             const int j = el / 12, e = el - 12 * j;
             const DevJoint& jd = rb.joints[j];
-            M[el] = jd.T[e] + sc[2 * j] * jd.C1[e] + sc[2 * j + 1] * jd.C2[e];
+            M[16 * j + 4 * (e & 3) + (e >> 2)] = jd.T[e] + sc[2 * j] * jd.C1[e] + sc[2 * j + 1] * jd.C2[e];  // stored by columns
         }
         // chain T_child = T_parent * M_j on lanes 0..11; lanes 12..23 run the SAME recurrence from the root
         // (1 / res) * inverse_origin * base, which yields the world->voxel transforms G_l = (1 / res) * inverse_origin * T_l
@@ -375,10 +375,13 @@ __device__ __noinline__ void kinematics(int wb, int X, int derive) {
         for (int j = 0; j < rb.J; j++) {
             const DevJoint& jd = rb.joints[j];
             if (in_chain) {
-                const double* Tp = chain + 12 * jd.parent;
-                const double* Mj = M + 12 * j;
-                double v = Tp[4 * r + 0] * Mj[cc] + Tp[4 * r + 1] * Mj[4 + cc] + Tp[4 * r + 2] * Mj[8 + cc];
-                if (cc == 3) v += Tp[4 * r + 3];
+                // row r of the parent transform and column cc of the joint matrix, two 128-bit loads each
+                const double* Tp = chain + 12 * jd.parent + 4 * r;
+                const double* Mc = M + 16 * j + 4 * cc;
+                const double2 t01 = *reinterpret_cast<const double2*>(Tp), t23 = *reinterpret_cast<const double2*>(Tp + 2);
+                const double2 m01 = *reinterpret_cast<const double2*>(Mc), m23 = *reinterpret_cast<const double2*>(Mc + 2);
+                double v = t01.x * m01.x + t01.y * m01.y + t23.x * m23.x;
+                if (cc == 3) v += t23.y;
                 chain[12 * jd.child + e12] = v;
             }
             __syncwarp();
