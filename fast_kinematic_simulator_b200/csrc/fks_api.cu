@@ -481,6 +481,12 @@ int fks_robot_create(int device, const fks_robot_desc* r, fks_robot** out) {
                 }
         }
     }
+    static_assert(kMaxLinks <= 16 && kMaxJoints <= 16, "joint_parents / joint_children pack one nibble per joint");
+    h.joint_parents = h.joint_children = 0ull;
+    for (int j = 0; j < h.J; j++) {
+        h.joint_parents |= (unsigned long long)h.joints[j].parent << (4 * j);
+        h.joint_children |= (unsigned long long)h.joints[j].child << (4 * j);
+    }
     int rc = upload(&rob->d_robot, &rob->host, 1);
     if (rc == FKS_OK) rc = upload(&rob->d_pxy, pxy.data(), pxy.size());
     if (rc == FKS_OK) rc = upload(&rob->d_pzl, pzl.data(), pzl.size());

@@ -52,6 +52,7 @@ struct DevRobot {
     double pos_w, rot_w;
     DevAxis axes[kMaxDof];
     DevJoint joints[kMaxJoints];
+    unsigned long long joint_parents, joint_children;  // link indices of joint j in bits 4j .. 4j+3 (kMaxLinks = kMaxJoints = 16)
     int active_joint[kMaxDof];        // active dof -> joint index
     int link_begin[kMaxLinks + 1];
     unsigned link_ancestors[kMaxLinks];  // bit j: joint j is on the path from the root to this link

@@ -372,17 +372,17 @@ __device__ __noinline__ void kinematics(int wb, int X, int derive) {
         const int r = e12 >> 2, cc = e12 & 3;
         double* chain = lane < 12 ? T : G;
         const bool in_chain = lane < 12 || (lane < 24 && derive);
-        for (int j = 0; j < rb.J; j++) {
-            const DevJoint& jd = rb.joints[j];
+        unsigned long long parents = rb.joint_parents, children = rb.joint_children;  // one nibble per joint
+        for (int j = 0; j < rb.J; j++, parents >>= 4, children >>= 4) {
             if (in_chain) {
                 // row r of the parent transform and column cc of the joint matrix, two 128-bit loads each
-                const double* Tp = chain + 12 * jd.parent + 4 * r;
+                const double* Tp = chain + 12 * (int)(parents & 0xFull) + 4 * r;
                 const double* Mc = M + 16 * j + 4 * cc;
                 const double2 t01 = *reinterpret_cast<const double2*>(Tp), t23 = *reinterpret_cast<const double2*>(Tp + 2);
                 const double2 m01 = *reinterpret_cast<const double2*>(Mc), m23 = *reinterpret_cast<const double2*>(Mc + 2);
                 double v = t01.x * m01.x + t01.y * m01.y + t23.x * m23.x;
                 if (cc == 3) v += t23.y;
-                chain[12 * jd.child + e12] = v;
+                chain[12 * (int)(children & 0xFull) + e12] = v;
             }
             __syncwarp();
         }
@@ -1486,6 +1486,7 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
     int nonzero_pivots = size;
     unsigned order = 0u;        // 4 bits per step: the column picked at step k
     unsigned pos = 0x76543210u; // 4 bits per column: its position in the permuted order
+    unsigned colof = 0x76543210u; // 4 bits per position: the column sitting there (inverse of pos)
     bool near_cut = false;
     constexpr int NF = (NC + 1 <= 4) ? 4 : 8;  // width of the folded reductions
 #pragma unroll 1
@@ -1533,10 +1534,11 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
                 if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
                 if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
                 // the column that sat at position k takes the pivot's old position, the pivot takes position k
-#pragma unroll
-                for (int j = 0; j < NC; j++)
-                    if ((int)((pos >> (4 * j)) & 0xFu) == k) pos = (pos & ~(0xFu << (4 * j))) | ((unsigned)best_pos << (4 * j));
+                const unsigned q = (colof >> (4 * k)) & 0xFu;
+                pos = (pos & ~(0xFu << (4 * q))) | ((unsigned)best_pos << (4 * q));
                 pos = (pos & ~(0xFu << (4 * p))) | ((unsigned)k << (4 * p));
+                colof = (colof & ~(0xFu << (4 * best_pos))) | (q << (4 * best_pos));
+                colof = (colof & ~(0xFu << (4 * k))) | ((unsigned)p << (4 * k));
                 nsq_p = big_sq;
             } else {
                 nsq_p = __shfl_sync(FKS_FULL, y, fold_lane<NF>(k));
@@ -1568,8 +1570,10 @@ __device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int
         if (lane == k) {
             v[0] = 1.0;
             rdiag_mine = inv_beta;
+            if (reduce_only) {  // R(k,k) itself is only read by the fold's write-back (the solve uses its reciprocal)
 #pragma unroll
-            for (int j = 0; j < NC; j++) a[0][j] = (j == p) ? beta : a[0][j];
+                for (int j = 0; j < NC; j++) a[0][j] = (j == p) ? beta : a[0][j];
+            }
         }
         const bool apply_b = reduce_only || nonzero_pivots > k;  // Eigen's solve applies the first nonzero_pivots reflectors to c
         // ---- applyHouseholderOnTheLeft to the remaining columns and the right-hand side ----------------------------
