@@ -456,8 +456,11 @@ __device__ __forceinline__ float sdf_cell(const DevEnv& e, int x, int y, int z) 
     return __ldg(e.sdf + ((x * e.ny + y) * e.nz + z));
 }
 
+#ifndef FKS_COLLECT_ESTIMATE
+#define FKS_COLLECT_ESTIMATE estimate_distance_inl
+#endif
 // SignedDistanceField::EstimateDistance4d for an in-bounds point whose cell (x,y,z) holds d0f
-__device__ __noinline__ double estimate_distance(double wx, double wy, double wz, int x, int y, int z, float d0f) {
+__device__ __forceinline__ double estimate_distance_inl(double wx, double wy, double wz, int x, int y, int z, float d0f) {
     const DevEnv& e = frame().a.env;
     const double res = e.sdf_res;
     const double d0 = (double)d0f;
@@ -485,6 +488,11 @@ __device__ __noinline__ double estimate_distance(double wx, double wy, double wz
     double adj = 0.0;
     if (gg > 0.0) adj = (vx * g0 + vy * g1 + vz * g2) / sqrt(gg);
     return dc + adj;
+}
+// out-of-line copy for the rare second tier of check_env; collect_corrections inlines the body (a call there spills a
+// dozen live doubles around it)
+__device__ __noinline__ double estimate_distance(double wx, double wy, double wz, int x, int y, int z, float d0f) {
+    return estimate_distance_inl(wx, wy, wz, x, y, z, d0f);
 }
 
 // voxel of a link-relative point through the composite transform G_l; false when out of bounds.
@@ -1147,7 +1155,7 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
                 const float f = __uint_as_float(rec2.y);
                 const long long li = ((long long)vxx * e.ny + vyy) * e.nz + vzz;
                 const uint2 nrange = (f < 0.5f * near) ? normal_range_probe(e, li) : make_uint2(0u, 0u);  // issued early
-                const double est = estimate_distance(wx, wy, wz, vxx, vyy, vzz, f);
+                const double est = FKS_COLLECT_ESTIMATE(wx, wy, wz, vxx, vyy, vzz, f);
                 if (est < 0.0) {  // resolution_distance_threshold_ = 0.0 (spcs:425,1874)
                     double qx, qy, qz;
                     apply_T(Tprev + 12 * l, lx, ly, lz, qx, qy, qz);
