@@ -1687,6 +1687,12 @@ __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned
 #ifndef FKS_FREE_ROUNDS
 #define FKS_FREE_ROUNDS 3
 #endif
+// Rounds group 1 may run while the solvers of a super-cycle are busy (it stops earlier when they finish).  The solvers are the
+// critical path and share the schedulers with group 1: measured 1 / 2 / 3 / 4 / 8 / 16 / 32 rounds on the arm contact workload
+// 107.6 / 101.5 / 100.4 / 102.3 / 105.4 / 105.5 / 107.4 ms, on SE(3) 58.7 / 51.8 / 50.9 / 49.4 / 49.9 / 50.0 / 50.4 ms.
+#ifndef FKS_G1_ROUNDS
+#define FKS_G1_ROUNDS(kind) ((kind) == FKS_ROBOT_LINKED ? 3 : 4)
+#endif
 #ifndef FKS_SLOT_ITERATIONS
 #define FKS_SLOT_ITERATIONS(kind) ((kind) == FKS_ROBOT_SE2 ? 1 : 0)
 #endif
@@ -2164,7 +2170,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             }
             if (!counted_solver) {
                 // group 1 only: another round while group 2 is still busy (decision made uniform by the barrier reduction)
-                const bool keep = (*g2_done < (unsigned)n_solvers) && (round < 16 * (kSlotIters > 1 ? kSlotIters : 1));
+                const bool keep = (*g2_done < (unsigned)n_solvers) && (round < FKS_G1_ROUNDS(KIND) * (kSlotIters > 1 ? kSlotIters : 1));
                 const bool go_on = named_barrier_or(1, bar_threads, keep);
                 FKS_TICK(1)
 #ifdef FKS_PHASE_TIMERS
