@@ -53,12 +53,14 @@ def bench_md():
                                                                                g["achieved_gathers_per_s"], g["l2_peak_gathers_per_s"], g["frac_of_l2_peak"]))
     L.append("Full JSON of the default run:\n\n```json\n%s\n```\n" % json.dumps(main))
     eight = load("bench_8gpu.json")
+    base8 = load("bench_8gpu_base.json") or main  # the one-GPU line measured with the same kernel build as the 8-GPU line
     if eight:
         L.append("## Eight GPUs (`gpurun --gpus 8`, `python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8 --steps 5 --warmup 3`, NCCL "
                  "all-gather of the 72-byte end-state records inside the timed step; this round's final solver)\n\n%.3e particle-microsteps/s over "
-                 "%d particles, %.1f ms/step (weak scaling, 65 536 particles per GPU): %.1f %% of eight times the one-GPU value above.\n\n"
+                 "%d particles, %.1f ms/step (weak scaling, 65 536 particles per GPU): %.1f %% of eight times the one-GPU value of the same "
+                 "kernel build (%.3e, %.1f ms/step; the table above may be a later build).\n\n"
                  "```json\n%s\n```\n" % (eight["value"], eight["config"]["particles_total"], eight["ms_per_step"],
-                                          100.0 * eight["value"] / (8.0 * main["value"]), json.dumps(eight)))
+                                          100.0 * eight["value"] / (8.0 * base8["value"]), base8["value"], base8["ms_per_step"], json.dumps(eight)))
     two = load("bench_r1_2gpu.json")
     if two:
         L.append("## Two GPUs (`gpurun --gpus 2`, torchrun, NCCL all-gather of the 72-byte end-state records inside the timed step; measured "
