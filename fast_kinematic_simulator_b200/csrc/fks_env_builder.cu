@@ -195,11 +195,14 @@ __global__ void __launch_bounds__(256) edt_line_kernel(int* __restrict__ field, 
         const int own = tile[q * W + tx];
         const int sign = own > 0 ? 1 : -1;
         int best = own * sign;
+        // outwards from q while r^2 can still beat the best; past the ends of the line the index is clamped: the end cell is then
+        // re-read with a larger r^2 than when it was met at its true distance, which cannot lower the minimum
         const int rmax = max(q, n - 1 - q);
-        for (int r = 1; r <= rmax && r * r < best; r++) {
-            const int rr = r * r;
-            if (q - r >= 0) best = min(best, max(sign * tile[(q - r) * W + tx], 0) + rr);
-            if (q + r < n) best = min(best, max(sign * tile[(q + r) * W + tx], 0) + rr);
+        const int* col = tile + tx;
+        for (int r = 1, rr = 1; r <= rmax && rr < best; rr += 2 * r + 1, r++) {
+            const int lo = max(q - r, 0), hi = min(q + r, n - 1);
+            const int cand = min(max(sign * col[lo * W], 0), max(sign * col[hi * W], 0)) + rr;
+            best = min(best, cand);
         }
         best = min(best, kInf);
         if (FINAL) {
@@ -536,7 +539,7 @@ extern "C" int fks_env_build_device(int device, const fks_obstacle* obstacles, s
         cudaGetLastError();
     }
     cudaStream_t st = 0;
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 10; i++) {  // 8 phase boundaries + the two ends of the table-allocation gap inside phase 6
         cudaEvent_t e;
         FKS_TRY(cudaEventCreate(&e));
         tmp.events.push_back(e);
@@ -608,6 +611,7 @@ extern "C" int fks_env_build_device(int device, const fks_obstacle* obstacles, s
     FKS_TRY(cudaGetLastError());
     unsigned long long total = 0;
     FKS_TRY(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
+    FKS_TRY(cudaEventRecord(tmp.events[8], st));  // the stream idles from here until the table arrays are allocated
     FKS_TRY(cudaStreamSynchronize(st));
     const size_t n_normal_cells = (size_t)(total >> 32), n_entries = (size_t)(total & 0xffffffffull);
     // the table arrays also come from the stream-ordered pool (fks_env_destroy releases them with cudaFree, which accepts both)
@@ -617,6 +621,7 @@ extern "C" int fks_env_build_device(int device, const fks_obstacle* obstacles, s
     FKS_TRY(Temps::pooled_alloc((void**)&env->d_entries, std::max<size_t>(n_entries, 1) * 6 * sizeof(double), st));
     FKS_TRY(Temps::pooled_alloc((void**)&env->d_cell_index, std::max<size_t>(n_normal_cells, 1) * sizeof(long long), st));
     FKS_TRY(Temps::pooled_alloc((void**)&env->d_cell_start, (n_normal_cells + 1) * sizeof(unsigned), st));
+    FKS_TRY(cudaEventRecord(tmp.events[9], st));
     FKS_TRY(cudaMemsetAsync(env->d_keys, 0, 2 * cap * sizeof(unsigned long long), st));
     FKS_TRY(cudaMemsetAsync(env->d_entries, 0, std::max<size_t>(n_entries, 1) * 6 * sizeof(double), st));
     normals_emit_kernel<<<(unsigned)n_blocks, kScanThreads, 0, st>>>(d_obs, g, env->d_sdf, d_winner, d_count, d_block_sums, env->d_cell_index,
@@ -648,6 +653,11 @@ extern "C" int fks_env_build_device(int device, const fks_obstacle* obstacles, s
         float ms = 0.f;
         cudaEventElapsedTime(&ms, tmp.events[0], tmp.events[7]);
         env->build_ms[0] = ms;
+        // phase 6 without the host-side allocation of the table arrays (size known only after the scan; cudaMalloc of
+        // hundreds of MB takes 5-20 ms and is not device work): reported separately as [8]
+        cudaEventElapsedTime(&ms, tmp.events[8], tmp.events[9]);
+        env->build_ms[8] = ms;
+        env->build_ms[6] -= ms;
     }
 
     DevEnv& d = env->dev;
@@ -673,7 +683,7 @@ extern "C" int fks_env_build_device(int device, const fks_obstacle* obstacles, s
 
 extern "C" int fks_env_build_timings(const fks_env* env, double* out_ms, int n) {
     if (!env || !out_ms || n < 0) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_env_build_timings: invalid argument");
-    for (int i = 0; i < n; i++) out_ms[i] = i < 8 ? env->build_ms[i] : 0.0;
+    for (int i = 0; i < n; i++) out_ms[i] = i < 9 ? env->build_ms[i] : 0.0;
     return FKS_OK;
 }
 

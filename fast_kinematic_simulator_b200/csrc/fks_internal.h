@@ -38,7 +38,7 @@ struct fks_env {
     size_t n_entries;
     size_t sdf_bytes;
     size_t l2_window_bytes;
-    double build_ms[8];           // device builder phase timings (fks_env_build_timings)
+    double build_ms[9];           // device builder phase timings (fks_env_build_timings)
 };
 
 // Host environment (fks_build_environment / fks_env_download).

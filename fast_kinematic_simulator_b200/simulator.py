@@ -98,7 +98,8 @@ def _obstacle_array(obstacles):
     return arr, len(obstacles)
 
 
-BUILD_PHASES = ("total", "rasterize", "edt_z", "edt_y", "edt_x_sdf", "normals_mark", "normals_emit", "distance_field_check")
+BUILD_PHASES = ("total", "rasterize", "edt_z", "edt_y", "edt_x_sdf", "normals_mark", "normals_emit", "distance_field_check",
+                "table_allocation")
 
 
 def build_complete_environment_on_device(obstacles, resolution, device=0):

@@ -317,7 +317,8 @@ void fks_built_env_destroy(fks_built_env* env);
  * rasterisation, exact Euclidean distance transform, float SDF, surface-normal table and its hash -- with no host
  * copy of the grids.  Results are bit-identical to fks_build_environment + fks_env_create.
  * fks_env_build_timings: out_ms[0] = total device time of the build, [1] rasterise, [2] z pass, [3] y pass,
- * [4] x pass + SDF, [5] surface marking, [6] normal count/scan/emit, [7] distance-field check (milliseconds).
+ * [4] x pass + SDF, [5] surface marking, [6] normal count/scan/emit, [7] distance-field check, [8] the host-side allocation
+ * of the table arrays inside phase 6 (their size is known only after the scan; included in [0], not in [6]) -- milliseconds.
  * fks_env_download: copies a device environment back into host arrays (any fks_env; occupancy only when the
  * environment was built on the device, else fks_built_env_occupancy returns NULL).
  * ----------------------------------------------------------------------------------------- */

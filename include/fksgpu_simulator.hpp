@@ -95,9 +95,9 @@ public:
     DeviceEnvironment(const DeviceEnvironment&) = delete;
     DeviceEnvironment& operator=(const DeviceEnvironment&) = delete;
     fks_env* Handle() const { return env_; }
-    // milliseconds of device time: total, rasterise, z / y / x passes, surface marking, normal emit, distance-field check
+    // milliseconds: total, rasterise, z / y / x passes, surface marking, normal emit, distance-field check, table allocation
     std::vector<double> BuildTimingsMs() const {
-        std::vector<double> ms(8, 0.0);
+        std::vector<double> ms(9, 0.0);
         Check(fks_env_build_timings(env_, ms.data(), (int)ms.size()));
         return ms;
     }
