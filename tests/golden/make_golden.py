@@ -4,6 +4,9 @@ vectors, which come from the REFERENCE's own header through oracle/_ref/pid_ref)
     python tests/golden/make_golden.py
 
 * pid_golden.json        -- outputs of the reference's SimplePIDController (bit-exact pin of the PID restatement)
+* env_golden.npz         -- BuildCompleteEnvironment of two small obstacle sets (tests/env_cases.py: thin_plates, rotated_boxes)
+                            by the oracle: occupancy, float SDF, surface-normal table (host and device builder are held to it)
+* trace_golden.npz       -- step traces (ForwardSimulationStepTrace, flat) of single particles by the oracle, Philox noise
 * forward_golden.npz     -- oracle end states for small seeded batches of every robot kind with the recorded
                             noise tape: the GPU tests replay the tape and compare, so a GPU box without the oracle
                             build (or a future oracle change) is still pinned to these numbers.  The reference
@@ -54,7 +57,44 @@ def forward():
     np.savez_compressed(os.path.join(HERE, "forward_golden.npz"), **out)
 
 
+ENV_CASES = ("thin_plates", "rotated_boxes")
+TRACE_CASES = (("se2_arena", 3), ("arm_elbow", 0), ("se3_narrow_passage", 5))
+
+
+def environments():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from env_cases import CASES
+
+    out = {}
+    for name in ENV_CASES:
+        obstacles, res = CASES[name]()
+        e = OB.build_environment(obstacles, res)
+        out[name + "_shape"] = np.array(e["shape"], dtype=np.int64)
+        out[name + "_origin"] = e["origin"]
+        out[name + "_occupancy"] = np.packbits(e["occupancy"].reshape(-1))
+        out[name + "_sdf"] = e["sdf"]
+        out[name + "_cells"] = e["normal_cell_index"]
+        out[name + "_starts"] = e["normal_cell_start"]
+        out[name + "_entries"] = e["normal_entries"]
+    np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **out)
+
+
+def traces():
+    out = {}
+    for name, pid_ in TRACE_CASES:
+        w = W.make(name, n_particles=8)
+        orc = OB.OracleSimulator(w.environment().desc, w.robot.to_c(), capi.default_solver_params(), 25.0, 42, 1)
+        t = w.targets[0] if w.targets.shape[0] == 1 else w.targets[pid_]
+        res, tr = orc.forward_simulate_traced(w.starts[pid_], t, True, capi.NOISE_PHILOX, particle_id=pid_)
+        out[name + "_header"] = np.stack([tr["kind"], tr["step"], tr["microstep"], tr["iteration"]], axis=1)
+        out[name + "_values"] = tr["values"]
+        out[name + "_cfg"] = res["cfg"]
+    np.savez_compressed(os.path.join(HERE, "trace_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     pid()
     forward()
+    environments()
+    traces()
     print("golden fixtures written")
