@@ -40,6 +40,8 @@ FLAG_EMPTY_JACOBIAN = 1 << 11
 FLAG_TAPE_EXHAUSTED = 1 << 12
 FLAG_NEAR_RANK_CUT = 1 << 13
 FLAG_J_SPILLED = 1 << 14
+FLAG_DECISION_OVERRIDDEN = 1 << 15
+FLAG_DECISION_DESYNC = 1 << 16
 TRACE_CONTROL_INPUT, TRACE_CONTROL_INPUT_STEP, TRACE_POST_ACTION, TRACE_RESOLUTION_STEP, TRACE_RETURNED_PREVIOUS = range(5)
 NUM_STATS = 11
 STAT_NAMES = (
@@ -137,7 +139,8 @@ class RobotDesc(C.Structure):
 
 
 class NoiseTape(C.Structure):
-    _fields_ = [("draws", C.POINTER(C.c_double)), ("offsets", C.POINTER(C.c_uint64))]
+    _fields_ = [("draws", C.POINTER(C.c_double)), ("offsets", C.POINTER(C.c_uint64)),
+                ("decisions", C.POINTER(C.c_uint64)), ("decision_offsets", C.POINTER(C.c_uint64))]
 
 
 class Obstacle(C.Structure):
@@ -180,6 +183,7 @@ EXPORTS = (
     "fks_env_build_device",
     "fks_env_build_timings",
     "fks_env_download",
+    "fks_debug_qr_solve",
     "fks_measure_fp64_peak",
     "fks_measure_gather_rate",
 )
@@ -230,6 +234,7 @@ lib.fks_built_env_destroy.restype = None
 lib.fks_env_build_device.argtypes = [C.c_int, P(Obstacle), C.c_size_t, C.c_double, P(C.c_void_p)]
 lib.fks_env_build_timings.argtypes = [C.c_void_p, P(C.c_double), C.c_int]
 lib.fks_env_download.argtypes = [C.c_void_p, P(C.c_void_p)]
+lib.fks_debug_qr_solve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_size_t, C.c_void_p, C.c_void_p]
 lib.fks_measure_fp64_peak.argtypes = [C.c_int, P(C.c_double)]
 lib.fks_measure_gather_rate.argtypes = [C.c_int, C.c_size_t, P(C.c_double)]
 

@@ -111,9 +111,15 @@ struct fks_sim {
     unsigned int* d_counter;
     // staging for the host-buffer entry point (grown on demand)
     double *d_starts, *d_targets, *d_tape;
-    unsigned long long* d_tape_off;
+    unsigned long long *d_tape_off, *d_dec, *d_dec_off;
     char* d_results;
-    size_t cap_starts, cap_targets, cap_tape, cap_tape_off, cap_results;
+    size_t cap_starts, cap_targets, cap_tape, cap_tape_off, cap_results, cap_dec, cap_dec_off;
+    size_t smem_limit;
+    // launches of one simulator share its particle counter, scratch slots and statistics: a launch on another stream waits
+    // for the previous one (fks_forward_simulate_device takes the caller's stream)
+    cudaEvent_t last_done;
+    cudaStream_t last_stream;
+    bool has_last;
     uint64_t launches;
     std::string info;
     // set by fks_forward_simulate_traced around its launch, null otherwise
@@ -532,9 +538,17 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     s->d_stats = nullptr;
     s->d_counter = nullptr;
     s->d_starts = s->d_targets = s->d_tape = nullptr;
-    s->d_tape_off = nullptr;
+    s->d_tape_off = s->d_dec = s->d_dec_off = nullptr;
     s->d_results = nullptr;
-    s->cap_starts = s->cap_targets = s->cap_tape = s->cap_tape_off = s->cap_results = 0;
+    s->cap_starts = s->cap_targets = s->cap_tape = s->cap_tape_off = s->cap_results = s->cap_dec = s->cap_dec_off = 0;
+    s->last_done = nullptr;
+    s->last_stream = nullptr;
+    s->has_last = false;
+    {
+        int lim = 0;
+        if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, env->device) != cudaSuccess || lim <= 0) lim = 48 * 1024;
+        s->smem_limit = (size_t)lim;
+    }
     s->launches = 0;
     s->d_trace = nullptr;
     s->d_trace_count = nullptr;
@@ -561,7 +575,7 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     // largest lock-step CTA whose shared memory fits the SM (robots with many links / points get fewer warps per CTA)
     int rc = 0;
     for (;; wpb = (wpb > 4) ? wpb - 4 : wpb - 1) {
-        s->dyn_smem = simulate_smem_plan(&s->plan, h.L, h.J, h.D, h.P, robot->stride, wpb);
+        s->dyn_smem = simulate_smem_plan(&s->plan, h.L, h.J, h.D, h.P, robot->stride, wpb, s->smem_limit);
         s->kinfo.max_blocks_per_sm = 0;
         rc = simulate_kernel_info(h.kind, s->dyn_smem, wpb, &s->kinfo);
         if ((rc == 0 && s->kinfo.max_blocks_per_sm >= 1) || wpb <= 1) break;
@@ -582,6 +596,7 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     s->num_sms = prop.multiProcessorCount;
     const size_t scratch_bytes = (size_t)s->grid_max * wpb * s->plan.sl.total;
     if ((err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (err = cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_scratch, scratch_bytes)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_stats, 64 * sizeof(unsigned long long))) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_counter, sizeof(unsigned int))) != cudaSuccess ||
@@ -604,6 +619,7 @@ void fks_sim_destroy(fks_sim* s) {
     if (!s) return;
     DeviceGuard guard(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->has_last) cudaEventSynchronize(s->last_done);
     cudaFree(s->d_scratch);
     cudaFree(s->d_stats);
     cudaFree(s->d_counter);
@@ -611,7 +627,10 @@ void fks_sim_destroy(fks_sim* s) {
     cudaFree(s->d_targets);
     cudaFree(s->d_tape);
     cudaFree(s->d_tape_off);
+    cudaFree(s->d_dec);
+    cudaFree(s->d_dec_off);
     cudaFree(s->d_results);
+    if (s->last_done) cudaEventDestroy(s->last_done);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -622,6 +641,7 @@ size_t fks_sim_result_stride(const fks_sim* sim) {
 
 static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* d_targets, size_t n, size_t n_targets,
                               int allow_contacts, int noise_mode, const double* d_tape, const uint64_t* d_tape_off,
+                              const uint64_t* d_dec, const uint64_t* d_dec_off,
                               uint64_t first_particle_id, void* d_results, cudaStream_t stream) {
     if (n == 0) return FKS_OK;
     if (n > 0xFFFFFF00ull) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_forward_simulate: too many particles for one call");
@@ -635,6 +655,8 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
     a.targets = d_targets;
     a.tape = d_tape;
     a.tape_off = (const unsigned long long*)d_tape_off;
+    a.dec_tape = (noise_mode == FKS_NOISE_INJECTED) ? (const unsigned long long*)d_dec : nullptr;
+    a.dec_off = (const unsigned long long*)d_dec_off;
     a.results = (char*)d_results;
     a.stats = s->d_stats;
     a.counter = s->d_counter;
@@ -659,10 +681,14 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
     const size_t dyn_smem = (size_t)a.sync_off + 16;
     const size_t blocks_needed = (n + (size_t)wpb - 1) / (size_t)wpb;
     const int grid = (int)std::min<size_t>((size_t)s->grid_max, blocks_needed);
+    if (s->has_last && stream != s->last_stream) FKS_CUDA(cudaStreamWaitEvent(stream, s->last_done, 0));
     FKS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
     const int rc = launch_simulate(s->robot->host.kind, a, grid, dyn_smem, stream, s->env->l2_window_bytes ? s->env->d_sdf : nullptr,
                                    s->env->l2_window_bytes);
     if (rc != 0) return cuda_fail((cudaError_t)rc, "simulate kernel launch");
+    FKS_CUDA(cudaEventRecord(s->last_done, stream));
+    s->last_stream = stream;
+    s->has_last = true;
     s->launches++;
     return FKS_OK;
 }
@@ -695,18 +721,30 @@ int fks_forward_simulate(fks_sim* s, const double* starts, const double* targets
     if ((rc = ensure(&s->d_starts, &s->cap_starts, n * stride)) != FKS_OK) return rc;
     if ((rc = ensure(&s->d_targets, &s->cap_targets, n_targets * stride)) != FKS_OK) return rc;
     if ((rc = ensure(&s->d_results, &s->cap_results, n * rec)) != FKS_OK) return rc;
+    const bool with_decisions = noise_mode == FKS_NOISE_INJECTED && tape->decisions && tape->decision_offsets;
+    size_t n_dec_words = 0;
     if (noise_mode == FKS_NOISE_INJECTED) {
         if ((rc = ensure(&s->d_tape, &s->cap_tape, std::max<size_t>(n_draws, 1))) != FKS_OK) return rc;
         if ((rc = ensure(&s->d_tape_off, &s->cap_tape_off, n + 1)) != FKS_OK) return rc;
+        if (with_decisions) {
+            n_dec_words = (size_t)tape->decision_offsets[n] * (size_t)(2 + s->robot->host.D);
+            if ((rc = ensure(&s->d_dec, &s->cap_dec, std::max<size_t>(n_dec_words, 1))) != FKS_OK) return rc;
+            if ((rc = ensure(&s->d_dec_off, &s->cap_dec_off, n + 1)) != FKS_OK) return rc;
+        }
     }
     FKS_CUDA(cudaMemcpyAsync(s->d_starts, starts, n * stride * 8, cudaMemcpyHostToDevice, s->stream));
     FKS_CUDA(cudaMemcpyAsync(s->d_targets, targets, n_targets * stride * 8, cudaMemcpyHostToDevice, s->stream));
     if (noise_mode == FKS_NOISE_INJECTED) {
         if (n_draws) FKS_CUDA(cudaMemcpyAsync(s->d_tape, tape->draws, n_draws * 8, cudaMemcpyHostToDevice, s->stream));
         FKS_CUDA(cudaMemcpyAsync(s->d_tape_off, tape->offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+        if (with_decisions) {
+            if (n_dec_words) FKS_CUDA(cudaMemcpyAsync(s->d_dec, tape->decisions, n_dec_words * 8, cudaMemcpyHostToDevice, s->stream));
+            FKS_CUDA(cudaMemcpyAsync(s->d_dec_off, tape->decision_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+        }
     }
     rc = simulate_on_stream(s, s->d_starts, s->d_targets, n, n_targets, allow_contacts, noise_mode, s->d_tape,
-                            (const uint64_t*)s->d_tape_off, first_particle_id, s->d_results, s->stream);
+                            (const uint64_t*)s->d_tape_off, with_decisions ? (const uint64_t*)s->d_dec : nullptr,
+                            with_decisions ? (const uint64_t*)s->d_dec_off : nullptr, first_particle_id, s->d_results, s->stream);
     if (rc != FKS_OK) return rc;
     FKS_CUDA(cudaMemcpyAsync(results, s->d_results, n * rec, cudaMemcpyDeviceToHost, s->stream));
     FKS_CUDA(cudaStreamSynchronize(s->stream));
@@ -773,7 +811,7 @@ int fks_forward_simulate_device(fks_sim* s, const double* d_starts, const double
     DeviceGuard guard(s->device);
     if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_forward_simulate_device: cudaSetDevice failed");
     return simulate_on_stream(s, d_starts, d_targets, n, n_targets, allow_contacts, noise_mode, d_tape_draws, d_tape_offsets,
-                              first_particle_id, d_results, (cudaStream_t)cuda_stream);
+                              nullptr, nullptr, first_particle_id, d_results, (cudaStream_t)cuda_stream);
 }
 
 int fks_check_config_collision(fks_sim* s, const double* configs, size_t n, double inflation_ratio, uint8_t* out) {
@@ -811,19 +849,30 @@ int fks_check_config_collision(fks_sim* s, const double* configs, size_t n, doub
     return FKS_OK;
 }
 
+// waits for the simulator's own work only: its stream and the last launch made on a caller's stream
+static int sync_simulator(fks_sim* s) {
+    FKS_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->has_last) FKS_CUDA(cudaEventSynchronize(s->last_done));
+    return FKS_OK;
+}
+
 int fks_get_statistics(fks_sim* s, uint64_t* out) {
     if (!s || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_get_statistics: null argument");
     DeviceGuard guard(s->device);
-    FKS_CUDA(cudaDeviceSynchronize());
-    FKS_CUDA(cudaMemcpy(out, s->d_stats, FKS_NUM_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    int rc = sync_simulator(s);
+    if (rc != FKS_OK) return rc;
+    FKS_CUDA(cudaMemcpyAsync(out, s->d_stats, FKS_NUM_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    FKS_CUDA(cudaStreamSynchronize(s->stream));
     return FKS_OK;
 }
 
 int fks_reset_statistics(fks_sim* s) {
     if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_reset_statistics: null argument");
     DeviceGuard guard(s->device);
-    FKS_CUDA(cudaDeviceSynchronize());
-    FKS_CUDA(cudaMemset(s->d_stats, 0, 64 * sizeof(uint64_t)));
+    int rc = sync_simulator(s);
+    if (rc != FKS_OK) return rc;
+    FKS_CUDA(cudaMemsetAsync(s->d_stats, 0, 64 * sizeof(uint64_t), s->stream));
+    FKS_CUDA(cudaStreamSynchronize(s->stream));
     return FKS_OK;
 }
 
@@ -839,6 +888,43 @@ int fks_debug_phase_cycles(fks_sim* s, uint64_t* out16) {
 }
 
 const char* fks_sim_kernel_info(fks_sim* s) { return s ? s->info.c_str() : ""; }
+
+// ---------------------------------------------------------------------------------------------
+// test entry: the device's stacked-Jacobian solver on caller-provided systems (fksgpu.h)
+// ---------------------------------------------------------------------------------------------
+int fks_debug_qr_solve(int device, const double* systems, const uint64_t* offsets, const int32_t* rows, int32_t cols, size_t n,
+                       double* solutions, uint32_t* flags) {
+    if (n == 0) return FKS_OK;
+    if (!systems || !offsets || !rows || !solutions || !flags || cols < 1 || cols >= kMaxDof)
+        return fail(FKS_ERR_INVALID_ARGUMENT, "fks_debug_qr_solve: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(FKS_ERR_NO_DEVICE, "no CUDA device");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "cudaSetDevice failed");
+    const size_t total = (size_t)offsets[n];
+    double *d_work = nullptr, *d_x = nullptr;
+    unsigned long long* d_off = nullptr;
+    int* d_rows = nullptr;
+    unsigned* d_flags = nullptr;
+    int rc = upload(&d_work, systems, total);
+    if (rc == FKS_OK) rc = upload(&d_off, (const unsigned long long*)offsets, n + 1);
+    if (rc == FKS_OK) rc = upload(&d_rows, (const int*)rows, n);
+    if (rc == FKS_OK) rc = upload(&d_x, (const double*)nullptr, n * (size_t)cols);
+    if (rc == FKS_OK) rc = upload(&d_flags, (const unsigned*)nullptr, n);
+    if (rc == FKS_OK) {
+        const int lrc = launch_qr_solve(d_work, d_off, d_rows, cols, (int)n, d_x, d_flags, nullptr);
+        cudaError_t err = lrc ? (cudaError_t)lrc : cudaDeviceSynchronize();
+        if (err == cudaSuccess) err = cudaMemcpy(solutions, d_x, n * (size_t)cols * 8, cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess) err = cudaMemcpy(flags, d_flags, n * 4, cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) rc = cuda_fail(err, "fks_debug_qr_solve");
+    }
+    cudaFree(d_work);
+    cudaFree(d_off);
+    cudaFree(d_rows);
+    cudaFree(d_x);
+    cudaFree(d_flags);
+    return rc;
+}
 
 // ---------------------------------------------------------------------------------------------
 // roofline micro-benchmarks

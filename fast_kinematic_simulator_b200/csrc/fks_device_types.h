@@ -100,10 +100,11 @@ inline __host__ __device__ unsigned long long normal_hash(unsigned long long cel
 // per-particle bookkeeping of a warp, kept in shared memory (uniform across lanes)
 struct WarpVars {
     unsigned long long pid, tape_pos, tape_end;
+    unsigned long long dec_pos, dec_end;  // decision tape (parity mode): next / one-past-last record of this particle
     double scaling;
     unsigned step, micro, number_microsteps, resolver_iterations, flags, n_micro_total, n_iter_total, n_steps;
     int collided, any_resolve_failed, step_collided, step_failed, step_stopped;
-    int pend_rows, pend_row0, _pad;  // a tall stacked system folded in the previous solver slot waits for its final solve (pend_rows > 0)
+    int _pad;
 };
 constexpr int kWarpVarsDoubles = (int)((sizeof(WarpVars) + 7) / 8);
 
@@ -111,18 +112,24 @@ constexpr int kWarpVarsDoubles = (int)((sizeof(WarpVars) + 7) / 8);
 // Three kinematic states X = 0, 1, 2: configuration cfg + X*S and link transforms T + X*L12.  States 0 / 1
 // ping-pong between "previous" and "current" configuration of a microstep, state 2 is the scratch state of
 // the motion estimates.  G / caps are derived from the CURRENT state only.
+// The stacked Jacobian of a contact solve lives in shared memory when it is small (jsm): the region aliases what is dead
+// between the collision check and the motion estimate of the correction -- the scratch state's transforms, the joint
+// matrices and the capsule end points (all rebuilt before they are read again) -- plus whatever shared memory the robot
+// leaves free (jsm_extra).  Taller systems use the warp's global scratch slot.
 struct WarpLayout {
     int S;        // vector slot (doubles) >= max(cfg_stride, D), even
     int L12;      // 12 * links
     int cfg;      // 3 * S
-    int T;        // 3 * L12
+    int T;        // 3 * L12; state 2 is the LAST one and starts the jsm region
     int G;        // L12: per link, (1/res) * inverse_origin * T_link  (world -> voxel coordinates in one transform)
     int caps;     // 6 * L: world end points of every link's bounding capsule
-    int M;        // 12 * J: joint_transform * motion(value)
+    int M;        // 16 * J: joint_transform * motion(value), by columns
+    int jsm;      // start of the shared-memory Jacobian store (= T + 2 * L12)
+    int jsm_ld;   // its leading dimension (odd: the column-per-lane solver reads one row of every column at a time)
     int jaxis, jorig;  // 3 * J each
     int target, scfg, act, ru, du, raw, stepv;  // S each
     int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
-    int qr;       // 4 * S doubles: bookkeeping of the generic QR (norms, Householder coefficients, transpositions)
+    int qr;       // S doubles: the actuated twist of the SE(3) robot (apply_control)
     int cand;     // 32 doubles = 32 candidate records of collect_corrections
     int vars;     // WarpVars (kWarpVarsDoubles) + 2 * S doubles of PID state
     int stats;    // FKS_NUM_STATS u64 counters of this warp
@@ -131,7 +138,7 @@ struct WarpLayout {
     int noise_batch;
 };
 
-inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int stride) {
+inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int stride, int jsm_extra = 0) {
     WarpLayout w;
     int S = stride > D ? stride : D;
     S = (S + 1) & ~1;
@@ -140,13 +147,21 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.noise_batch = 32 / D < 1 ? 1 : (32 / D > 8 ? 8 : 32 / D);
     int o = 0;
     w.cfg = o; o += 3 * S;
-    w.T = o; o += 3 * w.L12;
     // kinematics<LINKED> runs the T chain (lanes 0..11) and the G chain (lanes 12..23) in the same instructions: their row loads
-    // must not share banks, so G starts 2 doubles (mod 16 = one bank cycle) after a multiple of 16 from T
-    o += (2 + 16 - (o - w.T) % 16) % 16;
+    // must not share banks, so T starts 2 doubles (mod 16 = one bank cycle) after a multiple of 16 from G
     w.G = o; o += w.L12;
-    w.caps = o; o += 6 * L;
+    o += (2 + 16 - (o - w.G) % 16) % 16;
+    w.T = o; o += 3 * w.L12;
+    w.jsm = w.T + 2 * w.L12;
     w.M = o; o += 16 * J;  // joint matrices, TRANSPOSED and padded: element (row k, column c) of joint j at 16 j + 4 c + k
+    w.caps = o; o += 6 * L;
+    o += jsm_extra;
+    {
+        // (D + 1) columns of jsm_ld doubles; an odd leading dimension spreads a row of 8 columns over 16 distinct banks
+        int ld = (o - w.jsm) / (D + 1);
+        if ((ld & 1) == 0) ld -= 1;
+        w.jsm_ld = ld < 0 ? 0 : ld;
+    }
     w.jaxis = o; o += 3 * J;
     w.jorig = o; o += 3 * J;
     o = (o + 1) & ~1;
@@ -158,7 +173,7 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.raw = o; o += S;
     w.stepv = o; o += S;
     w.tn = o; o += w.noise_batch * S;
-    w.qr = o; o += 4 * S;  // generic solver: 3 D doubles + D ints; SE3: the actuated twist
+    w.qr = o; o += S;
     w.cand = o; o += 32;
     w.vars = o; o += kWarpVarsDoubles + 2 * S;
     w.stats = o; o += FKS_NUM_STATS;
@@ -217,6 +232,8 @@ struct LaunchArgs {
     const double* targets;
     const double* tape;
     const unsigned long long* tape_off;
+    const unsigned long long* dec_tape;  // decision tape (parity mode, fksgpu.h): records of 2 + D words, or null
+    const unsigned long long* dec_off;   // [n + 1] first record of each particle
     char* results;
     unsigned long long* stats;
     unsigned int* counter;
@@ -252,8 +269,10 @@ int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelI
 int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
                     const void* l2_window_base, size_t l2_window_bytes);
 // fills args.wl / pts_off / warps_off / warps_per_block and returns the dynamic shared memory size
-size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block);
+size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block, size_t smem_limit);
 int launch_check_config(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream, double inflation_ratio, unsigned char* out);
+int launch_qr_solve(double* work, const unsigned long long* offsets, const int* rows, int cols, int n, double* x_out, unsigned* flags_out,
+                    void* stream);
 int launch_fp64_peak(double* out, int grid, int iters, void* stream);
 int launch_gather(const float* data, unsigned long long n_mask, float* out, int grid, int iters, void* stream);
 

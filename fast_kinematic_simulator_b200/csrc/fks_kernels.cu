@@ -1037,7 +1037,8 @@ __device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur,
 
 // ------------------------------------------------------------------------------------------------
 // CollectPointCorrectionsAndJacobians (spcs:1818-1939): fills the stacked Jacobian (column major,
-// leading dimension ldj, column D holds the corrections), rows in link-major point-minor order.
+// column D holds the corrections), rows in link-major point-minor order, into *store (leading dimension
+// *store_ld): the warp's shared-memory store when the candidate count fits it, else its global scratch slot.
 // Returns the number of rows.
 //
 // Two passes.  Pass 1 is the cheap voxel test of check_env over all points, kBatch gathers in flight per
@@ -1047,7 +1048,7 @@ __device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur,
 // normal lookup, the Jacobian row -- on the survivors only.
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, bool has_self) {
+__device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, bool has_self, double** store, int* store_ld) {
     const Frame& fr = frame();
     const DevRobot& rb = fr.rb;
     const DevEnv& e = fr.a.env;
@@ -1061,14 +1062,13 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
     char* slot = scratch_slot();
-    double* A = reinterpret_cast<double*>(slot + fr.a.sl.jstore);
-    const int ld = fr.a.sl.ldj;
+    double* Ag = reinterpret_cast<double*>(slot + fr.a.sl.jstore);
     const unsigned char* sflag = reinterpret_cast<const unsigned char*>(slot + fr.a.sl.sflag);
     const double* selfcorr = reinterpret_cast<const double*>(slot + fr.a.sl.selfcorr);
     // candidate list: {point index | bit 31 = needs the environment estimate, raw cell value}; the first kCandShared
-    // live in shared memory, the rest behind the Jacobian columns
+    // live in shared memory, the rest behind the Jacobian columns of the global store
     uint2* cand_s = reinterpret_cast<uint2*>(ws + wl.cand);
-    uint2* cand_g = reinterpret_cast<uint2*>(A + (size_t)(D + 1) * ld);
+    uint2* cand_g = reinterpret_cast<uint2*>(Ag + (size_t)(D + 1) * fr.a.sl.ldj);
     double* jaxis = ws + wl.jaxis;
     double* jorig = ws + wl.jorig;
     if (KIND == FKS_ROBOT_LINKED) {
@@ -1124,6 +1124,12 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
         }
     }
     __syncwarp();
+    // the stacked system has at most 3 * ncand rows: small ones are built (and solved) in shared memory
+    const bool in_smem = 3 * ncand <= wl.jsm_ld;
+    double* A = in_smem ? ws + wl.jsm : Ag;
+    const int ld = in_smem ? wl.jsm_ld : fr.a.sl.ldj;
+    *store = A;
+    *store_ld = ld;
     // ---- pass 2 -----------------------------------------------------------------------------------
     int npts = 0;
     for (int base = 0; base < ncand; base += 32) {
@@ -1233,410 +1239,214 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
 }
 
 // ------------------------------------------------------------------------------------------------
-// ComputeResolverCorrectionStepStackedJacobian (spcs:1990-1998): x = J.colPivHouseholderQr().solve(c),
-// Eigen 3.3 semantics.  A is rows x cols column major (leading dimension ld) in the scratch
-// slot, b = column `cols` of the same store.  Lanes stride over rows.  Result in the shared vector at x_off.
+// ComputeResolverCorrectionStepStackedJacobian (spcs:1990-1998): x = J.colPivHouseholderQr().solve(c).
+//
+// Eigen 3.3's ColPivHouseholderQR::compute + solve restated OPERATION FOR OPERATION (the oracle's
+// colpiv_qr_solve is the same restatement): LAPACK-style downdated column norms, pivot = first largest updated norm, rank
+// cut |pivot|^2 < (eps max|col|)^2 / rows (rows - k), makeHouseholderInPlace from the tail's squared norm, reflectors
+// applied as  tmp = essential . bottom + top;  top -= tau tmp;  bottom -= (tau essential) tmp,  basic solution.
+//
+// Why verbatim, and why one lane per COLUMN.  With a single distal link of the arm in contact the stacked Jacobian has
+// rank <= 6 in 7 unknowns: the last pivot is pure round-off and Eigen cuts or keeps it by the last bit; when it is kept
+// the solve divides by it and the "correction" saturates every joint, which usually fails the resolve.  How OFTEN that
+// happens (6.7 % of such solves in the oracle) decides the failure rate of the whole workload, and it moves between 6 %
+// and 11 % with the summation order, the association of the reflector update or FMA contraction
+// (profiles/r2_qr_keep_rate.md).  So every sum here runs over the rows in row order and every product and sum rounds
+// once (__dmul_rn / __dadd_rn: the reference is x86-64 code without FMA): lane j < cols owns column j, lane `cols` the
+// right-hand side, and the row loops are sequential per lane.  On identical input this solver returns the oracle's bits.
+// It is also a loop nest of ~300 instructions (the register-resident warp-cooperative QR it replaces was 2 500 per copy,
+// instruction-cache bound) and needs no shuffle trees: an 8-row dot product is 8 dependent adds, not 2 x 9 exchanges.
+//
+// A = (cols + 1) columns of leading dimension ld (shared memory when the system is small, the warp's global scratch slot
+// otherwise: generic addressing), column `cols` = right-hand side.  Result in the shared vector at x_off.
+//
+// Parity mode (decision tape, fksgpu.h): the pivot order and the rank are taken from the tape, the solver's own are
+// still computed and a difference raises FKS_FLAG_DECISION_OVERRIDDEN; a record flagged OVERRIDE_SOLUTION replaces the
+// solve altogether.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ void colpiv_qr_solve(int wb, int rows, int cols, int x_off) {
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows, int cols, int x_off) {
     const Frame& fr = frame();
     const int lane = lane_id();
     double* ws = wsd(wb);
-    double* A = reinterpret_cast<double*>(scratch_slot() + fr.a.sl.jstore);
-    const int ld = fr.a.sl.ldj;
+    WarpVars* wv = reinterpret_cast<WarpVars*>(ws + fr.a.wl.vars);
     double* x = ws + x_off;
-    double* nu = ws + fr.a.wl.qr;  // norms updated
-    double* nd = nu + cols;        // norms direct
-    double* hc = nd + cols;        // householder coefficients
-    int* transp = (int*)(hc + cols);
-    double* b = A + (size_t)cols * ld;
-    const int size = rows < cols ? rows : cols;
-    double max_norm = 0.0;
-    for (int k = 0; k < cols; k++) {
-        const double* ck = A + (size_t)k * ld;
-        double s = 0.0;
-        for (int r = lane; r < rows; r += 32) s += ck[r] * ck[r];
-        const double n = sqrt(warp_sum(s));
+    const bool is_col = lane < cols;
+    const bool is_rhs = lane == cols;
+    double* mine = A + (size_t)(lane <= cols ? lane : 0) * ld;
+    // ---- decision tape (parity mode only) ----------------------------------------------------------------------
+    bool forced = false;
+    int f_rank = 0;
+    unsigned long long f_order = 0ull;
+    if (fr.a.dec_tape != nullptr) {
+        const unsigned long long dp = wv->dec_pos;
+        bool desync = true, replaced = false;
+        if (dp < wv->dec_end) {
+            const unsigned long long* rec = fr.a.dec_tape + dp * (unsigned long long)(2 + cols);
+            const unsigned long long w0 = rec[0];
+            if ((int)((w0 >> 16) & 0xFFFFFFFFull) == rows) {
+                desync = false;
+                forced = true;
+                f_rank = (int)(w0 & 0xFFull);
+                f_order = rec[1];
+                if (w0 & (unsigned long long)FKS_DECISION_OVERRIDE_SOLUTION) {
+                    replaced = true;
+                    if (is_col) x[lane] = __longlong_as_double((long long)rec[2 + lane]);
+                }
+            }
+        }
+        __syncwarp();
         if (lane == 0) {
-            nd[k] = n;
-            nu[k] = n;
+            wv->dec_pos = dp + 1ull;
+            if (desync) raise_flag(wb, FKS_FLAG_DECISION_DESYNC);
+            if (replaced) raise_flag(wb, FKS_FLAG_DECISION_OVERRIDDEN);
         }
-        max_norm = fmax(max_norm, n);
+        __syncwarp();
+        if (replaced) return;
     }
-    __syncwarp();
-    const double eps = DBL_EPSILON;
-    const double threshold_helper = ((max_norm * eps) * (max_norm * eps)) / (double)rows;
-    const double norm_downdate_threshold = sqrt(eps);
-    int nonzero_pivots = size;
+    const int size = rows < cols ? rows : cols;
+    // colNormsDirect / colNormsUpdated of this lane's column
+    double nu = 0.0, nd = 0.0;
+    if (is_col) {
+        double s = 0.0;
+#pragma unroll 4
+        for (int r = 0; r < rows; r++) {
+            const double a = mine[r];
+            s = add_rn(s, mul_rn(a, a));
+        }
+        nd = nu = sqrt(s);
+    }
+    const double max_norm = warp_max(is_col ? nu : 0.0);
+    const double me = mul_rn(max_norm, DBL_EPSILON);
+    const double threshold_helper = div_rn(mul_rn(me, me), (double)rows);
+    const double norm_downdate_threshold = 1.4901161193847656e-08;  // sqrt(epsilon)
+    int own_rank = size, nonzero_pivots = size;
+    int pos = lane;                   // position of this lane's column in Eigen's permuted order
+    unsigned long long order = 0ull;  // 4 bits per position: the lane (= original column) sitting there
+    bool differed = false, near_cut = false;
+#pragma unroll 1
     for (int k = 0; k < size; k++) {
-        int biggest = k;
-        double big = nu[k];
-        for (int j = k + 1; j < cols; j++) {
-            const double v = nu[j];
-            if (v > big) {
-                big = v;
-                biggest = j;
+        // biggest updated norm among the positions k .. cols-1, the first position wins (Eigen's maxCoeff scan)
+        const bool cand_ok = is_col && pos >= k;
+        double bv = cand_ok ? nu : -1.0;
+        int bp = cand_ok ? pos : 0x7fffffff, bl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FKS_FULL, bv, o);
+            const int op = __shfl_xor_sync(FKS_FULL, bp, o), ol = __shfl_xor_sync(FKS_FULL, bl, o);
+            if (ov > bv || (ov == bv && op < bp)) {
+                bv = ov;
+                bp = op;
+                bl = ol;
             }
         }
-        const double big_sq = big * big;
-        const double cut = threshold_helper * (double)(rows - k);
-        if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
-        if (lane == 0 && max_norm > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
-        __syncwarp();
-        double* ck = A + (size_t)k * ld;
-        if (k != biggest) {
-            double* cb = A + (size_t)biggest * ld;
-            for (int r = lane; r < rows; r += 32) {
-                const double t = ck[r];
-                ck[r] = cb[r];
-                cb[r] = t;
-            }
-            if (lane == 0) {
-                double t = nu[k]; nu[k] = nu[biggest]; nu[biggest] = t;
-                t = nd[k]; nd[k] = nd[biggest]; nd[biggest] = t;
+        int p = bl;
+        if (forced) {
+            const int fp = (int)((f_order >> (4 * k)) & 0xFull);
+            const int fpos = __shfl_sync(FKS_FULL, pos, fp);
+            if (fp < cols && fpos >= k) {
+                if (fp != p) differed = true;
+                p = fp;
+                bp = fpos;
+                bv = __shfl_sync(FKS_FULL, nu, fp);
+            } else {
+                differed = true;  // a record that does not fit this system: keep the solver's own pivot
             }
         }
-        if (lane == 0) transp[k] = biggest;
-        __syncwarp();
+        const double big_sq = mul_rn(bv, bv);
+        const double cut = mul_rn(threshold_helper, (double)(rows - k));
+        if (own_rank == size && big_sq < cut) own_rank = k;
+        if (max_norm > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
+        nonzero_pivots = forced ? (f_rank < size ? f_rank : size) : own_rank;
+        // the column that sat at position k takes the pivot's old position (m_qr.col(k).swap(m_qr.col(biggest)))
+        if (is_col && pos == k) pos = bp;
+        if (lane == p) pos = k;
+        order |= (unsigned long long)p << (4 * k);
+        double* piv = A + (size_t)p * ld;
         // makeHouseholderInPlace on col(k).tail(rows - k)
-        double ts = 0.0;
-        for (int r = k + 1 + lane; r < rows; r += 32) ts += ck[r] * ck[r];
-        const double tail_sq = warp_sum(ts);
-        const double c0 = ck[k];
+        double tail_sq = 0.0, c0 = 0.0;
+        if (lane == p) {
+#pragma unroll 4
+            for (int r = k + 1; r < rows; r++) {
+                const double a = piv[r];
+                tail_sq = add_rn(tail_sq, mul_rn(a, a));
+            }
+            c0 = piv[k];
+        }
+        tail_sq = __shfl_sync(FKS_FULL, tail_sq, p);
+        c0 = __shfl_sync(FKS_FULL, c0, p);
         double tau, beta;
-        __syncwarp();
         if (tail_sq <= DBL_MIN) {
             tau = 0.0;
             beta = c0;
-            for (int r = k + 1 + lane; r < rows; r += 32) ck[r] = 0.0;
+            for (int r = k + 1 + lane; r < rows; r += 32) piv[r] = 0.0;
         } else {
-            beta = sqrt(c0 * c0 + tail_sq);
+            beta = sqrt(add_rn(mul_rn(c0, c0), tail_sq));
             if (c0 >= 0.0) beta = -beta;
-            const double denom = c0 - beta;
-            for (int r = k + 1 + lane; r < rows; r += 32) ck[r] = ck[r] / denom;
-            tau = (beta - c0) / beta;
+            const double denom = sub_rn(c0, beta);
+            for (int r = k + 1 + lane; r < rows; r += 32) piv[r] = div_rn(piv[r], denom);  // element-wise: any lane may do it
+            tau = div_rn(sub_rn(beta, c0), beta);
         }
-        if (lane == 0) {
-            hc[k] = tau;
-            ck[k] = beta;
-        }
+        if (lane == p) piv[k] = beta;
         __syncwarp();
-        // applyHouseholderOnTheLeft to the trailing columns
-        if (rows - k == 1) {
-            if (lane == 0)
-                for (int j = k + 1; j < cols; j++) A[(size_t)j * ld + k] *= (1.0 - tau);
-        } else if (tau != 0.0) {
-            for (int j = k + 1; j < cols; j++) {
-                double* cj = A + (size_t)j * ld;
-                double t = 0.0;
-                for (int r = k + 1 + lane; r < rows; r += 32) t += ck[r] * cj[r];
-                const double tmp = warp_sum(t) + cj[k];
-                __syncwarp();
-                if (lane == 0) cj[k] -= tau * tmp;
-                for (int r = k + 1 + lane; r < rows; r += 32) cj[r] -= (tau * ck[r]) * tmp;
+        // applyHouseholderOnTheLeft to the remaining columns; to the right-hand side only below the rank cut (Eigen's solve
+        // applies the first nonzero_pivots reflectors to c)
+        if ((is_col && pos > k) || (is_rhs && nonzero_pivots > k)) {
+            if (rows - k == 1) {
+                mine[k] = mul_rn(mine[k], sub_rn(1.0, tau));
+            } else if (tau != 0.0) {
+                double tmp = 0.0;
+#pragma unroll 4
+                for (int r = k + 1; r < rows; r++) tmp = add_rn(tmp, mul_rn(piv[r], mine[r]));
+                tmp = add_rn(tmp, mine[k]);
+                mine[k] = sub_rn(mine[k], mul_rn(tau, tmp));
+#pragma unroll 4
+                for (int r = k + 1; r < rows; r++) mine[r] = sub_rn(mine[r], mul_rn(mul_rn(tau, piv[r]), tmp));
             }
-        }
-        __syncwarp();
-        // LAPACK-style norm downdate
-        for (int j = k + 1; j < cols; j++) {
-            const double nuj = nu[j];
-            if (nuj != 0.0) {
-                const double* cj = A + (size_t)j * ld;
-                double temp = fabs(cj[k]) / nuj;
-                temp = (1.0 + temp) * (1.0 - temp);
+            if (is_col && nu != 0.0) {  // LAPACK-style norm downdate
+                double temp = div_rn(fabs(mine[k]), nu);
+                temp = mul_rn(add_rn(1.0, temp), sub_rn(1.0, temp));
                 temp = temp < 0.0 ? 0.0 : temp;
-                const double ratio = nuj / nd[j];
-                const double temp2 = temp * (ratio * ratio);
-                double newu, newd = nd[j];
+                const double ratio = div_rn(nu, nd);
+                const double temp2 = mul_rn(temp, mul_rn(ratio, ratio));
                 if (temp2 <= norm_downdate_threshold) {
                     double s = 0.0;
-                    for (int r = k + 1 + lane; r < rows; r += 32) s += cj[r] * cj[r];
-                    newd = sqrt(warp_sum(s));
-                    newu = newd;
-                } else {
-                    newu = nuj * sqrt(temp);
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    nu[j] = newu;
-                    nd[j] = newd;
-                }
-            }
-        }
-        __syncwarp();
-    }
-    // c = H_{nz-1} ... H_0 b
-    for (int k = 0; k < nonzero_pivots; k++) {
-        const double tau = hc[k];
-        const double* ck = A + (size_t)k * ld;
-        if (rows - k == 1) {
-            if (lane == 0) b[k] *= (1.0 - tau);
-        } else if (tau != 0.0) {
-            double t = 0.0;
-            for (int r = k + 1 + lane; r < rows; r += 32) t += ck[r] * b[r];
-            const double tmp = warp_sum(t) + b[k];
-            __syncwarp();
-            if (lane == 0) b[k] -= tau * tmp;
-            for (int r = k + 1 + lane; r < rows; r += 32) b[r] -= (tau * ck[r]) * tmp;
-        }
-        __syncwarp();
-    }
-    if (lane < cols) x[lane] = 0.0;
-    __syncwarp();
-    if (lane == 0 && nonzero_pivots > 0) {
-        // back substitution on the leading nz x nz upper triangle, then un-permute (perm kept as 4-bit nibbles)
-        for (int i = nonzero_pivots - 1; i >= 0; i--) {
-            double s = b[i];
-            for (int j = i + 1; j < nonzero_pivots; j++) s -= A[(size_t)j * ld + i] * b[j];
-            b[i] = s / A[(size_t)i * ld + i];
-        }
-        unsigned long long perm = 0xFEDCBA9876543210ull;
-        for (int k = 0; k < size; k++) {
-            const int t = transp[k];
-            const unsigned long long pk = (perm >> (4 * k)) & 0xFull, pt = (perm >> (4 * t)) & 0xFull;
-            perm &= ~((0xFull << (4 * k)) | (0xFull << (4 * t)));
-            perm |= (pt << (4 * k)) | (pk << (4 * t));
-        }
-        for (int i = 0; i < nonzero_pivots; i++) x[(perm >> (4 * i)) & 0xFull] = b[i];
-    }
-    __syncwarp();
-}
-
-// ---- the solver of the reference's three robots (NC = 3 / 6 / 7 columns known at compile time) -----------------------------
-// Register-resident column-pivoted Householder QR, rows <= 32 R held R per lane (row lane + 32 s in slot s).  Rows beyond
-// `rows` are zero, which leaves every Householder quantity unchanged.  Per step: tree 1 sums the squares of every column
-// over the rows from the diagonal row on -- the residual column norms Eigen tracks by LAPACK-style downdating; the direct
-// sums are the exact quantities those approximate, so the pivot order only differs on ties the oracle reports as
-// SENS_PIVOT_TIE / SENS_RANK_CUT -- then the pivot, the reflector, and tree 2 = the reflector's dot products with all
-// columns and the right-hand side (reflectors are applied to the right-hand side as they are formed, only those below the
-// rank cut, as Eigen's solve does).
-// The step loop is a REAL loop over ONE copy of the step.  An earlier version unrolled it (column swaps as register
-// renames): ~9 000 instructions, 147 KB of straight-line code per (NC, R) pair, against a 32 KB instruction cache shared
-// by a dozen solver warps at different places -- ncu showed 61 % of its stall samples on instruction fetch.  What was
-// compile-time because of the step index is data here:
-//   * columns are never swapped: column j stays in registers a[.][j] and `pos` holds its position in Eigen's permuted
-//     order (candidates are the columns with pos >= k; ties go to the smallest position, as Eigen's scan over k .. NC-1 does);
-//   * the pivot column is read through a select chain on the run-time pivot index;
-//   * trees and updates run over all NC (+1) columns with the finished ones masked out.
-// Same speed on the arm workloads, 5-10 % faster on SE(3), a sixth of the code (profiles/r1_kernel_experiments.md).
-//
-// Tall systems (rows > 64) are first folded, 64 rows at a time, into an NC x (NC + 1) triangle by UNPIVOTED reflections
-// (template flag reduce_only: pivot = step index, triangle written back over the last NC rows of the chunk, returns the new first row):
-// [A | c] -> Q^T [A | c] = [R | d ; 0 | *].  An orthogonal transformation from the left changes neither the Gram matrix of
-// the columns nor the least-squares problem, so the column-pivoted QR of the folded system (triangle + remaining rows)
-// makes the same pivot choices, rank decision (rows_thr = the ORIGINAL row count enters Eigen's threshold) and solution as
-// the one of the full system up to round-off -- the same class of difference as the summation order of the trees.  This
-// replaced a four-slot register variant (spilled at 64 registers) and a memory-resident one for > 128 rows.
-// Sum of N (4 or 8) per-lane values over the warp by a HALVING butterfly: at each of the first log2(N) levels a lane keeps
-// one half of its values and sends the other half to its partner, so the level costs N/2, N/4, ... exchanges instead of N;
-// the remaining levels are plain butterflies on the single value left.  Lane l ends with the total of value fold_index(l);
-// fold_lane(j) is a lane that holds the total of value j.  9 exchanges for 8 values instead of 40.
-template <int N>
-__device__ __forceinline__ int fold_index(int lane) {
-    return N == 8 ? (((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1) : (((lane >> 4) & 1) << 1) | ((lane >> 3) & 1);
-}
-template <int N>
-__device__ __forceinline__ int fold_lane(int j) {
-    return N == 8 ? ((j & 4) << 2) | ((j & 2) << 2) | ((j & 1) << 2) : ((j & 2) << 3) | ((j & 1) << 3);
-}
-template <int N>
-__device__ __forceinline__ double warp_fold(const double (&v)[N], int lane) {
-    double w[N / 2];
-    {
-        const bool hi = (lane & 16) != 0;
-#pragma unroll
-        for (int j = 0; j < N / 2; j++) w[j] = (hi ? v[j + N / 2] : v[j]) + __shfl_xor_sync(FKS_FULL, hi ? v[j] : v[j + N / 2], 16);
-    }
-    double x[N / 4];
-    {
-        const bool hi = (lane & 8) != 0;
-#pragma unroll
-        for (int j = 0; j < N / 4; j++) x[j] = (hi ? w[j + N / 4] : w[j]) + __shfl_xor_sync(FKS_FULL, hi ? w[j] : w[j + N / 4], 8);
-    }
-    double y;
-    if (N == 8) {
-        const bool hi = (lane & 4) != 0;
-        y = (hi ? x[N / 4 - 1] : x[0]) + __shfl_xor_sync(FKS_FULL, hi ? x[0] : x[N / 4 - 1], 4);
-    } else {
-        y = x[0] + __shfl_xor_sync(FKS_FULL, x[0], 4);
-    }
-    y += __shfl_xor_sync(FKS_FULL, y, 2);
-    y += __shfl_xor_sync(FKS_FULL, y, 1);
-    return y;
-}
-
-template <int NC>
-__device__ __forceinline__ double select_col(int p, const double (&v)[NC + 1]) {
-    double r = v[0];
-#pragma unroll
-    for (int j = 1; j < NC; j++) r = (p == j) ? v[j] : r;
-    return r;
-}
-
-// R = row slots per lane (rows <= 32 R).  Register budget at 64 registers per thread: the matrix (2 R (NC + 1) registers),
-// ONE transient array of NC + 1 sums, and the positions packed four bits each in one register -- nothing spills.  To get
-// there the sums run over the rows FROM the diagonal row on (not below it): tree 1 gives the residual column norms
-// directly and beta = -sign(c0) sqrt(norm) for the pivot column;
-// tree 2 uses the full Householder vector (1 on the diagonal row), so it needs no separate broadcast of row k.
-template <int NC, int R, bool reduce_only>
-__device__ __noinline__ int qr_rolled(int wb, int rows, int x_off, int row0, int rows_thr) {
-    const Frame& fr = frame();
-    const int lane = lane_id();
-    double* ws = wsd(wb);
-    double* A = reinterpret_cast<double*>(scratch_slot() + fr.a.sl.jstore) + row0;
-    const int ld = fr.a.sl.ldj;
-    double a[R][NC + 1];  // slot s holds row lane + 32 s; column NC = right-hand side
-#pragma unroll
-    for (int sl = 0; sl < R; sl++)
-#pragma unroll
-        for (int c = 0; c <= NC; c++) a[sl][c] = (lane + 32 * sl < rows) ? A[(size_t)c * ld + lane + 32 * sl] : 0.0;
-    const int size = rows < NC ? rows : NC;
-    double threshold_helper = -1.0, rdiag_mine = 0.0;
-    int nonzero_pivots = size;
-    unsigned order = 0u;        // 4 bits per step: the column picked at step k
-    unsigned pos = 0x76543210u; // 4 bits per column: its position in the permuted order
-    unsigned colof = 0x76543210u; // 4 bits per position: the column sitting there (inverse of pos)
-    bool near_cut = false;
-    constexpr int NF = (NC + 1 <= 4) ? 4 : 8;  // width of the folded reductions
-#pragma unroll 1
-    for (int k = 0; k < size; k++) {
-        const bool from_diag = lane >= k;  // slot-0 rows not yet finished (rows above the diagonal row belong to R)
-        int p = k;
-        double nsq_p;
-        {
-            // ---- tree 1: squared residual norms (rows >= k) of every column, folded: this lane gets column fold_index --
-            double sq[NF];
-#pragma unroll
-            for (int j = 0; j < NF; j++) {
-                double v = 0.0;
-                if (j < NC) {
-                    v = from_diag ? a[0][j] * a[0][j] : 0.0;
-#pragma unroll
-                    for (int sl = 1; sl < R; sl++) v += a[sl][j] * a[sl][j];
-                }
-                sq[j] = v;
-            }
-            double y = warp_fold<NF>(sq, lane);
-            if (!reduce_only) {
-                // arg-max over the columns not yet chosen (position >= k), ties to the smallest position (Eigen's scan order):
-                // three more exchange levels between the lane groups that hold different columns
-                int col = fold_index<NF>(lane);
-                int pcol = col < NC ? (int)((pos >> (4 * col)) & 0xFu) : -1;
-                if (pcol < k) y = -1.0;
-#pragma unroll
-                for (int o = 16; o >= (NF == 8 ? 4 : 8); o >>= 1) {
-                    const double oy = __shfl_xor_sync(FKS_FULL, y, o);
-                    const int oc = __shfl_xor_sync(FKS_FULL, col, o), op = __shfl_xor_sync(FKS_FULL, pcol, o);
-                    if (oy > y || (oy == y && op < pcol)) {
-                        y = oy;
-                        col = oc;
-                        pcol = op;
+#pragma unroll 4
+                    for (int r = k + 1; r < rows; r++) {
+                        const double a = mine[r];
+                        s = add_rn(s, mul_rn(a, a));
                     }
-                }
-                p = col;
-                const double big_sq = y;
-                const int best_pos = pcol;
-                // Eigen: colNormsUpdated.maxCoeff() before the first step (tested on the value, not on k == 0, so that the
-                // compiler does not peel the first iteration off the loop: that doubled the code)
-                if (threshold_helper < 0.0) threshold_helper = (big_sq * (DBL_EPSILON * DBL_EPSILON)) / (double)rows_thr;
-                const double cut = threshold_helper * (double)(rows_thr - k);
-                if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
-                if (threshold_helper > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
-                // the column that sat at position k takes the pivot's old position, the pivot takes position k
-                const unsigned q = (colof >> (4 * k)) & 0xFu;
-                pos = (pos & ~(0xFu << (4 * q))) | ((unsigned)best_pos << (4 * q));
-                pos = (pos & ~(0xFu << (4 * p))) | ((unsigned)k << (4 * p));
-                colof = (colof & ~(0xFu << (4 * best_pos))) | (q << (4 * best_pos));
-                colof = (colof & ~(0xFu << (4 * k))) | ((unsigned)p << (4 * k));
-                nsq_p = big_sq;
-            } else {
-                nsq_p = __shfl_sync(FKS_FULL, y, fold_lane<NF>(k));
-            }
-        }
-        order |= (unsigned)p << (4 * k);
-        // ---- makeHouseholderInPlace on the pivot column ----------------------------------------------------------
-        double v[R];
-#pragma unroll
-        for (int sl = 0; sl < R; sl++) v[sl] = select_col<NC>(p, a[sl]);
-        const double c0 = __shfl_sync(FKS_FULL, v[0], k);
-        // Eigen skips the reflection when the tail's squared norm is <= DBL_MIN.  nsq_p - c0^2 would lose a tail below
-        // ~1e-8 |c0| to cancellation, so the test is made on the entries themselves.
-        bool tail_entry = lane > k && v[0] != 0.0;
-#pragma unroll
-        for (int sl = 1; sl < R; sl++) tail_entry = tail_entry || v[sl] != 0.0;
-        double tau = 0.0, beta = c0;
-        const bool has_tail = __any_sync(FKS_FULL, tail_entry);
-        if (has_tail) {
-            beta = sqrt(nsq_p);
-            if (c0 >= 0.0) beta = -beta;
-            const double inv_denom = 1.0 / (c0 - beta);
-            v[0] = (lane > k) ? v[0] * inv_denom : 0.0;
-#pragma unroll
-            for (int sl = 1; sl < R; sl++) v[sl] *= inv_denom;
-        }
-        const double inv_beta = 1.0 / beta;  // 1 / R(k,k); tau = (beta - c0) / beta through the same reciprocal
-        if (has_tail) tau = (beta - c0) * inv_beta;
-        if (lane == k) {
-            v[0] = 1.0;
-            rdiag_mine = inv_beta;
-            if (reduce_only) {  // R(k,k) itself is only read by the fold's write-back (the solve uses its reciprocal)
-#pragma unroll
-                for (int j = 0; j < NC; j++) a[0][j] = (j == p) ? beta : a[0][j];
-            }
-        }
-        const bool apply_b = reduce_only || nonzero_pivots > k;  // Eigen's solve applies the first nonzero_pivots reflectors to c
-        // ---- applyHouseholderOnTheLeft to the remaining columns and the right-hand side ----------------------------
-        // (a single remaining row, rows - k == 1, is the same formula with an empty tail: a -= tau * a)
-        if (tau != 0.0) {
-            double dt[NF];
-#pragma unroll
-            for (int j = 0; j < NF; j++) {
-                double t = 0.0;
-                if (j <= NC) {
-                    t = (lane >= k) ? v[0] * a[0][j] : 0.0;
-#pragma unroll
-                    for (int sl = 1; sl < R; sl++) t += v[sl] * a[sl][j];
-                }
-                dt[j] = t;
-            }
-            const double folded = warp_fold<NF>(dt, lane);
-#pragma unroll
-            for (int j = 0; j <= NC; j++) {
-                const bool active = (j == NC) ? apply_b : ((int)((pos >> (4 * (j < NC ? j : 0))) & 0xFu) > k);
-                const double dtj = __shfl_sync(FKS_FULL, folded, fold_lane<NF>(j));
-                if (active) {
-                    const double tmp = tau * dtj;
-                    if (lane >= k) a[0][j] -= v[0] * tmp;
-#pragma unroll
-                    for (int sl = 1; sl < R; sl++) a[sl][j] -= v[sl] * tmp;
+                    nd = sqrt(s);
+                    nu = nd;
+                } else {
+                    nu = mul_rn(nu, sqrt(temp));
                 }
             }
-        }
-    }
-    if (reduce_only) {  // R == 2, a full chunk of 64 rows
-        __syncwarp();   // every lane has read its rows before the last NC of them are overwritten
-        if (lane < NC) {
-#pragma unroll
-            for (int c = 0; c <= NC; c++) A[(size_t)c * ld + (64 - NC) + lane] = (c < lane) ? 0.0 : a[0][c];
         }
         __syncwarp();
-        return row0 + 64 - NC;
     }
-    if (near_cut && lane == 0) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
-    // back substitution on the leading nz x nz triangle (lane i owns row i), unknowns written in column order
-    if (lane < NC) ws[x_off + lane] = 0.0;
+    if (lane == 0) {
+        if (near_cut) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
+        if (forced && (differed || own_rank != nonzero_pivots)) raise_flag(wb, FKS_FLAG_DECISION_OVERRIDDEN);
+    }
+    // solve: back substitution on the leading nonzero_pivots x nonzero_pivots triangle, the other unknowns zero
+    if (is_col) x[lane] = 0.0;
     __syncwarp();
-    double sres = a[0][NC];
-#pragma unroll 1
-    for (int i = nonzero_pivots - 1; i >= 0; i--) {
-        const int pc = (int)((order >> (4 * i)) & 0xFu);
-        const double yi = __shfl_sync(FKS_FULL, sres * rdiag_mine, i);
-        sres -= select_col<NC>(pc, a[0]) * yi;
-        if (lane == 0) ws[x_off + pc] = yi;
+    if (is_rhs && nonzero_pivots > 0) {
+        for (int i = nonzero_pivots - 1; i >= 0; i--) {
+            double s = mine[i];
+            for (int j = i + 1; j < nonzero_pivots; j++)
+                s = sub_rn(s, mul_rn(A[(size_t)((order >> (4 * j)) & 0xFull) * ld + i], mine[j]));
+            mine[i] = div_rn(s, A[(size_t)((order >> (4 * i)) & 0xFull) * ld + i]);
+        }
+        for (int i = 0; i < nonzero_pivots; i++) x[(order >> (4 * i)) & 0xFull] = mine[i];
     }
     __syncwarp();
-    return 0;
 }
-
 
 // actuator noise of the next `count` microsteps, one truncated-normal draw per axis in axis order
 __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned step, unsigned micro0, int count,
@@ -1801,7 +1611,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
     int free_rounds = 0, free_streak = 0;  // rounds the next super-cycle runs before its first CTA barrier (free flight only)
     for (;;) {
         int bar_id = 0, bar_threads = 32 * n_warps, n_solvers = 0;
-        bool counted_solver = false, any_tall = false;
+        bool counted_solver = false;
         int slot_iter = 0;
         constexpr int kSlotIters = FKS_SLOT_ITERATIONS(KIND);
         for (int round = 0;; round++) {
@@ -1865,7 +1675,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             wv->tape_pos = a.tape_off[wv->pid];
                             wv->tape_end = a.tape_off[wv->pid + 1];
                         }
-                        wv->pend_rows = 0;
+                        wv->dec_pos = wv->dec_end = 0ull;
+                        if (a.dec_tape != nullptr) {
+                            wv->dec_pos = a.dec_off[wv->pid];
+                            wv->dec_end = a.dec_off[wv->pid + 1];
+                        }
                         wv->collided = wv->any_resolve_failed = false;
                         wv->flags = wv->n_micro_total = wv->n_iter_total = wv->n_steps = 0u;
                         wv->step = 0u;
@@ -2186,63 +2000,35 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #ifdef FKS_PHASE_TIMERS
             const long long tc0 = clock64();
 #endif
-            // A tall system (more than 64 rows) takes two solver slots: this one collects and folds it to <= 64 rows, the
-            // next one solves it.  The slowest solver warp gates the CTA, and with a dozen solvers per slot one of them is
-            // tall in 3 slots of 4 -- a fold pass AND a solve pass in the same slot made every slot as long as the tall ones.
-            int row0 = 0;
-            const bool resumed = wv->pend_rows > 0;
-            if (resumed) {
-                rows = wv->pend_rows;
-                row0 = wv->pend_row0;
-            } else {
-                rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
-                if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
-            }
+            double* jstore = nullptr;
+            int jld = 0;
+            rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u, &jstore, &jld);
+            if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
 #ifdef FKS_PHASE_TIMERS
             tacc[10] += clock64() - tc0;
             tacc[11] += 1;
 #endif
             FKS_TICK(6)
-            // the solvers of this super-cycle agree on ONE copy of the QR code: the two-slot copy if any of them has more than
-            // 32 rows, else the one-slot copy -- two copies live at once cost more in instruction fetch than the second row
-            // slot costs the small systems (A/B in profiles/r1_kernel_experiments.md)
-            // (only the first iteration of a slot is common to all of its solvers; later ones keep the choice unless they
-            // turn out tall themselves)
-            if (slot_iter == 0) any_tall = named_barrier_or(2, 32 * n_solvers, rows - row0 > 32);
-            else any_tall = any_tall || (rows - row0 > 32);
             FKS_TICK(7)
             // ======================= phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
 #ifdef FKS_PHASE_TIMERS
             const long long tq0 = clock64();
 #endif
-            bool deferred = false;
             if (rows == 0) {
                 // Eigen would return an empty vector and ApplyControlInput would assert; documented device
                 // behaviour: zero correction wv->step
                 wv->flags |= FKS_FLAG_EMPTY_JACOBIAN;
                 if (lane < D) ws[wl.raw + lane] = 0.0;
                 __syncwarp();
-            } else if (KIND == FKS_ROBOT_LINKED && D != 7) {
-                colpiv_qr_solve(wb, rows, D, wl.raw);
             } else {
-                constexpr int NCK = KIND == FKS_ROBOT_SE2 ? 3 : (KIND == FKS_ROBOT_SE3 ? 6 : 7);
-                if (rows - row0 > 64) {  // tall and not folded yet: fold now, solve in the next slot
-                    while (rows - row0 > 64) row0 = qr_rolled<NCK, 2, true>(wb, 64, 0, row0, 0);
-                    wv->pend_rows = rows;  // every lane stores the same value
-                    wv->pend_row0 = row0;
-                    deferred = true;
-                } else {
-                    if (!any_tall) qr_rolled<NCK, 1, false>(wb, rows - row0, wl.raw, row0, rows);
-                    else qr_rolled<NCK, 2, false>(wb, rows - row0, wl.raw, row0, rows);
-                    wv->pend_rows = 0;
-                }
+                colpiv_qr_lanes(wb, jstore, jld, rows, D, wl.raw);
             }
 #ifdef FKS_PHASE_TIMERS
             if (rows <= 64) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
 #endif
             // motion estimate of the raw correction (spcs:1630) in the same solver slot: one lock-step round per
             // resolver iteration instead of two
-            if (!deferred) {
+            {
 #ifdef FKS_PHASE_TIMERS
             const long long te0 = clock64();
 #endif
@@ -2260,9 +2046,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             measure = M_CHECK;
             after = AF_RESOLVE_CHECK;
             want_solve = false;
-            }  // a deferred warp keeps want_solve: it is a solver of the next slot again and skips the rounds until then
+            }
             slot_iter++;
-            if (deferred || kSlotIters == 0) break;  // folded: the solve comes in the next super-cycle's slot
+            if (kSlotIters == 0) break;
         }
         }  // rounds
         if (counted_solver) {
@@ -2422,6 +2208,40 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) check_config
 }
 
 // ------------------------------------------------------------------------------------------------
+// Test entry (fks_debug_qr_solve): the contact solver of the simulate kernel on caller-provided stacked systems, one
+// warp per system.  `work` holds, per system, (cols + 1) columns of rows[i] doubles (column major, the right-hand side
+// last) starting at offsets[i]; they are factored in place.  The solutions go to x_out (cols doubles per system), the
+// FKS_FLAG_* bits the solver raised to flags_out.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) qr_solve_kernel(double* work, const unsigned long long* offsets, const int* rows, int cols, int n,
+                                                       double* x_out, unsigned* flags_out) {
+    Frame* f = reinterpret_cast<Frame*>(smem_raw);
+    {
+        unsigned* dst = reinterpret_cast<unsigned*>(f);
+        for (int i = threadIdx.x; i < (int)(sizeof(Frame) / 4); i += blockDim.x) dst[i] = 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        f->a.wl = make_warp_layout(1, 0, cols, cols);
+        f->a.warps_off = (int)((sizeof(Frame) + 15) & ~(size_t)15);
+    }
+    __syncthreads();
+    const Frame& fr = frame();
+    const int lane = lane_id();
+    const int wb = fr.a.warps_off + (threadIdx.x >> 5) * fr.a.wl.total * 8;
+    double* ws = wsd(wb);
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps_total) {
+        if (lane == 0) *reinterpret_cast<unsigned*>(ws + fr.a.wl.flags) = 0u;
+        __syncwarp();
+        colpiv_qr_lanes(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw);
+        if (lane < cols) x_out[(size_t)i * cols + lane] = ws[fr.a.wl.raw + lane];
+        if (lane == 0) flags_out[i] = *reinterpret_cast<const unsigned*>(ws + fr.a.wl.flags);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // roofline micro-benchmarks: FP64 FMA throughput and random 4-byte gather rate
 // ------------------------------------------------------------------------------------------------
 __global__ void fp64_peak_kernel(double* out, int iters) {
@@ -2454,16 +2274,29 @@ __global__ void gather_kernel(const float* __restrict__ data, unsigned long long
 // ------------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------------
-size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block) {
-    args->wl = make_warp_layout(L, J, D, stride);
+size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block, size_t smem_limit) {
     args->sl = make_scratch_layout(D, P);
     args->P = P;
     args->warps_per_block = warps_per_block;
-    size_t off = (sizeof(Frame) + 15) & ~(size_t)15;
-    args->pts_off = (int)off;
-    off += (size_t)P * (sizeof(double2) + sizeof(PointZL));
-    args->warps_off = (int)off;
-    off += (size_t)warps_per_block * args->wl.total * 8;
+    const size_t pts_off = (sizeof(Frame) + 15) & ~(size_t)15;
+    const size_t warps_off = pts_off + (size_t)P * (sizeof(double2) + sizeof(PointZL));
+    // shared-memory Jacobian store: whatever the CTA leaves free goes to it, up to every point of the robot (3 P rows)
+    const WarpLayout w0 = make_warp_layout(L, J, D, stride, 0);
+    const size_t base = warps_off + (size_t)warps_per_block * w0.total * 8 + 16;
+    int extra = 0;
+    if (smem_limit > base) {
+        const long long spare = (long long)((smem_limit - base) / (size_t)warps_per_block / 8);
+        int want_ld = 3 * P < 255 ? 3 * P : 255;
+        want_ld |= 1;
+        const long long want = (long long)(D + 1) * want_ld - (long long)(12 * L + 16 * J + 6 * L);
+        long long e = want < spare ? want : spare;
+        if (e < 0) e = 0;
+        extra = (int)(e & ~1ll);
+    }
+    args->wl = make_warp_layout(L, J, D, stride, extra);
+    args->pts_off = (int)pts_off;
+    args->warps_off = (int)warps_off;
+    size_t off = warps_off + (size_t)warps_per_block * args->wl.total * 8;
     args->sync_off = (int)off;  // one 16-byte word of CTA-level synchronisation state
     off += 16;
     return off;
@@ -2502,7 +2335,9 @@ int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem,
     const int block_threads = 32 * args.warps_per_block;
     const void* fn = kernel_ptr(kind, args.trace != nullptr);
     if (!fn) return (int)cudaErrorInvalidValue;
-    if (args.trace != nullptr) {  // the tracing instantiation is launched rarely: set its shared-memory limit on the spot
+    {
+        // the attribute is per function and per device, and simulators of the same robot kind share the function: set it for
+        // THIS launch (a second simulator with a smaller robot must not lower the limit under a live one)
         const cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
         if (err != cudaSuccess) return (int)err;
     }
@@ -2547,6 +2382,18 @@ int launch_check_config(int kind, const LaunchArgs& args, int grid, size_t dyn_s
         default:
             return (int)cudaErrorInvalidValue;
     }
+    return (int)cudaGetLastError();
+}
+
+int launch_qr_solve(double* work, const unsigned long long* offsets, const int* rows, int cols, int n, double* x_out, unsigned* flags_out,
+                    void* stream) {
+    const int warps = 4;
+    const WarpLayout wl = make_warp_layout(1, 0, cols, cols);
+    const size_t smem = ((sizeof(Frame) + 15) & ~(size_t)15) + (size_t)warps * wl.total * 8;
+    cudaError_t err = cudaFuncSetAttribute(qr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const int grid = (n + warps - 1) / warps < 4096 ? (n + warps - 1) / warps : 4096;
+    qr_solve_kernel<<<grid, 32 * warps, smem, (cudaStream_t)stream>>>(work, offsets, rows, cols, n, x_out, flags_out);
     return (int)cudaGetLastError();
 }
 

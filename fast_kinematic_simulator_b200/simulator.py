@@ -263,13 +263,25 @@ class SimulationResults:
         return len(self.records)
 
 
-def make_tape(draws, offsets):
+def make_tape(draws, offsets, decisions=None, decision_offsets=None):
+    """fks_noise_tape: the injected truncated-normal draws and, optionally, the decision tape (include/fksgpu.h)."""
     draws = _as_f64(draws)
+    if not draws.size:
+        draws = np.zeros(1)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     t = capi.NoiseTape()
-    t.draws = _dptr(draws if draws.size else np.zeros(1))
+    t.draws = _dptr(draws)
     t.offsets = offsets.ctypes.data_as(C.POINTER(C.c_uint64))
-    return t, (draws, offsets)
+    keep = [draws, offsets]
+    if decisions is not None:
+        decisions = np.ascontiguousarray(decisions, dtype=np.uint64)
+        if not decisions.size:
+            decisions = np.zeros(1, dtype=np.uint64)
+        decision_offsets = np.ascontiguousarray(decision_offsets, dtype=np.uint64)
+        t.decisions = decisions.ctypes.data_as(C.POINTER(C.c_uint64))
+        t.decision_offsets = decision_offsets.ctypes.data_as(C.POINTER(C.c_uint64))
+        keep += [decisions, decision_offsets]
+    return t, keep
 
 
 class GpuParticleContactSimulator:
@@ -405,3 +417,24 @@ def make_linked_simulator(built_env, robot_description, solver_params=None, simu
                           debug_level=0, device=0):
     """MakeLinkedSimulator (fast_kinematic_simulator.cpp:50-71)."""
     return _make(capi.ROBOT_LINKED, built_env, robot_description, solver_params, simulation_controller_frequency, prng_seed, debug_level, device)
+
+
+def debug_qr_solve(systems, device=0):
+    """fks_debug_qr_solve: the device's stacked-Jacobian solver on a list of (A rows x cols, b) systems sharing `cols`.
+    Returns (solutions n x cols, flags n)."""
+    n = len(systems)
+    cols = int(systems[0][0].shape[1])
+    rows = np.array([A.shape[0] for A, _ in systems], dtype=np.int32)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(rows.astype(np.uint64) * np.uint64(cols + 1))
+    flat = np.empty(int(offsets[-1]), dtype=np.float64)
+    for i, (A, b) in enumerate(systems):
+        o = int(offsets[i])
+        r = int(rows[i])
+        flat[o:o + r * cols] = np.asarray(A, dtype=np.float64).T.reshape(-1)  # column major
+        flat[o + r * cols:o + r * (cols + 1)] = b
+    x = np.zeros((n, cols))
+    flags = np.zeros(n, dtype=np.uint32)
+    check(lib.fks_debug_qr_solve(int(device), flat.ctypes.data, offsets.ctypes.data, rows.ctypes.data, cols, n, x.ctypes.data,
+                                 flags.ctypes.data))
+    return x, flags

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FKS_ABI_VERSION 1
+#define FKS_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------ */
 enum {
@@ -74,7 +74,12 @@ enum {
     FKS_FLAG_TAPE_EXHAUSTED         = 1u << 12, /* injected tape shorter than the draws consumed         */
     FKS_FLAG_NEAR_RANK_CUT          = 1u << 13, /* a QR pivot came within 1e3x of Eigen's rank threshold
                                                    (result is round-off determined in the reference)    */
-    FKS_FLAG_J_SPILLED              = 1u << 14  /* stacked Jacobian exceeded the shared-memory tile     */
+    FKS_FLAG_J_SPILLED              = 1u << 14, /* stacked Jacobian exceeded the shared-memory tile     */
+    /* parity mode with a decision tape (fks_noise_tape.decisions) only: */
+    FKS_FLAG_DECISION_OVERRIDDEN    = 1u << 15, /* the device's own pivot order / rank differed from the
+                                                   injected one, or a round-off solution was injected   */
+    FKS_FLAG_DECISION_DESYNC        = 1u << 16  /* the tape ran out or its row count did not match the
+                                                   device's stacked system: trajectories have diverged  */
 };
 
 /* spcs.hpp:345-369 (same field order, defaults :357-368) */
@@ -152,10 +157,29 @@ typedef struct fks_robot_desc {
 } fks_robot_desc;
 
 /* Injected noise: the truncated-normal outputs of noise_distribution_(rng) (unc.hpp:86) in the
- * order the reference draws them, [particle][step][microstep][dof]. */
+ * order the reference draws them, [particle][step][microstep][dof].
+ *
+ * Optional DECISION TAPE (parity instrumentation, NULL in production): the discrete outcomes of every
+ * J.colPivHouseholderQr().solve(c) (spcs.hpp:1990-1998) the reference side took for a particle, in call order.
+ * Eigen's rank decision compares a pivot with ~epsilon * the largest column norm; when the stacked Jacobian is
+ * structurally rank deficient (a single distal link of a 7-dof arm touching: rank <= 6 in 7 unknowns) the last
+ * pivot IS round-off and the reference cuts or keeps it by the last bit.  No other arithmetic reproduces that bit,
+ * so in parity mode the device takes the decision from the tape (and reports where its own differed) and everything
+ * downstream of it stays comparable.  One record per solve, 2 + n_dof 64-bit words:
+ *   word 0: bits 0..7 nonzero_pivots, bits 8..15 FKS_DECISION_* flags, bits 16..47 rows of the stacked system
+ *   word 1: pivot order, 4 bits per step: the column picked at step k
+ *   words 2..: the reference's solution (bit pattern of n_dof doubles); consumed only with
+ *              FKS_DECISION_OVERRIDE_SOLUTION (a round-off pivot was KEPT: the solution itself is round-off) */
+enum {
+    FKS_DECISION_OVERRIDE_SOLUTION = 1u << 8,
+    FKS_DECISION_ROUNDOFF_PIVOT    = 1u << 9,  /* informational: a pivot at round-off level was met */
+    FKS_DECISION_PIVOT_TIE         = 1u << 10  /* informational: two pivot candidates within 1e-9 relative */
+};
 typedef struct fks_noise_tape {
     const double* draws;       /* flat */
     const uint64_t* offsets;   /* [n_particles+1] start of each particle's draws */
+    const uint64_t* decisions;        /* flat records of 2 + n_dof words, or NULL */
+    const uint64_t* decision_offsets; /* [n_particles+1] first RECORD of each particle, or NULL */
 } fks_noise_tape;
 
 /* Tail of every result record; record = cfg_stride doubles followed by this struct. */
@@ -326,6 +350,16 @@ int fks_env_build_device(int device, const fks_obstacle* obstacles, size_t n_obs
                          fks_env** out);
 int fks_env_build_timings(const fks_env* env, double* out_ms, int n);
 int fks_env_download(const fks_env* env, fks_built_env** out);
+
+/* -------------------------------------------------------------------------------------------
+ * Test entry: the device's stacked-Jacobian solver (ComputeResolverCorrectionStepStackedJacobian, spcs.hpp:1990-1998 =
+ * J.colPivHouseholderQr().solve(c)) on caller-provided systems, one warp each.  System i has rows[i] rows and `cols`
+ * unknowns and is stored at systems + offsets[i] as cols + 1 columns of rows[i] doubles (column major, right-hand side
+ * last); offsets has n + 1 entries.  solutions: n * cols doubles; flags: the FKS_FLAG_* bits the solver raised.
+ * The solver follows Eigen operation for operation, so on the same system it returns the bits of the CPU oracle.
+ * ----------------------------------------------------------------------------------------- */
+int fks_debug_qr_solve(int device, const double* systems, const uint64_t* offsets, const int32_t* rows, int32_t cols, size_t n,
+                       double* solutions, uint32_t* flags);
 
 /* -------------------------------------------------------------------------------------------
  * Device micro-benchmarks used for the roofline denominators: dependent-free DFMA

@@ -42,6 +42,11 @@
 #include <omp.h>
 #endif
 
+// CPU model of the DEVICE solver (fks_qr_model.cpp), used only when a study asks for it (oracle_set_qr_model)
+extern "C" void oracle_qr_device_model(const double* A_colmajor, const double* b, int rows, int cols, int opt_bits, double* x, double* out4);
+extern "C" void oracle_qr_device_model_forced(const double* A_colmajor, const double* b, int rows, int cols, int opt_bits, uint64_t order,
+                                              int rank, double* x);
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -58,8 +63,13 @@ enum {
     SENS_ANGLE_WRAP = 1u << 7,     // an angle within tol of +-pi at a wrap
     SENS_SELF_COLLISION = 1u << 8, // a self-collision candidate cell was evaluated
     SENS_RAW_THRESHOLD = 1u << 9,  // (unused: raw float compares only change with the cell)
-    SENS_STEP_FRACTION = 1u << 10  // m/res within tol of 1 (max() kink, spcs:1681)
+    SENS_STEP_FRACTION = 1u << 10, // m/res within tol of 1 (max() kink, spcs:1681)
+    SENS_ILL_CONDITIONED = 1u << 11 // a stacked system with condition estimate > kIllConditioned was solved (and not replaced through
+                                    // the decision tape): the step is reproducible to cond x epsilon only, and later solves amplify
+                                    // the difference.  Measured (tests/test_oracle_decision_tape.py): with another solver arithmetic
+                                    // every particle whose largest estimate stays below 1e3 reproduces to 1e-9, the others mostly do
 };
+constexpr double kIllConditioned = 1e3;
 
 const double kPi = 3.14159265358979323846;
 
@@ -667,8 +677,25 @@ struct Robot {
 // debug histogram of log10(pivot_norm^2 / rank_cut) for pivots near the rank decision (oracle_debug_rank_hist)
 long long g_rank_hist[42];
 long long g_rows_hist[16];  // debug: histogram of stacked-Jacobian row counts, bucket = min(15, rows / 24)
-void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32_t* sens) {
+
+// The discrete decisions of one solve (recorded on the DECISION TAPE next to the noise tape): Eigen's nonzero_pivots and
+// the pivot order.  `roundoff_seen`: some pivot was at round-off level (0 < |pivot|^2 < 1e8 x Eigen's rank threshold; the
+// histogram of |pivot|^2 / threshold is bimodal -- <= 10 or >= 1e17 on every workload here -- so 1e8 separates the modes);
+// `roundoff_kept`: such a pivot was NOT cut, i.e. the solution divides by round-off and no other arithmetic (x86 with a
+// different summation order, a GPU) reproduces it.
+struct QrInfo {
+    int rank, size;
+    uint64_t order;  // nibble k: ORIGINAL index of the column picked at step k
+    bool roundoff_seen, roundoff_kept, tie;
+    double cond_est;  // |R(0,0)| / min |R(k,k)| over the kept pivots: the usual estimate of the pivoted triangle's condition
+};
+constexpr double kRoundoffPivotBand = 1e8;
+
+void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32_t* sens, QrInfo* info = nullptr) {
     const int size = std::min(rows, cols);
+    int colidx[kMaxDof];
+    for (int j = 0; j < cols; j++) colidx[j] = j;
+    QrInfo qi = {size, size, 0ull, false, false, false, 1.0};
     double hcoeff[kMaxDof];
     int transp[kMaxDof];
     double norms_updated[kMaxDof], norms_direct[kMaxDof];
@@ -693,15 +720,20 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
                 big = norms_updated[j];
                 biggest = j;
             }
-        if (sens) {
-            for (int j = k; j < cols; j++)
-                if (j != biggest && norms_updated[j] != big && std::abs(norms_updated[j] - big) <= 1e-9 * big)
-                    *sens |= SENS_PIVOT_TIE;
-        }
+        for (int j = k; j < cols; j++)
+            if (j != biggest && norms_updated[j] != big && std::abs(norms_updated[j] - big) <= 1e-9 * big) {
+                if (sens) *sens |= SENS_PIVOT_TIE;
+                qi.tie = true;
+            }
         const double big_sq = big * big;
         const double cut = threshold_helper * (double)(rows - k);
         if (nonzero_pivots == size && big_sq < cut) nonzero_pivots = k;
-        if (sens && max_norm > 0.0 && big_sq < cut * 1e8 && big_sq > 0.0) *sens |= SENS_RANK_CUT;
+        if (max_norm > 0.0 && big_sq < cut * kRoundoffPivotBand && big_sq > 0.0) {
+            if (sens) *sens |= SENS_RANK_CUT;
+            qi.roundoff_seen = true;
+            if (nonzero_pivots == size) qi.roundoff_kept = true;
+        }
+        qi.order |= (uint64_t)colidx[biggest] << (4 * k);
         if (sens && max_norm > 0.0) {
             int bucket = 41;  // exact zero
             if (big_sq > 0.0) {
@@ -721,6 +753,7 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
             }
         }
         transp[k] = biggest;
+        std::swap(colidx[k], colidx[biggest]);
         if (k != biggest) {
             for (int r = 0; r < rows; r++) std::swap(col(k)[r], col(biggest)[r]);
             std::swap(norms_updated[k], norms_updated[biggest]);
@@ -781,6 +814,12 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
     for (int j = 0; j < cols; j++) perm[j] = j;
     for (int k = 0; k < size; k++) std::swap(perm[k], perm[transp[k]]);
     for (int j = 0; j < cols; j++) x[j] = 0.0;
+    qi.rank = nonzero_pivots;
+    for (int k = 1; k < nonzero_pivots; k++) {
+        const double dk = std::abs(col(k)[k]);
+        qi.cond_est = std::max(qi.cond_est, dk > 0.0 ? std::abs(col(0)[0]) / dk : INFINITY);
+    }
+    if (info) *info = qi;
     if (nonzero_pivots == 0) return;
     // c = H_{nz-1} ... H_0 b
     for (int k = 0; k < nonzero_pivots; k++) {
@@ -881,6 +920,10 @@ struct NoiseSource {
     uint64_t seed, particle_id;
     // recording
     std::vector<double>* record;
+    std::vector<uint64_t>* record_decisions = nullptr;  // decision tape (fks_noise_tape.decisions), see QrInfo
+    double* max_condition = nullptr;                    // largest QrInfo::cond_est among this particle's solves
+    const uint64_t* dec_tape = nullptr;                 // replayed decision tape (studies with the device-solver model)
+    uint64_t dec_pos = 0, dec_end = 0;
 
     void begin_step(const Robot& robot) {
         // each controller step works on a fresh Clone() of the robot (spcs:1548), whose actuator
@@ -905,6 +948,28 @@ struct NoiseSource {
         }
     }
 };
+
+// debug capture of the stacked systems the resolver solves (oracle_debug_capture_systems): rows, cols, A column major, b
+struct CapturedSystem {
+    int rows, cols;
+    std::vector<double> A, b;
+};
+std::vector<CapturedSystem> g_captured;
+size_t g_capture_limit = 0;
+void capture_system(const double* A, const double* b, int rows, int cols) {
+    if (g_capture_limit == 0) return;
+#pragma omp critical(fks_capture)
+    {
+        if (g_captured.size() < g_capture_limit) {
+            CapturedSystem cs;
+            cs.rows = rows;
+            cs.cols = cols;
+            cs.A.assign(A, A + (size_t)rows * cols);
+            cs.b.assign(b, b + rows);
+            g_captured.push_back(std::move(cs));
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // The simulator (spcs:371-1999)
@@ -931,7 +996,11 @@ struct Sim {
     uint64_t stats[FKS_NUM_STATS];
     // recorded tape of the last call
     std::vector<std::vector<double>> recorded;
+    std::vector<std::vector<uint64_t>> recorded_decisions;
     std::vector<uint32_t> sensitivity;
+    std::vector<double> max_condition;
+    double decision_cond_limit = INFINITY;  // solves whose cond_est exceeds it are recorded with their solution (oracle_set_decision_cond_limit)
+    int qr_model = -1;  // >= 0: solve with the CPU model of the DEVICE solver (fks_qr_model.cpp), option bits = value (studies only)
 
     // CheckEnvironmentCollision (spcs:921-981)
     bool check_env(const Robot& r, double collision_threshold, uint32_t* sens) const {
@@ -1233,7 +1302,49 @@ struct Sim {
                         bvec = corr;
                         for (int r = 0; r < rows; r++)
                             for (int c = 0; c < D; c++) Acm[(size_t)c * rows + r] = Jrows[(size_t)r * D + c];
-                        colpiv_qr_solve(Acm.data(), bvec.data(), rows, D, raw, sens);  // spcs:1629,1990-1998
+                        capture_system(Acm.data(), bvec.data(), rows, D);
+                        if (qr_model >= 0 && (qr_model & 4) && noise.dec_tape) {
+                            // what the GPU does in parity mode: the decisions (and flagged solutions) of the recorded run
+                            // injected into the device solver's arithmetic
+                            const uint64_t rec_words = 2 + (uint64_t)D;
+                            if (noise.dec_pos < noise.dec_end) {
+                                const uint64_t* rec = noise.dec_tape + noise.dec_pos * rec_words;
+                                noise.dec_pos++;
+                                const int rank = (int)(rec[0] & 0xFFull);
+                                if ((int)((rec[0] >> 16) & 0xFFFFFFFFull) != rows) *flags |= FKS_FLAG_DECISION_DESYNC;
+                                if (rec[0] & FKS_DECISION_OVERRIDE_SOLUTION) {
+                                    for (int i = 0; i < D; i++) std::memcpy(&raw[i], &rec[2 + i], 8);
+                                } else {
+                                    oracle_qr_device_model_forced(Acm.data(), bvec.data(), rows, D, qr_model & 3, rec[1], rank, raw);
+                                }
+                            } else {
+                                *flags |= FKS_FLAG_DECISION_DESYNC;
+                                oracle_qr_device_model(Acm.data(), bvec.data(), rows, D, qr_model & 3, raw, nullptr);
+                            }
+                        } else if (qr_model >= 0) {
+                            oracle_qr_device_model(Acm.data(), bvec.data(), rows, D, qr_model, raw, nullptr);
+                        } else {
+                            QrInfo qi;
+                            colpiv_qr_solve(Acm.data(), bvec.data(), rows, D, raw, sens, &qi);  // spcs:1629,1990-1998
+                            if (noise.max_condition && !qi.roundoff_kept) *noise.max_condition = std::max(*noise.max_condition, qi.cond_est);
+                            if (noise.record_decisions) {
+                                // one record of 2 + D words per solve (fksgpu.h, fks_noise_tape.decisions)
+                                std::vector<uint64_t>& dv = *noise.record_decisions;
+                                uint64_t w0 = (uint64_t)qi.rank | ((uint64_t)rows << 16);
+                                if (qi.roundoff_kept || qi.cond_est > decision_cond_limit) w0 |= FKS_DECISION_OVERRIDE_SOLUTION;
+                                if (qi.cond_est > kIllConditioned && qi.cond_est <= decision_cond_limit && !qi.roundoff_kept && sens)
+                                    *sens |= SENS_ILL_CONDITIONED;
+                                if (qi.roundoff_seen) w0 |= FKS_DECISION_ROUNDOFF_PIVOT;
+                                if (qi.tie) w0 |= FKS_DECISION_PIVOT_TIE;
+                                dv.push_back(w0);
+                                dv.push_back(qi.order);
+                                for (int i = 0; i < D; i++) {
+                                    uint64_t bits;
+                                    std::memcpy(&bits, &raw[i], 8);
+                                    dv.push_back(bits);
+                                }
+                            }
+                        }
                     }
                     static const bool trace = std::getenv("FKS_ORACLE_TRACE") != nullptr;
                     if (trace) {
@@ -1403,7 +1514,9 @@ int oracle_forward_simulate(oracle_sim* o, const double* starts, const double* t
     const int stride = s.proto.cfg_stride();
     const size_t rec = (size_t)stride * 8 + sizeof(fks_result_tail);
     s.recorded.assign(record_tape ? n : 0, std::vector<double>());
+    s.recorded_decisions.assign(record_tape ? n : 0, std::vector<uint64_t>());
     s.sensitivity.assign(n, 0);
+    s.max_condition.assign(n, 1.0);
     const int T = s.num_threads;
     std::vector<std::vector<uint64_t>> tstats((size_t)T, std::vector<uint64_t>(FKS_NUM_STATS, 0));
 #pragma omp parallel for schedule(static) num_threads(T)
@@ -1422,10 +1535,17 @@ int oracle_forward_simulate(oracle_sim* o, const double* starts, const double* t
         ns.seed = s.seed;
         ns.particle_id = first_particle_id + (uint64_t)idx;
         ns.record = record_tape ? &s.recorded[(size_t)idx] : nullptr;
+        ns.record_decisions = record_tape ? &s.recorded_decisions[(size_t)idx] : nullptr;
+        ns.max_condition = &s.max_condition[(size_t)idx];
         if (noise_mode == FKS_NOISE_INJECTED) {
             ns.tape = tape->draws;
             ns.tape_pos = tape->offsets[idx];
             ns.tape_end = tape->offsets[idx + 1];
+            if (tape->decisions && tape->decision_offsets) {
+                ns.dec_tape = tape->decisions;
+                ns.dec_pos = tape->decision_offsets[idx];
+                ns.dec_end = tape->decision_offsets[idx + 1];
+            }
         }
         const double* start = starts + (size_t)idx * stride;
         const double* target = targets + (n_targets == n ? (size_t)idx * stride : 0);
@@ -1500,6 +1620,45 @@ void oracle_copy_tape(const oracle_sim* o, double* draws, uint64_t* offsets) {
     }
     offsets[i] = pos;
 }
+// decision tape of the last recorded call: total 64-bit words, then the flat words + per-particle offsets in RECORDS
+uint64_t oracle_decision_words(const oracle_sim* o) {
+    uint64_t t = 0;
+    for (auto& v : o->s.recorded_decisions) t += v.size();
+    return t;
+}
+void oracle_copy_decisions(const oracle_sim* o, uint64_t* words, uint64_t* offsets) {
+    const uint64_t rec_words = 2 + (uint64_t)o->s.proto.D;
+    uint64_t pos = 0;
+    size_t i = 0;
+    for (auto& v : o->s.recorded_decisions) {
+        offsets[i++] = pos / rec_words;
+        std::memcpy(words + pos, v.data(), v.size() * sizeof(uint64_t));
+        pos += v.size();
+    }
+    offsets[i] = pos / rec_words;
+}
+// studies: solve with the CPU model of the device solver (opt_bits >= 0) instead of the Eigen-semantics solver (-1)
+void oracle_set_qr_model(oracle_sim* o, int opt_bits) { o->s.qr_model = opt_bits; }
+// decision tape: also record (FKS_DECISION_OVERRIDE_SOLUTION) the solution of every solve whose condition estimate exceeds `limit`
+void oracle_set_decision_cond_limit(oracle_sim* o, double limit) { o->s.decision_cond_limit = limit; }
+// studies: keep the next `limit` stacked systems the resolver solves
+void oracle_debug_capture_systems(size_t limit) {
+    g_captured.clear();
+    g_capture_limit = limit;
+}
+size_t oracle_debug_captured_count(void) { return g_captured.size(); }
+// sizes of system i; with non-null pointers also copies A (rows x cols column major) and b
+void oracle_debug_captured_system(size_t i, int* rows, int* cols, double* A, double* b) {
+    const CapturedSystem& cs = g_captured[i];
+    *rows = cs.rows;
+    *cols = cs.cols;
+    if (A) std::memcpy(A, cs.A.data(), cs.A.size() * sizeof(double));
+    if (b) std::memcpy(b, cs.b.data(), cs.b.size() * sizeof(double));
+}
+// per particle of the last call: the largest condition estimate among its solves (1 when it never solved)
+void oracle_copy_max_condition(const oracle_sim* o, double* out) {
+    std::memcpy(out, o->s.max_condition.data(), o->s.max_condition.size() * sizeof(double));
+}
 void oracle_copy_sensitivity(const oracle_sim* o, uint32_t* out) {
     std::memcpy(out, o->s.sensitivity.data(), o->s.sensitivity.size() * sizeof(uint32_t));
 }
@@ -1522,6 +1681,16 @@ void oracle_debug_rank_hist(long long* out42, int reset) {
 void oracle_colpiv_qr_solve(const double* A_colmajor, const double* b, int rows, int cols, double* x, uint32_t* sens) {
     std::vector<double> A(A_colmajor, A_colmajor + (size_t)rows * cols), bb(b, b + rows);
     colpiv_qr_solve(A.data(), bb.data(), rows, cols, x, sens);
+}
+// same, also returning the decisions: out4 = {rank, size, order nibbles, flags (1 round-off pivot seen, 2 kept, 4 tie)}
+void oracle_colpiv_qr_solve_info(const double* A_colmajor, const double* b, int rows, int cols, double* x, uint64_t* out4) {
+    std::vector<double> A(A_colmajor, A_colmajor + (size_t)rows * cols), bb(b, b + rows);
+    QrInfo qi;
+    colpiv_qr_solve(A.data(), bb.data(), rows, cols, x, nullptr, &qi);
+    out4[0] = (uint64_t)qi.rank;
+    out4[1] = (uint64_t)qi.size;
+    out4[2] = qi.order;
+    out4[3] = (qi.roundoff_seen ? 1u : 0u) | (qi.roundoff_kept ? 2u : 0u) | (qi.tie ? 4u : 0u);
 }
 void oracle_pid_run(double kp, double ki, double kd, double iclamp, const double* errors, const double* timesteps, int n,
                     double* out) {

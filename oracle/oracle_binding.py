@@ -14,8 +14,16 @@ PID_REF = os.path.join(_HERE, "_ref", "pid_ref")
 
 ORACLE_NOISE_MT19937 = 3
 SENS_NAMES = ("cell_boundary", "est_threshold", "est_zero", "rank_cut", "pivot_tie", "nmicro", "normal_tie",
-              "angle_wrap", "self_collision", "raw_threshold", "step_fraction")
+              "angle_wrap", "self_collision", "raw_threshold", "step_fraction", "ill_conditioned")
+SENS_RANK_CUT = 1 << 3
+SENS_PIVOT_TIE = 1 << 4
 SENS_SELF_COLLISION = 1 << 8
+SENS_ILL_CONDITIONED = 1 << 11
+# Sensitivities that stop mattering once the GPU consumes the oracle's DECISION TAPE (QR rank / pivot order injected), plus the
+# informational self-collision bit (the impulse solve is compared like everything else).
+SENS_COVERED_BY_DECISION_TAPE = SENS_RANK_CUT | SENS_PIVOT_TIE | SENS_SELF_COLLISION
+# decision record word 0 (include/fksgpu.h)
+DECISION_OVERRIDE_SOLUTION, DECISION_ROUNDOFF_PIVOT, DECISION_PIVOT_TIE = 1 << 8, 1 << 9, 1 << 10
 
 
 def build():
@@ -42,6 +50,26 @@ def load():
     lib.oracle_copy_tape.restype = None
     lib.oracle_copy_sensitivity.argtypes = [C.c_void_p, C.c_void_p]
     lib.oracle_copy_sensitivity.restype = None
+    lib.oracle_decision_words.argtypes = [C.c_void_p]
+    lib.oracle_decision_words.restype = C.c_uint64
+    lib.oracle_copy_decisions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_copy_decisions.restype = None
+    lib.oracle_copy_max_condition.argtypes = [C.c_void_p, C.c_void_p]
+    lib.oracle_copy_max_condition.restype = None
+    lib.oracle_set_qr_model.argtypes = [C.c_void_p, C.c_int]
+    lib.oracle_set_qr_model.restype = None
+    lib.oracle_set_decision_cond_limit.argtypes = [C.c_void_p, C.c_double]
+    lib.oracle_set_decision_cond_limit.restype = None
+    lib.oracle_debug_capture_systems.argtypes = [C.c_size_t]
+    lib.oracle_debug_capture_systems.restype = None
+    lib.oracle_debug_captured_count.argtypes = []
+    lib.oracle_debug_captured_count.restype = C.c_size_t
+    lib.oracle_debug_captured_system.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.oracle_debug_captured_system.restype = None
+    lib.oracle_colpiv_qr_solve_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oracle_colpiv_qr_solve_info.restype = None
+    lib.oracle_qr_device_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oracle_qr_device_model.restype = None
     lib.oracle_get_statistics.argtypes = [C.c_void_p, C.c_void_p]
     lib.oracle_get_statistics.restype = None
     lib.oracle_reset_statistics.argtypes = [C.c_void_p]
@@ -169,10 +197,17 @@ class OracleSimulator:
                 draws = np.zeros(1)
 
             class T(C.Structure):
-                _fields_ = [("draws", C.c_void_p), ("offsets", C.c_void_p)]
+                _fields_ = [("draws", C.c_void_p), ("offsets", C.c_void_p), ("decisions", C.c_void_p), ("decision_offsets", C.c_void_p)]
 
-            ctape = T(draws.ctypes.data, offs.ctypes.data)
+            ctape = T(draws.ctypes.data, offs.ctypes.data, None, None)
             keep = (draws, offs)
+            if len(tape) >= 4:
+                dec = np.ascontiguousarray(tape[2], dtype=np.uint64)
+                if dec.size == 0:
+                    dec = np.zeros(1, dtype=np.uint64)
+                dec_offs = np.ascontiguousarray(tape[3], dtype=np.uint64)
+                ctape = T(draws.ctypes.data, offs.ctypes.data, dec.ctypes.data, dec_offs.ctypes.data)
+                keep = (draws, offs, dec, dec_offs)
         rc = lib().oracle_forward_simulate(self._h, starts.ctypes.data, targets.ctypes.data, n, targets.shape[0],
                                            int(bool(allow_contacts)), int(noise_mode),
                                            C.addressof(ctape) if ctape is not None else None, int(first_particle_id),
@@ -223,7 +258,8 @@ class OracleSimulator:
 
 
 def run_with_tape(oracle, starts, targets, allow_contacts=True, noise_mode=ORACLE_NOISE_MT19937, first_particle_id=0):
-    """Run the oracle recording its truncated-normal draws; returns (records, (draws, offsets), sensitivity)."""
+    """Run the oracle recording its truncated-normal draws and its solver decisions; returns
+    (records, (draws, offsets, decision words, decision offsets), sensitivity)."""
     starts = _f64(starts).reshape(-1, oracle.stride)
     n = starts.shape[0]
     rec = oracle.forward_simulate(starts, targets, allow_contacts, noise_mode, None, first_particle_id, record_tape=True)
@@ -233,7 +269,64 @@ def run_with_tape(oracle, starts, targets, allow_contacts=True, noise_mode=ORACL
     lib().oracle_copy_tape(oracle._h, draws.ctypes.data, offs.ctypes.data)
     sens = np.zeros(n, dtype=np.uint32)
     lib().oracle_copy_sensitivity(oracle._h, sens.ctypes.data)
-    return rec, (draws[:total], offs), sens
+    nwords = int(lib().oracle_decision_words(oracle._h))
+    dec = np.zeros(max(nwords, 1), dtype=np.uint64)
+    dec_offs = np.zeros(n + 1, dtype=np.uint64)
+    lib().oracle_copy_decisions(oracle._h, dec.ctypes.data, dec_offs.ctypes.data)
+    return rec, (draws[:total], offs, dec[:nwords], dec_offs), sens
+
+
+def decision_records(tape, n_dof):
+    """Structured view of a decision tape: rank, flags, rows, order, solution per solve (include/fksgpu.h)."""
+    words = np.asarray(tape[2], dtype=np.uint64).reshape(-1, 2 + n_dof)
+    w0 = words[:, 0]
+    return dict(rank=(w0 & np.uint64(0xFF)).astype(np.int64), flags=(w0 & np.uint64(0xFF00)).astype(np.int64),
+                rows=((w0 >> np.uint64(16)) & np.uint64(0xFFFFFFFF)).astype(np.int64), order=words[:, 1],
+                solution=words[:, 2:].view(np.float64), offsets=np.asarray(tape[3], dtype=np.int64))
+
+
+def captured_systems(limit=None):
+    """The stacked systems kept by oracle_debug_capture_systems: list of (A rows x cols, b)."""
+    n = int(lib().oracle_debug_captured_count())
+    out = []
+    for i in range(n if limit is None else min(n, limit)):
+        r, c = C.c_int(), C.c_int()
+        lib().oracle_debug_captured_system(i, C.byref(r), C.byref(c), None, None)
+        A = np.zeros((c.value, r.value))
+        b = np.zeros(r.value)
+        lib().oracle_debug_captured_system(i, C.byref(r), C.byref(c), A.ctypes.data, b.ctypes.data)
+        out.append((A.T.copy(), b))
+    return out
+
+
+def qr_solve_info(A, b):
+    """Eigen-semantics solver of the oracle on A (rows x cols), b -> (x, rank, order, flags)."""
+    A = np.asarray(A, dtype=np.float64)
+    Acm = np.ascontiguousarray(A.T)
+    b = _f64(b)
+    x = np.zeros(A.shape[1])
+    out = np.zeros(4, dtype=np.uint64)
+    lib().oracle_colpiv_qr_solve_info(Acm.ctypes.data, b.ctypes.data, A.shape[0], A.shape[1], x.ctypes.data, out.ctypes.data)
+    return x, int(out[0]), int(out[2]), int(out[3])
+
+
+def qr_device_model(A, b, opt_bits=3):
+    """CPU model of the DEVICE solver (oracle/fks_qr_model.cpp); opt_bits: 1 = fma in norms / back substitution, 2 = fma in
+    the reflector dots / updates.  -> (x, rank, order, min pivot^2 / cut)."""
+    A = np.asarray(A, dtype=np.float64)
+    Acm = np.ascontiguousarray(A.T)
+    b = _f64(b)
+    x = np.zeros(A.shape[1])
+    out = np.zeros(4)
+    lib().oracle_qr_device_model(Acm.ctypes.data, b.ctypes.data, A.shape[0], A.shape[1], int(opt_bits), x.ctypes.data, out.ctypes.data)
+    return x, int(out[0]), int(out[2]), float(out[3])
+
+
+def max_condition_of_last_call(oracle, n):
+    """Per particle: the largest condition estimate (|R00| / min |Rkk|) among the stacked systems it solved."""
+    out = np.ones(n)
+    lib().oracle_copy_max_condition(oracle._h, out.ctypes.data)
+    return out
 
 
 def sensitivity_of_last_call(oracle, n):

@@ -7,8 +7,9 @@ vectors, which come from the REFERENCE's own header through oracle/_ref/pid_ref)
 * env_golden.npz         -- BuildCompleteEnvironment of two small obstacle sets (tests/env_cases.py: thin_plates, rotated_boxes)
                             by the oracle: occupancy, float SDF, surface-normal table (host and device builder are held to it)
 * trace_golden.npz       -- step traces (ForwardSimulationStepTrace, flat) of single particles by the oracle, Philox noise
-* forward_golden.npz     -- oracle end states for small seeded batches of every robot kind with the recorded
-                            noise tape: the GPU tests replay the tape and compare, so a GPU box without the oracle
+* forward_golden.npz     -- oracle end states for small seeded batches of every robot kind (and of BASELINE config 3's
+                            contact regime, arm_table) with the recorded noise and decision tapes: the GPU tests replay the
+                            tapes and compare, so a GPU box without the oracle
                             build (or a future oracle change) is still pinned to these numbers.  The reference
                             ships no fixtures of its own: these are the builder's.
 """
@@ -39,7 +40,10 @@ def pid():
               open(os.path.join(HERE, "pid_golden.json"), "w"))
 
 
-GOLDEN_CASES = (("se2_arena", 32), ("se3_narrow_passage", 48), ("arm_elbow", 24), ("arm_selfcollision", 8))
+GOLDEN_CASES = (("se2_arena", 32), ("se3_narrow_passage", 48), ("arm_elbow", 24), ("arm_selfcollision", 8), ("arm_table", 48))
+# arm_table (BASELINE config 3's contact regime): its solves are rank deficient by round-off, so its
+# decision tape also carries the solution of every solve with a condition estimate above 100 -- every particle reproduces
+DECISION_COND_LIMIT = {"arm_table": 100.0}
 
 
 def forward():
@@ -47,7 +51,11 @@ def forward():
     for name, n in GOLDEN_CASES:
         w = W.make(name, n_particles=n)
         orc = OB.OracleSimulator(w.environment().desc, w.robot.to_c(), capi.default_solver_params(), 25.0, 42, 1)
-        rec, (draws, offs), sens = OB.run_with_tape(orc, w.starts, w.targets)
+        if name in DECISION_COND_LIMIT:
+            OB.lib().oracle_set_decision_cond_limit(orc._h, DECISION_COND_LIMIT[name])
+        rec, (draws, offs, dec, dec_offs), sens = OB.run_with_tape(orc, w.starts, w.targets)
+        out[name + "_decisions"] = dec
+        out[name + "_decision_offsets"] = dec_offs
         out[name + "_cfg"] = rec["cfg"]
         out[name + "_tail"] = np.stack([rec["flags"], rec["n_microsteps"], rec["n_resolver_iters"], rec["n_steps"]], axis=1)
         out[name + "_draws"] = draws

@@ -23,7 +23,7 @@ def test_header_functions_are_exported():
 
 
 def test_abi_version_and_defaults():
-    assert capi.lib.fks_abi_version() == 1
+    assert capi.lib.fks_abi_version() == 2
     p = capi.default_solver_params()  # SimulatorSolverParameters() defaults, spcs.hpp:357-368
     assert (p.forward_simulation_time, p.simulation_shortcut_distance, p.environment_collision_check_tolerance) == (1.0, 0.0, 0.001)
     assert (p.resolve_correction_step_scaling_decay_rate, p.resolve_correction_initial_step_size, p.resolve_correction_min_step_scaling) == (0.5, 1.0, 0.03125)
@@ -35,7 +35,7 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(capi.AxisParams) == 64
     assert C.sizeof(capi.JointDesc) == 16 + 12 * 8 + 3 * 8 + 3 * 8
     assert C.sizeof(capi.Obstacle) == 12 * 8 + 3 * 8 + 8
-    assert C.sizeof(capi.NoiseTape) == 16
+    assert C.sizeof(capi.NoiseTape) == 32
 
 
 def test_no_device_is_an_error_not_a_fallback():

@@ -6,21 +6,27 @@ import pytest
 from fast_kinematic_simulator_b200 import capi, workloads as W
 
 import parity
+from oracle import oracle_binding as OB
 
 pytestmark = pytest.mark.gpu
 
 
-def _assert_parity(rep, sens, min_insensitive_frac=0.0):
+def _assert_parity(rep, sens, min_insensitive_frac=0.5, min_match_frac=0.999):
+    """No particle without an enumerated reason may differ, most particles must BE without such a reason, and nearly all
+    particles (sensitive or not) must reproduce: a green test means the trajectories were compared, not excused."""
     print(parity.describe(rep, sens))
     assert len(rep["bad_insensitive"]) == 0, "insensitive particles differ: %s" % rep["bad_insensitive"][:16]
-    assert rep["n_insensitive"] >= min_insensitive_frac * rep["n"]
+    assert rep["n_insensitive"] >= min_insensitive_frac * rep["n"], (rep["n_insensitive"], rep["n"])
+    assert rep["n_match"] >= min_match_frac * rep["n"], (rep["n_match"], rep["n"])
+    if rep["n_match"] == rep["n"]:
+        assert rep["n_desync"] == 0
 
 
 def test_se2_arena_parity():
     w = W.se2_arena(128)
     rep, gpu, ref, sens = parity.run_parity(w, 128)
     _assert_parity(rep, sens, 0.25)
-    assert gpu.did_contact.all()
+    assert gpu.did_contact.all() and rep["n_match"] == 128
     # every particle insensitive in the oracle must reproduce the 8 statistics too when nothing is enumerated
     if len(rep["bad_sensitive"]) == 0:
         assert rep["gpu_stats"] == rep["oracle_stats"]
@@ -34,17 +40,61 @@ def test_se2_no_contacts_allowed():
 
 
 def test_se3_narrow_passage_parity():
-    w = W.se3_narrow_passage(1024)
-    rep, gpu, ref, sens = parity.run_parity(w, 1024)
-    _assert_parity(rep, sens, 0.25)
+    """BASELINE config 2 at its full size (16 384 particles) in injection mode.  The three translation columns of the SE(3)
+    Jacobian [R | R (e x p)] have EQUAL norms up to round-off, so Eigen's first pivots are ties the reference breaks by the
+    last bit: the decision tape carries the order."""
+    w = W.se3_narrow_passage(16384)
+    rep, gpu, ref, sens = parity.run_parity(w, 16384)
+    _assert_parity(rep, sens, 0.9)
     assert gpu.did_contact.any() and not gpu.did_contact.all()
 
 
 def test_arm_table_parity():
-    w = W.arm_table(512)
-    rep, gpu, ref, sens = parity.run_parity(w, 512)
-    _assert_parity(rep, sens)
-    assert gpu.did_contact.any()
+    """BASELINE config 3's contact regime, 4 096 particles: one distal link on the table -> stacked Jacobians of rank <= 6
+    in 7 unknowns, whose last pivot is round-off.  With the oracle's decisions injected every
+    particle must reproduce unless the oracle met an ill-conditioned solve on its way (condition estimate > 1e3: last-bit
+    differences of the solve's INPUT come out multiplied by that) -- those are enumerated with that reason, and most of
+    them reproduce anyway."""
+    w = W.arm_table(4096)
+    rep, gpu, ref, sens = parity.run_parity(w, 4096)
+    _assert_parity(rep, sens, min_insensitive_frac=0.5, min_match_frac=0.97)
+    assert gpu.did_contact.all() and gpu.resolve_failed.any()
+    for i in rep["bad_sensitive"]:
+        assert int(sens[i]) & OB.SENS_ILL_CONDITIONED, (i, int(sens[i]))  # every exception has the non-rank reason
+    # the recorded decisions are what the test is about: round-off pivots cut AND kept must both occur
+    d = rep["decisions"]
+    assert ((d["flags"] & OB.DECISION_ROUNDOFF_PIVOT) != 0).sum() > 1000 and ((d["flags"] & OB.DECISION_OVERRIDE_SOLUTION) != 0).sum() > 50
+
+
+def test_arm_table_parity_with_ill_conditioned_solves_injected():
+    """The same batch with the solution of every solve whose condition estimate exceeds 100 taken from the tape as well
+    (a third of the solves): nothing is left to amplify round-off, so EVERY particle must reproduce -- all the way through
+    kinematics, collision checks, normals, Jacobians, the well-conditioned solves, step scaling and failure handling."""
+    w = W.arm_table(4096)
+    rep, gpu, ref, sens = parity.run_parity(w, 4096, decision_cond_limit=100.0)
+    _assert_parity(rep, sens, min_insensitive_frac=0.99, min_match_frac=1.0)
+    assert rep["gpu_stats"] == rep["oracle_stats"]
+
+
+def test_arm_table_aggregates_free_running():
+    """No tapes: Philox noise on both sides, every decision the solver's own.  Individual particles diverge (the keep-or-cut
+    of a round-off pivot is a coin flip in the reference itself), the DISTRIBUTIONS must agree: the device solver follows
+    Eigen operation for operation, so it keeps such pivots at the reference's rate."""
+    n = 4096
+    w = W.arm_table(n)
+    sim = w.make_simulator()
+    g = sim.forward_simulate_robots(w.starts, w.targets, True, capi.NOISE_PHILOX)
+    orc = parity.make_oracle(w)
+    r = orc.forward_simulate(w.starts, w.targets, True, capi.NOISE_PHILOX)
+    gf, rf = g.resolve_failed.mean(), ((r["flags"] & capi.FLAG_RESOLVE_FAILED) != 0).mean()
+    se_f = np.sqrt(2 * 0.25 / n)
+    print("failed %.4f / %.4f, microsteps %.2f / %.2f, iterations %.2f / %.2f, steps %.3f / %.3f" % (
+        gf, rf, g.n_microsteps.mean(), r["n_microsteps"].mean(), g.n_resolver_iters.mean(), r["n_resolver_iters"].mean(),
+        g.n_steps.mean(), r["n_steps"].mean()))
+    assert abs(gf - rf) < 4 * se_f
+    for a, b in ((g.n_microsteps, r["n_microsteps"]), (g.n_resolver_iters, r["n_resolver_iters"]), (g.n_steps, r["n_steps"])):
+        se = np.sqrt((a.var() + b.var()) / n)
+        assert abs(a.mean() - b.mean()) < 4 * se, (a.mean(), b.mean(), se)
 
 
 def test_arm_free_motion_parity():
@@ -59,17 +109,18 @@ def test_arm_free_motion_parity():
 def test_arm_elbow_parity():
     """Contact on the proximal links: structurally-zero Jacobian columns, spherical-shoulder rank loss (rank 2 of 3),
     failing resolves.  Every particle must reproduce exactly."""
-    w = W.arm_elbow(256)
-    rep, gpu, ref, sens = parity.run_parity(w, 256)
+    w = W.arm_elbow(2048)
+    rep, gpu, ref, sens = parity.run_parity(w, 2048)
     _assert_parity(rep, sens)
-    assert rep["n_match"] == 256 and gpu.resolve_failed.any()
+    assert rep["n_match"] == 2048 and gpu.resolve_failed.any()
     assert rep["gpu_stats"] == rep["oracle_stats"]
 
 
 def test_arm_selfcollision_parity():
-    w = W.arm_selfcollision(128)
-    rep, gpu, ref, sens = parity.run_parity(w, 128)
+    w = W.arm_selfcollision(512)
+    rep, gpu, ref, sens = parity.run_parity(w, 512)
     _assert_parity(rep, sens)
+    assert rep["n_match"] == 512
     assert rep["gpu_stats"]["unsuccessful_self_collision_resolves"] == rep["oracle_stats"]["unsuccessful_self_collision_resolves"]
 
 
@@ -136,8 +187,8 @@ def test_philox_matches_oracle_statistically():
 
 def test_gantry_parity_all_joint_types():
     """PRISMATIC + FIXED + REVOLUTE (limit reached) + CONTINUOUS (wraps through pi) joints, wall contact."""
-    w = W.gantry(128)
-    rep, gpu, ref, sens = parity.run_parity(w, 128)
+    w = W.gantry(1024)
+    rep, gpu, ref, sens = parity.run_parity(w, 1024)
     _assert_parity(rep, sens, 0.5)
     assert gpu.did_contact.mean() > 0.9 and np.array_equal(gpu.did_contact, (ref["flags"] & 1) != 0)
     # the y axis target lies beyond the prismatic limit: the joint saturates at +0.2
