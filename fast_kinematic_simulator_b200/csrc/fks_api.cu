@@ -298,7 +298,7 @@ int fks_robot_create(int device, const fks_robot_desc* r, fks_robot** out) {
     if (r->n_points <= 0 || r->n_points > (1 << 20) || !r->points_xyz || !r->point_link || !r->axes)
         return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: bad point/axis arrays");
     const int L = r->n_links, J = r->n_joints, D = r->n_dof;
-    if (L < 1 || L > kMaxLinks || J < 0 || J > kMaxJoints || D < 1 || D > kMaxDof)
+    if (L < 1 || L > kMaxLinks || J < 0 || J > kMaxJoints || D < 1 || D > kMaxDof - 1)  // the solver keeps D + 1 <= 16 columns
         return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: link/joint/dof count out of range");
     if (r->kind == FKS_ROBOT_SE2 && (L != 1 || D != 3)) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: SE2 needs 1 link, 3 dof");
     if (r->kind == FKS_ROBOT_SE3 && (L != 1 || D != 6)) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: SE3 needs 1 link, 6 dof");

@@ -125,7 +125,7 @@ struct WarpLayout {
     int caps;     // 6 * L: world end points of every link's bounding capsule
     int M;        // 16 * J: joint_transform * motion(value), by columns
     int jsm;      // start of the shared-memory Jacobian store (= T + 2 * L12)
-    int jsm_ld;   // its leading dimension (odd: the column-per-lane solver reads one row of every column at a time)
+    int jsm_ld;   // its leading dimension
     int jaxis, jorig;  // 3 * J each
     int target, scfg, act, ru, du, raw, stepv;  // S each
     int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
@@ -157,9 +157,13 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.caps = o; o += 6 * L;
     o += jsm_extra;
     {
-        // (D + 1) columns of jsm_ld doubles; an odd leading dimension spreads a row of 8 columns over 16 distinct banks
-        int ld = (o - w.jsm) / (D + 1);
-        if ((ld & 1) == 0) ld -= 1;
+        // (D + 1) columns of jsm_ld doubles.  The solver's lane 4 g + i reads rows = i (mod 4) of column g: a leading dimension
+        // = 4 (mod 16) puts the 16 lanes of a half warp on 16 different bank pairs; take it when it costs at most a quarter
+        // of the rows
+        const int cap = (o - w.jsm) / (D + 1);
+        int ld = cap;
+        const int pref = cap - ((cap - 4) & 15);
+        if (cap >= 20 && pref >= 20 && pref * 4 >= cap * 3) ld = pref;
         w.jsm_ld = ld < 0 ? 0 : ld;
     }
     w.jaxis = o; o += 3 * J;

@@ -1246,19 +1246,25 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
 // cut |pivot|^2 < (eps max|col|)^2 / rows (rows - k), makeHouseholderInPlace from the tail's squared norm, reflectors
 // applied as  tmp = essential . bottom + top;  top -= tau tmp;  bottom -= (tau essential) tmp,  basic solution.
 //
-// Why verbatim, and why one lane per COLUMN.  With a single distal link of the arm in contact the stacked Jacobian has
-// rank <= 6 in 7 unknowns: the last pivot is pure round-off and Eigen cuts or keeps it by the last bit; when it is kept
-// the solve divides by it and the "correction" saturates every joint, which usually fails the resolve.  How OFTEN that
-// happens (6.7 % of such solves in the oracle) decides the failure rate of the whole workload, and it moves between 6 %
-// and 11 % with the summation order, the association of the reflector update or FMA contraction
-// (profiles/r2_qr_keep_rate.md).  So every sum here runs over the rows in row order and every product and sum rounds
-// once (__dmul_rn / __dadd_rn: the reference is x86-64 code without FMA): lane j < cols owns column j, lane `cols` the
-// right-hand side, and the row loops are sequential per lane.  On identical input this solver returns the oracle's bits.
-// It is also a loop nest of ~300 instructions (the register-resident warp-cooperative QR it replaces was 2 500 per copy,
-// instruction-cache bound) and needs no shuffle trees: an 8-row dot product is 8 dependent adds, not 2 x 9 exchanges.
+// Why verbatim.  With a single distal link of the arm in contact the stacked Jacobian has rank <= 6 in 7 unknowns: the
+// last pivot is pure round-off and Eigen cuts or keeps it by the last bit; when it is kept the solve divides by it and the
+// "correction" saturates every joint, which usually fails the resolve.  How OFTEN that happens decides the failure rate of
+// the whole workload, and it moves between 6 % and 11 % with the summation order, the association of the reflector update
+// or FMA contraction (profiles/r2_qr_keep_rate.md).  So every product and sum here rounds once (__dmul_rn / __dadd_rn: the
+// reference is x86-64 code without FMA) and every reduction over rows uses the oracle's order -- Eigen's SSE2 reduction:
+// four interleaved partial sums, partial sum i over the rows congruent to i modulo 4 in ascending order, result
+// (p0 + p2) + (p1 + p3).  On identical input this solver returns the oracle's bits (tests/test_gpu_qr_solver.py).
+//
+// Mapping: FOUR lanes per column, lane 4 g + i owns the rows = i (mod 4) of column g (+ 8 per extra slot when there are
+// more than 8 columns; column `cols` is the right-hand side), so a partial sum is a private sequential loop and a reduction
+// ends with two exchanges inside the quad.  A lane only ever touches its own rows of its own columns, except for the pivot
+// column's essential part, which every lane reads (a broadcast).  The squared norms Eigen computes in separate passes (the
+// tail of the next pivot column, the recomputed norm of a downdate) are accumulated while the column is updated -- same
+// values, same order, no extra pass.  ~450 instructions in one loop nest: the register-resident warp-cooperative QR it
+// replaces was 2 500 per copy and instruction-cache bound.
 //
 // A = (cols + 1) columns of leading dimension ld (shared memory when the system is small, the warp's global scratch slot
-// otherwise: generic addressing), column `cols` = right-hand side.  Result in the shared vector at x_off.
+// otherwise: generic addressing).  Result in the shared vector at x_off.
 //
 // Parity mode (decision tape, fksgpu.h): the pivot order and the rank are taken from the tape, the solver's own are
 // still computed and a difference raises FKS_FLAG_DECISION_OVERRIDDEN; a record flagged OVERRIDE_SOLUTION replaces the
@@ -1268,16 +1274,21 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+// (p0 + p2) + (p1 + p3) over the four lanes of a quad; every lane of the quad gets the same bits (+ is commutative)
+__device__ __forceinline__ double quad_sum(unsigned mask, double p) {
+    p = add_rn(p, __shfl_xor_sync(mask, p, 2));
+    return add_rn(p, __shfl_xor_sync(mask, p, 1));
+}
 
+template <int SLOTS>  // columns per quad: 1 for up to 8 columns (every robot of the reference), 2 for up to 16
 __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows, int cols, int x_off) {
     const Frame& fr = frame();
     const int lane = lane_id();
     double* ws = wsd(wb);
     WarpVars* wv = reinterpret_cast<WarpVars*>(ws + fr.a.wl.vars);
     double* x = ws + x_off;
-    const bool is_col = lane < cols;
-    const bool is_rhs = lane == cols;
-    double* mine = A + (size_t)(lane <= cols ? lane : 0) * ld;
+    const int g = lane >> 2, i = lane & 3;
+    const unsigned quad = 0xFu << (lane & ~3);
     // ---- decision tape (parity mode only) ----------------------------------------------------------------------
     bool forced = false;
     int f_rank = 0;
@@ -1295,7 +1306,7 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
                 f_order = rec[1];
                 if (w0 & (unsigned long long)FKS_DECISION_OVERRIDE_SOLUTION) {
                     replaced = true;
-                    if (is_col) x[lane] = __longlong_as_double((long long)rec[2 + lane]);
+                    if (lane < cols) x[lane] = __longlong_as_double((long long)rec[2 + lane]);
                 }
             }
         }
@@ -1309,50 +1320,78 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
         if (replaced) return;
     }
     const int size = rows < cols ? rows : cols;
-    // colNormsDirect / colNormsUpdated of this lane's column
-    double nu = 0.0, nd = 0.0;
-    if (is_col) {
-        double s = 0.0;
-#pragma unroll 4
-        for (int r = 0; r < rows; r++) {
-            const double a = mine[r];
-            s = add_rn(s, mul_rn(a, a));
+    // per column slot of this quad: colNormsUpdated / colNormsDirect, the position in Eigen's permuted order, and this
+    // lane's partial of sum_{r > k} a_r^2 for the coming step (= the tail's squared norm should the column be the pivot)
+    double nu[SLOTS], nd[SLOTS], tailp[SLOTS];
+    int pos[SLOTS];
+    double max_norm = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; sl++) {
+        const int c = g + 8 * sl;
+        nu[sl] = nd[sl] = tailp[sl] = 0.0;
+        pos[sl] = c;
+        if (c < cols) {  // uniform inside the quad
+            const double* mine = A + (size_t)c * ld;
+            double pf = 0.0, pt = 0.0;
+            for (int r = i; r < rows; r += 4) {
+                const double a = mine[r];
+                const double sq = mul_rn(a, a);
+                pf = add_rn(pf, sq);
+                if (r >= 1) pt = add_rn(pt, sq);
+            }
+            nd[sl] = nu[sl] = sqrt(quad_sum(quad, pf));
+            tailp[sl] = pt;
+            max_norm = fmax(max_norm, nu[sl]);
         }
-        nd = nu = sqrt(s);
     }
-    const double max_norm = warp_max(is_col ? nu : 0.0);
+    max_norm = warp_max(max_norm);
     const double me = mul_rn(max_norm, DBL_EPSILON);
     const double threshold_helper = div_rn(mul_rn(me, me), (double)rows);
     const double norm_downdate_threshold = 1.4901161193847656e-08;  // sqrt(epsilon)
     int own_rank = size, nonzero_pivots = size;
-    int pos = lane;                   // position of this lane's column in Eigen's permuted order
-    unsigned long long order = 0ull;  // 4 bits per position: the lane (= original column) sitting there
+    unsigned long long order = 0ull;  // 4 bits per position: the column sitting there
     bool differed = false, near_cut = false;
 #pragma unroll 1
     for (int k = 0; k < size; k++) {
         // biggest updated norm among the positions k .. cols-1, the first position wins (Eigen's maxCoeff scan)
-        const bool cand_ok = is_col && pos >= k;
-        double bv = cand_ok ? nu : -1.0;
-        int bp = cand_ok ? pos : 0x7fffffff, bl = lane;
+        double bv = -1.0;
+        int bp = 0x7fffffff, bc = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int sl = 0; sl < SLOTS; sl++) {
+            const int c = g + 8 * sl;
+            if (c < cols && pos[sl] >= k && (nu[sl] > bv || (nu[sl] == bv && pos[sl] < bp))) {
+                bv = nu[sl];
+                bp = pos[sl];
+                bc = c;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o >= 4; o >>= 1) {
             const double ov = __shfl_xor_sync(FKS_FULL, bv, o);
-            const int op = __shfl_xor_sync(FKS_FULL, bp, o), ol = __shfl_xor_sync(FKS_FULL, bl, o);
+            const int op = __shfl_xor_sync(FKS_FULL, bp, o), oc = __shfl_xor_sync(FKS_FULL, bc, o);
             if (ov > bv || (ov == bv && op < bp)) {
                 bv = ov;
                 bp = op;
-                bl = ol;
+                bc = oc;
             }
         }
-        int p = bl;
+        int p = bc;
         if (forced) {
             const int fp = (int)((f_order >> (4 * k)) & 0xFull);
-            const int fpos = __shfl_sync(FKS_FULL, pos, fp);
+            // position and norm of the tape's pivot column, from its quad
+            double fnu = nu[0];
+            int fpos = pos[0];
+            if (SLOTS > 1 && (fp >> 3) == 1) {
+                fnu = nu[SLOTS - 1];
+                fpos = pos[SLOTS - 1];
+            }
+            fnu = __shfl_sync(FKS_FULL, fnu, 4 * (fp & 7));
+            fpos = __shfl_sync(FKS_FULL, fpos, 4 * (fp & 7));
             if (fp < cols && fpos >= k) {
                 if (fp != p) differed = true;
                 p = fp;
                 bp = fpos;
-                bv = __shfl_sync(FKS_FULL, nu, fp);
+                bv = fnu;
             } else {
                 differed = true;  // a record that does not fit this system: keep the solver's own pivot
             }
@@ -1363,22 +1402,21 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
         if (max_norm > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
         nonzero_pivots = forced ? (f_rank < size ? f_rank : size) : own_rank;
         // the column that sat at position k takes the pivot's old position (m_qr.col(k).swap(m_qr.col(biggest)))
-        if (is_col && pos == k) pos = bp;
-        if (lane == p) pos = k;
+        double tail_sq = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; sl++) {
+            const int c = g + 8 * sl;
+            if (c < cols && pos[sl] == k) pos[sl] = bp;
+            if (c == p) {
+                pos[sl] = k;
+                tail_sq = tailp[sl];
+            }
+        }
         order |= (unsigned long long)p << (4 * k);
         double* piv = A + (size_t)p * ld;
-        // makeHouseholderInPlace on col(k).tail(rows - k)
-        double tail_sq = 0.0, c0 = 0.0;
-        if (lane == p) {
-#pragma unroll 4
-            for (int r = k + 1; r < rows; r++) {
-                const double a = piv[r];
-                tail_sq = add_rn(tail_sq, mul_rn(a, a));
-            }
-            c0 = piv[k];
-        }
-        tail_sq = __shfl_sync(FKS_FULL, tail_sq, p);
-        c0 = __shfl_sync(FKS_FULL, c0, p);
+        // makeHouseholderInPlace on col(k).tail(rows - k): the tail's squared norm was accumulated with the last update
+        tail_sq = __shfl_sync(FKS_FULL, quad_sum(FKS_FULL, tail_sq), 4 * (p & 7));
+        const double c0 = piv[k];
         double tau, beta;
         if (tail_sq <= DBL_MIN) {
             tau = 0.0;
@@ -1391,39 +1429,56 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
             for (int r = k + 1 + lane; r < rows; r += 32) piv[r] = div_rn(piv[r], denom);  // element-wise: any lane may do it
             tau = div_rn(sub_rn(beta, c0), beta);
         }
-        if (lane == p) piv[k] = beta;
-        __syncwarp();
+        __syncwarp();  // c0 has been read by everyone, the essential part is visible to everyone
+        if (lane == 0) piv[k] = beta;
         // applyHouseholderOnTheLeft to the remaining columns; to the right-hand side only below the rank cut (Eigen's solve
-        // applies the first nonzero_pivots reflectors to c)
-        if ((is_col && pos > k) || (is_rhs && nonzero_pivots > k)) {
-            if (rows - k == 1) {
-                mine[k] = mul_rn(mine[k], sub_rn(1.0, tau));
-            } else if (tau != 0.0) {
-                double tmp = 0.0;
-#pragma unroll 4
-                for (int r = k + 1; r < rows; r++) tmp = add_rn(tmp, mul_rn(piv[r], mine[r]));
-                tmp = add_rn(tmp, mine[k]);
-                mine[k] = sub_rn(mine[k], mul_rn(tau, tmp));
-#pragma unroll 4
-                for (int r = k + 1; r < rows; r++) mine[r] = sub_rn(mine[r], mul_rn(mul_rn(tau, piv[r]), tmp));
+        // applies the first nonzero_pivots reflectors to c).  The loop that updates a column also accumulates the squared
+        // norms of its rows > k (a downdate may need it) and > k + 1 (the next tail).
+        const bool last_row = rows - k == 1;
+        const int r0 = k + 1 + ((i - (k + 1)) & 3);  // first row > k that is = i (mod 4)
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; sl++) {
+            const int c = g + 8 * sl;
+            const bool is_col = c < cols;
+            if (!((is_col && pos[sl] > k) || (c == cols && nonzero_pivots > k))) continue;  // uniform inside the quad
+            double* mine = A + (size_t)c * ld;
+            double ak = mine[k];
+            double tmp = 0.0;
+            const bool reflect = !last_row && tau != 0.0;
+            if (reflect) {
+                double pd = 0.0;
+                for (int r = r0; r < rows; r += 4) pd = add_rn(pd, mul_rn(piv[r], mine[r]));
+                tmp = add_rn(quad_sum(quad, pd), ak);
+                ak = sub_rn(ak, mul_rn(tau, tmp));
+            } else if (last_row) {
+                ak = mul_rn(ak, sub_rn(1.0, tau));
             }
-            if (is_col && nu != 0.0) {  // LAPACK-style norm downdate
-                double temp = div_rn(fabs(mine[k]), nu);
+            __syncwarp(quad);  // every lane of the quad has read the old mine[k]
+            if (i == 0) mine[k] = ak;
+            double p1 = 0.0, p2 = 0.0;
+            for (int r = r0; r < rows; r += 4) {
+                double v = mine[r];
+                if (reflect) {
+                    v = sub_rn(v, mul_rn(mul_rn(tau, piv[r]), tmp));
+                    mine[r] = v;
+                }
+                const double sq = mul_rn(v, v);
+                p1 = add_rn(p1, sq);
+                if (r >= k + 2) p2 = add_rn(p2, sq);
+            }
+            tailp[sl] = p2;
+            const double direct = quad_sum(quad, p1);
+            if (is_col && nu[sl] != 0.0) {  // LAPACK-style norm downdate
+                double temp = div_rn(fabs(ak), nu[sl]);
                 temp = mul_rn(add_rn(1.0, temp), sub_rn(1.0, temp));
                 temp = temp < 0.0 ? 0.0 : temp;
-                const double ratio = div_rn(nu, nd);
+                const double ratio = div_rn(nu[sl], nd[sl]);
                 const double temp2 = mul_rn(temp, mul_rn(ratio, ratio));
                 if (temp2 <= norm_downdate_threshold) {
-                    double s = 0.0;
-#pragma unroll 4
-                    for (int r = k + 1; r < rows; r++) {
-                        const double a = mine[r];
-                        s = add_rn(s, mul_rn(a, a));
-                    }
-                    nd = sqrt(s);
-                    nu = nd;
+                    nd[sl] = sqrt(direct);
+                    nu[sl] = nd[sl];
                 } else {
-                    nu = mul_rn(nu, sqrt(temp));
+                    nu[sl] = mul_rn(nu[sl], sqrt(temp));
                 }
             }
         }
@@ -1434,18 +1489,24 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
         if (forced && (differed || own_rank != nonzero_pivots)) raise_flag(wb, FKS_FLAG_DECISION_OVERRIDDEN);
     }
     // solve: back substitution on the leading nonzero_pivots x nonzero_pivots triangle, the other unknowns zero
-    if (is_col) x[lane] = 0.0;
+    if (lane < cols) x[lane] = 0.0;
     __syncwarp();
-    if (is_rhs && nonzero_pivots > 0) {
-        for (int i = nonzero_pivots - 1; i >= 0; i--) {
-            double s = mine[i];
-            for (int j = i + 1; j < nonzero_pivots; j++)
-                s = sub_rn(s, mul_rn(A[(size_t)((order >> (4 * j)) & 0xFull) * ld + i], mine[j]));
-            mine[i] = div_rn(s, A[(size_t)((order >> (4 * i)) & 0xFull) * ld + i]);
+    if (lane == 0 && nonzero_pivots > 0) {
+        double* rhs = A + (size_t)cols * ld;
+        for (int ii = nonzero_pivots - 1; ii >= 0; ii--) {
+            double s = rhs[ii];
+            for (int j = ii + 1; j < nonzero_pivots; j++)
+                s = sub_rn(s, mul_rn(A[(size_t)((order >> (4 * j)) & 0xFull) * ld + ii], rhs[j]));
+            rhs[ii] = div_rn(s, A[(size_t)((order >> (4 * ii)) & 0xFull) * ld + ii]);
         }
-        for (int i = 0; i < nonzero_pivots; i++) x[(order >> (4 * i)) & 0xFull] = mine[i];
+        for (int ii = 0; ii < nonzero_pivots; ii++) x[(order >> (4 * ii)) & 0xFull] = rhs[ii];
     }
     __syncwarp();
+}
+// the solver for `cols` unknowns (+ the right-hand side): one column per quad when they fit 8 quads
+__device__ __forceinline__ void colpiv_qr_solve(int wb, double* A, int ld, int rows, int cols, int x_off) {
+    if (cols + 1 <= 8) colpiv_qr_lanes<1>(wb, A, ld, rows, cols, x_off);
+    else colpiv_qr_lanes<2>(wb, A, ld, rows, cols, x_off);
 }
 
 // actuator noise of the next `count` microsteps, one truncated-normal draw per axis in axis order
@@ -2021,7 +2082,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 if (lane < D) ws[wl.raw + lane] = 0.0;
                 __syncwarp();
             } else {
-                colpiv_qr_lanes(wb, jstore, jld, rows, D, wl.raw);
+                colpiv_qr_solve(wb, jstore, jld, rows, D, wl.raw);
             }
 #ifdef FKS_PHASE_TIMERS
             if (rows <= 64) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
@@ -2234,7 +2295,7 @@ __global__ void __launch_bounds__(128) qr_solve_kernel(double* work, const unsig
     for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps_total) {
         if (lane == 0) *reinterpret_cast<unsigned*>(ws + fr.a.wl.flags) = 0u;
         __syncwarp();
-        colpiv_qr_lanes(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw);
+        colpiv_qr_solve(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw);
         if (lane < cols) x_out[(size_t)i * cols + lane] = ws[fr.a.wl.raw + lane];
         if (lane == 0) flags_out[i] = *reinterpret_cast<const unsigned*>(ws + fr.a.wl.flags);
         __syncwarp();

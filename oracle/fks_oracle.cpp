@@ -691,6 +691,20 @@ struct QrInfo {
 };
 constexpr double kRoundoffPivotBand = 1e8;
 
+// Every reduction over rows (squaredNorm, the reflector's dot products) goes through sum4.  RESTATEMENT: Eigen reduces
+// with SSE2 packets -- two packets of two doubles, i.e. FOUR interleaved partial sums that are added pairwise at the end
+// (redux_impl<..., LinearVectorizedTraversal>; the reference is built without -march, CMakeLists.txt:66) -- and where its
+// packets start depends on the alignment of the column in memory, which no second implementation can reproduce.  Fixed
+// here: partial sum i takes the entries whose ROW index is congruent to i modulo 4, in ascending row order, and the result
+// is (p0 + p2) + (p1 + p3) (packet_res0 + packet_res1, then predux).  The device solver uses the same order (one lane per
+// partial sum), which is what makes it return these bits (tests/test_gpu_qr_solver.py).
+template <class Term>
+inline double sum4(int lo, int hi, Term term) {
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int r = lo; r < hi; r++) p[r & 3] += term(r);
+    return (p[0] + p[2]) + (p[1] + p[3]);
+}
+
 void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32_t* sens, QrInfo* info = nullptr) {
     const int size = std::min(rows, cols);
     int colidx[kMaxDof];
@@ -702,9 +716,8 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
     auto col = [&](int j) { return A + (size_t)j * rows; };
     double max_norm = 0.0;
     for (int k = 0; k < cols; k++) {
-        double s = 0.0;
-        for (int r = 0; r < rows; r++) s += col(k)[r] * col(k)[r];
-        norms_direct[k] = std::sqrt(s);
+        const double* ck = col(k);
+        norms_direct[k] = std::sqrt(sum4(0, rows, [&](int r) { return ck[r] * ck[r]; }));
         norms_updated[k] = norms_direct[k];
         max_norm = std::max(max_norm, norms_updated[k]);
     }
@@ -742,15 +755,6 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
             }
 #pragma omp atomic
             g_rank_hist[bucket]++;
-            static const bool dbg = std::getenv("FKS_ORACLE_DEBUG_RANK") != nullptr;
-            if (dbg && bucket < 35) {
-#pragma omp critical
-                {
-                    std::fprintf(stderr, "near-rank pivot: rows %d cols %d k %d big %.3e max_norm %.3e norms_direct:", rows, cols, k, big, max_norm);
-                    for (int j = 0; j < cols; j++) std::fprintf(stderr, " %.3e", norms_direct[j]);
-                    std::fprintf(stderr, "\n");
-                }
-            }
         }
         transp[k] = biggest;
         std::swap(colidx[k], colidx[biggest]);
@@ -761,8 +765,7 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
         }
         // makeHouseholderInPlace on col(k).tail(rows-k)
         double* ck = col(k);
-        double tail_sq = 0.0;
-        for (int r = k + 1; r < rows; r++) tail_sq += ck[r] * ck[r];
+        const double tail_sq = sum4(k + 1, rows, [&](int r) { return ck[r] * ck[r]; });
         const double c0 = ck[k];
         double tau, beta;
         if (tail_sq <= DBL_MIN) {
@@ -784,8 +787,7 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
         } else if (tau != 0.0) {
             for (int j = k + 1; j < cols; j++) {
                 double* cj = col(j);
-                double tmp = 0.0;
-                for (int r = k + 1; r < rows; r++) tmp += ck[r] * cj[r];
+                double tmp = sum4(k + 1, rows, [&](int r) { return ck[r] * cj[r]; });
                 tmp += cj[k];
                 cj[k] -= tau * tmp;
                 for (int r = k + 1; r < rows; r++) cj[r] -= (tau * ck[r]) * tmp;
@@ -800,9 +802,8 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
                 const double ratio = norms_updated[j] / norms_direct[j];
                 const double temp2 = temp * (ratio * ratio);
                 if (temp2 <= norm_downdate_threshold) {
-                    double s = 0.0;
-                    for (int r = k + 1; r < rows; r++) s += col(j)[r] * col(j)[r];
-                    norms_direct[j] = std::sqrt(s);
+                    const double* cj = col(j);
+                    norms_direct[j] = std::sqrt(sum4(k + 1, rows, [&](int r) { return cj[r] * cj[r]; }));
                     norms_updated[j] = norms_direct[j];
                 } else {
                     norms_updated[j] *= std::sqrt(temp);
@@ -828,8 +829,7 @@ void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32
         if (rows - k == 1) {
             b[k] *= (1.0 - tau);
         } else if (tau != 0.0) {
-            double tmp = 0.0;
-            for (int r = k + 1; r < rows; r++) tmp += ck[r] * b[r];
+            double tmp = sum4(k + 1, rows, [&](int r) { return ck[r] * b[r]; });
             tmp += b[k];
             b[k] -= tau * tmp;
             for (int r = k + 1; r < rows; r++) b[r] -= (tau * ck[r]) * tmp;

@@ -53,6 +53,7 @@ def compare(gpu, ref, sens, rtol=RTOL, with_decisions=False):
         max_err_matching=float(cfg_err[ok].max()) if ok.any() else 0.0,
         cfg_err=cfg_err,
         ok=ok,
+        discrete_ok=flags_ok & counts_ok,
         n_overridden=int(((g["flags"] & capi.FLAG_DECISION_OVERRIDDEN) != 0).sum()),
         n_desync=int(((g["flags"] & capi.FLAG_DECISION_DESYNC) != 0).sum()),
     )
