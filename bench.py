@@ -10,10 +10,15 @@ workload: BASELINE config 3, the 7-DoF linked arm with 65,536 particles PER GPU 
 job simulates N x 65,536 particles, and for N > 1 every step ends with the NCCL all-gather of end-state records
 the north star names).  Noise is counter-based Philox keyed by global particle id.
 
-value  = particle-microsteps / s, whole job, inputs resident in HBM, device-timed (CUDA events), max over ranks.
-e2e    = the same metric through the C ABI with HOST buffers (pinned): H2D of starts/targets + kernel + D2H of
-         the result records inside the timed region.
---impl reference times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample.
+value   = particle-microsteps / s, whole job, inputs resident in HBM, device-timed (CUDA events), max over ranks.
+e2e     = the same metric with HOST buffers (pinned) through the C ABI: H2D of starts/targets + kernels + D2H of the
+          result records inside the timed region; at N > 1 the records of ALL ranks are gathered (ncclAllGather) and
+          read back on every rank inside it.
+config5 = BASELINE config 5 in the same line: 1,048,576 arm particles IN TOTAL split over the N GPUs (strong scaling),
+          all-gather of the end states included, device-timed.
+roofline= the contact kernel (the dominant one of the call's two) against the unit ncu shows binding for the workload.
+--impl reference times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample; that arm
+never loads libfksgpu.so.
 """
 import argparse
 import json
@@ -43,6 +48,7 @@ def parse_args():
     ap.add_argument("--workload", default="arm_table")
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the BASELINE config's count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config5-particles", type=int, default=1048576, help="total particles of the strong-scaling leg (0 = skip it)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -99,9 +105,10 @@ class ClockSampler(threading.Thread):
 
 
 def algorithmic_work(stats, P, D, J):
-    """ALGORITHMIC bytes and FP64 flops of a batch from its counters.
+    """ALGORITHMIC bytes, FP64 flops and SDF / normal-table gathers of a batch from its counters.
     bytes = 4 P per microstep + (28 P + 4 P) per resolver iteration + 56 per corrected point + (16 D + 16) per step;
-    flops = (FK + 39 P) per microstep + (3 FK + 174 P + 12 D P) per iteration + (40 + 6 D^2) per corrected point."""
+    flops = (FK + 39 P) per microstep + (3 FK + 174 P + 12 D P) per iteration + (40 + 6 D^2) per corrected point;
+    gathers = P per microstep + 8 P per iteration (one 4-byte SDF value per point per check, 7 per distance estimate)."""
     M = stats["total_microsteps"]
     I = stats["total_resolver_iterations"]
     K = stats["total_corrected_points"]
@@ -109,7 +116,21 @@ def algorithmic_work(stats, P, D, J):
     fk = 130 * J + 40 * J if J else (20 if D == 3 else 0)
     nbytes = 4 * P * M + 32 * P * I + 56 * K + (16 * D + 16) * S
     flops = (fk + 39 * P) * M + (3 * fk + P * (36 + 12 * D + 21 + 30) + 36 * P + 39 * P) * I + (40 + 6 * D * D) * K
-    return nbytes, flops
+    gathers = P * M + 8 * P * I
+    return nbytes, flops, gathers
+
+
+def oracle_simulator(w, threads):
+    """The CPU oracle for workload `w`, environment built by the oracle's own restatement of BuildCompleteEnvironment:
+    nothing of the product is loaded on this path."""
+    from fast_kinematic_simulator_b200 import abi
+    from oracle import oracle_binding as OB
+
+    env = OB.build_environment(w.obstacles, w.resolution)
+    desc, keep = abi.env_desc_from_arrays(env)
+    orc = OB.OracleSimulator(desc, w.robot.to_c(), abi.default_solver_params(), 25.0, 42, threads)
+    orc._keep_env = keep
+    return orc
 
 
 def run_reference(args, rank, world):
@@ -117,25 +138,24 @@ def run_reference(args, rank, world):
     compiled without Eigen/ROS/arc_utilities/sdf_tools), all host threads, bounded sample per step."""
     if rank != 0:
         return
-    from fast_kinematic_simulator_b200 import capi, workloads as W
-    from oracle import oracle_binding as OB
+    from fast_kinematic_simulator_b200 import abi, workloads as W
 
     n_per_gpu = args.particles or DEFAULT_PARTICLES.get(args.workload, 65536)
     w = W.make(args.workload, n_particles=min(n_per_gpu, 8192))
     # all host threads (torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly)
-    orc = OB.OracleSimulator(w.environment().desc, w.robot.to_c(), capi.default_solver_params(), 25.0, 42, host_threads())
+    orc = oracle_simulator(w, host_threads())
     # calibrate the sample so that one step is ~4 s of CPU work
     n0 = min(128, w.n_particles)
     s0, t0 = w.subset(n0)
     t = time.perf_counter()
-    orc.forward_simulate(s0, t0, True, capi.NOISE_PHILOX)
+    orc.forward_simulate(s0, t0, True, abi.NOISE_PHILOX)
     dt = max(time.perf_counter() - t, 1e-3)
     n = int(max(n0, min(w.n_particles, n0 * 4.0 / dt)))
     starts, targets = w.subset(n)
     times, micro = [], 0
     for it in range(args.warmup + args.steps):
         t = time.perf_counter()
-        rec = orc.forward_simulate(starts, targets, True, capi.NOISE_PHILOX)
+        rec = orc.forward_simulate(starts, targets, True, abi.NOISE_PHILOX)
         dt = time.perf_counter() - t
         if it >= args.warmup:
             times.append(dt)
@@ -143,12 +163,15 @@ def run_reference(args, rank, world):
     total = sum(times)
     value = micro * len(times) / total
     sample = "first %d of %d particles of workload %s per step, Philox noise, %d OpenMP threads" % (n, n_per_gpu, w.name, orc.num_threads)
+    loaded = [l.split()[-1] for l in open("/proc/self/maps") if ".so" in l and ("fks" in l)]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w.name, "particles_per_step": n, "description": w.description,
-                   "note": "CPU restatement of the reference (oracle port); the reference needs Eigen/ROS/arc_utilities/sdf_tools"},
+                   "note": "CPU restatement of the reference (oracle port, environment built by the oracle too); the reference "
+                           "itself needs Eigen/ROS/arc_utilities/sdf_tools",
+                   "native_libraries": sorted(set(os.path.basename(x) for x in loaded))},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -182,6 +205,7 @@ def main():
         # starts are regenerated per shard with a shard-specific seed
         w = W.make(args.workload, n_particles=n_local, seed=1003 + rank) if args.workload != "se2_arena" else w
     sim = w.make_simulator(device=local_rank)
+    sim.enable_kernel_timing(True)
     rd = w.robot
     P, D, J = rd.points.shape[0], rd.n_dof, len(rd.joints)
     stride, rec = sim.config_stride, sim.result_stride
@@ -196,11 +220,11 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
 
-    def device_step():
-        sim.forward_simulate_device(d_starts, d_targets, n_local, n_targets, d_results, True, capi.NOISE_PHILOX,
-                                    first_particle_id=first_id, stream=stream.cuda_stream)
+    def device_step(ds=d_starts, n=n_local, first=first_id, out=d_results, gather=d_gather):
+        sim.forward_simulate_device(ds, d_targets, n, n_targets if n_targets == 1 else n, out, True, capi.NOISE_PHILOX,
+                                    first_particle_id=first, stream=stream.cuda_stream)
         if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_results)
+            dist.all_gather_into_tensor(gather, out)
 
     def barrier():
         if world > 1:
@@ -217,68 +241,124 @@ def main():
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []  # per step: device time of [free flight, hand-over sort, contact] (or of the single kernel)
     barrier()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the timed events)
         ev[i][0].record(stream)
-        kev[i][0].record(stream)
-        sim.forward_simulate_device(d_starts, d_targets, n_local, n_targets, d_results, True, capi.NOISE_PHILOX,
-                                    first_particle_id=first_id, stream=stream.cuda_stream)
-        kev[i][1].record(stream)
-        if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_results)
+        device_step()
         ev[i][1].record(stream)
+        kernel_ms.append(sim.kernel_times_ms())  # waits for this step's kernels; the events above are on the stream
     barrier()
     step_ms = sum(a.elapsed_time(b) for a, b in ev)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kev)
     stats = sim.get_statistics()
+    free_stats = sim.free_flight_statistics()
     launches = sim.launch_count - launches0
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
 
-    # ---- end to end through the C ABI with host (pinned) buffers ---------------------------------
+    # ---- end to end with host (pinned) buffers: H2D, kernels, gather over the ranks, D2H, all inside the timed region ----
     h_starts = torch.from_numpy(w.starts).pin_memory()
     h_targets = torch.from_numpy(w.targets).pin_memory()
-    h_results = torch.empty(n_local * rec, dtype=torch.uint8).pin_memory()
-    out = h_results.numpy().view(sim.dtype)
-    hs, ht = h_starts.numpy(), h_targets.numpy()
+    if world == 1:
+        h_results = torch.empty(n_local * rec, dtype=torch.uint8).pin_memory()
+        out = h_results.numpy().view(sim.dtype)
+        hs, ht = h_starts.numpy(), h_targets.numpy()
+
+        def e2e_step():
+            return int(sim.forward_simulate_robots(hs, ht, True, capi.NOISE_PHILOX, first_particle_id=first_id, out=out).n_microsteps.sum())
+    else:
+        h_all = torch.empty(world * n_local * rec, dtype=torch.uint8).pin_memory()
+        view = h_all.numpy().view(sim.dtype)
+
+        def e2e_step():
+            d_starts.copy_(h_starts, non_blocking=True)
+            d_targets.copy_(h_targets, non_blocking=True)
+            device_step()
+            h_all.copy_(d_gather, non_blocking=True)
+            torch.cuda.synchronize()
+            return int(view["n_microsteps"][rank * n_local:(rank + 1) * n_local].sum())
     for _ in range(max(1, args.warmup // 2)):
-        sim.forward_simulate_robots(hs, ht, True, capi.NOISE_PHILOX, first_particle_id=first_id, out=out)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = sim.forward_simulate_robots(hs, ht, True, capi.NOISE_PHILOX, first_particle_id=first_id, out=out)
-        if world > 1:
-            pass  # the host API returns each rank's records; gathering them on the host is the caller's choice
+        micro_e2e = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
-    micro_e2e = int(res.n_microsteps.sum())
+
+    # ---- BASELINE config 5: 1,048,576 arm particles in total over the N GPUs (strong scaling), all-gather included ----
+    c5 = None
+    if args.config5_particles > 0 and args.workload == "arm_table":
+        n5 = args.config5_particles // world
+        w5 = W.make("arm_table", n_particles=n5, seed=2003 + rank)
+        s5 = torch.from_numpy(w5.starts).to(dev)
+        r5 = torch.empty(n5 * rec, dtype=torch.uint8, device=dev)
+        g5 = torch.empty(world * n5 * rec, dtype=torch.uint8, device=dev) if world > 1 else None
+        device_step(s5, n5, rank * n5, r5, g5)  # warm-up (allocates the hand-over buffers for this size)
+        barrier()
+        st0 = sim.get_statistics()
+        e5 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        reps5 = 2
+        e5[0].record(stream)
+        for _ in range(reps5):
+            device_step(s5, n5, rank * n5, r5, g5)
+        e5[1].record(stream)
+        barrier()
+        st1 = sim.get_statistics()
+        c5 = [e5[0].elapsed_time(e5[1]) / reps5, float(st1["total_microsteps"] - st0["total_microsteps"]) / reps5]
+        del s5, r5, g5
 
     # ---- reduce over ranks: max time, sum of work ------------------------------------------------
-    vals = torch.tensor([step_ms, kernel_ms, e2e_s], dtype=torch.float64, device=dev)
-    work = torch.tensor([float(stats[k]) for k in capi.STAT_NAMES] + [float(micro_e2e)], dtype=torch.float64, device=dev)
+    kms = [sum(k[j] for k in kernel_ms) / len(kernel_ms) for j in range(len(kernel_ms[0]))]
+    vals = torch.tensor([step_ms, e2e_s, c5[0] if c5 else 0.0], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(stats[k]) for k in capi.STAT_NAMES] + [float(micro_e2e), c5[1] if c5 else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    step_ms, kernel_ms, e2e_s = [float(x) for x in vals.tolist()]
-    tot = {k: int(v) for k, v in zip(capi.STAT_NAMES, work.tolist()[:-1])}
-    micro_e2e_total = int(work.tolist()[-1])
+    step_ms, e2e_s, c5_ms = [float(x) for x in vals.tolist()]
+    tot = {k: int(v) for k, v in zip(capi.STAT_NAMES, work.tolist()[:-2])}
+    micro_e2e_total, c5_micro = int(work.tolist()[-2]), work.tolist()[-1]
 
     if rank == 0:
         value = tot["total_microsteps"] / (step_ms * 1e-3)
         e2e_value = micro_e2e_total * args.steps / e2e_s
-        # roofline of the dominant (only) kernel, per launch, from THIS rank's counters and kernel events
-        nbytes, flops = algorithmic_work(stats, P, D, J)
-        k_s = (sum(a.elapsed_time(b) for a, b in kev) * 1e-3) / args.steps
+        # Roofline of the dominant kernel of the call, per launch, from THIS rank's counters and the device time of that kernel:
+        # the contact kernel when the call ran the free-flight / contact pair, else the single kernel.
+        two = len(kms) == 3
+        dom_stats = {k: stats[k] - (free_stats[k] if two else 0) for k in capi.STAT_NAMES}
+        nbytes, flops, gathers = algorithmic_work(dom_stats, P, D, J)
+        k_s = (kms[2] if two else kms[0]) * 1e-3
+        kname = "simulate_kernel<%d, false, %s>" % (w.kind, "kModeContact" if two else "kModeAll")
         peak, how = measured_peaks()
-        achieved = nbytes / args.steps / k_s / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get(w.name)
+        sdf_bytes = 4 * int(np.prod(w.environment().shape))
+        import ctypes as C
+        fp, ga, gh = C.c_double(), C.c_double(), C.c_double()
+        have_fp = capi.lib.fks_measure_fp64_peak(local_rank, C.byref(fp)) == 0
+        have_g = capi.lib.fks_measure_gather_rate(local_rank, 64 << 20, C.byref(ga)) == 0 and \
+            capi.lib.fks_measure_gather_rate(local_rank, 2 << 30, C.byref(gh)) == 0
+        hbm_resident = sdf_bytes > (100 << 20)
+        roof_hbm = {"bound": "hbm", "achieved": nbytes / args.steps / k_s / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": nbytes / args.steps / k_s / 1e9 / peak, "traffic": traffic, "peak_source": how, "kernel": kname,
+                    "kernel_ms_per_launch": 1e3 * k_s, "algorithmic_bytes_per_launch": nbytes // args.steps}
+        if hbm_resident or not have_g:
+            roofline = dict(roof_hbm, note="the SDF (%d MB) does not fit the L2: its gathers are HBM traffic" % (sdf_bytes >> 20))
+        else:
+            g_rate = gathers / args.steps / k_s
+            roofline = {"bound": "l2_gather", "achieved": g_rate / 1e9, "peak": ga.value / 1e9, "unit": "Ggather/s (4-byte, L2-resident)",
+                        "frac": g_rate / ga.value, "traffic": traffic,
+                        "peak_source": "random 4-byte __ldg gathers over an L2-resident 64 MiB array, measured in this job (fks_measure_gather_rate)",
+                        "kernel": kname, "kernel_ms_per_launch": 1e3 * k_s, "algorithmic_gathers_per_launch": gathers // args.steps,
+                        "algorithmic_bytes_per_launch": nbytes // args.steps,
+                        "note": "the %.1f MB SDF is L2-resident (persisting window): DRAM is idle (traffic = measured DRAM bytes of one launch), "
+                                "the binding units are the L2 gather path and the FP64 pipe; see roofline_hbm / roofline_fp64 for the other "
+                                "denominators" % (sdf_bytes / 1e6)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -291,56 +371,47 @@ def main():
                        "resolver_iterations_per_step": tot["total_resolver_iterations"] // args.steps},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * (n_local + n_targets) * stride * 8),
-                    "d2h_bytes_per_step": int(world * n_local * rec), "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "d2h_bytes_per_step": int(world * n_local * rec * (world if world > 1 else 1)), "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "includes": "H2D of starts/targets, kernels, %sD2H of the records" % ("ncclAllGather of all ranks' records, " if world > 1 else "")},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": how, "kernel": "simulate_kernel<%d>" % w.kind,
-                         "kernel_ms_per_launch": 1e3 * k_s, "algorithmic_bytes_per_launch": nbytes // args.steps,
-                         "note": "SURVEY 8(d) counts only SDF/normal gathers + particle state; the SDF is L2-resident by design, "
-                                 "so the binding unit is the FP64 pipe / LSU, see roofline_fp64"},
+            "kernels_ms_per_step": dict(zip(("free_flight", "handover_sort", "contact"), kms)) if two else {"single": kms[0]},
+            "roofline": roofline,
+            "roofline_hbm": roof_hbm,
             "kernel_info": sim.kernel_info,
         }
-        # FP64 and L2-gather denominators measured on this box in the same job
-        import ctypes as C
-        fp = C.c_double()
-        ga = C.c_double()
-        gh = C.c_double()
-        if capi.lib.fks_measure_fp64_peak(local_rank, C.byref(fp)) == 0:
+        if have_fp:
             af = flops / args.steps / k_s
             line["roofline_fp64"] = {"achieved": af / 1e12, "peak": fp.value / 1e12, "unit": "TFLOP/s", "frac": af / fp.value,
                                      "peak_source": "dependent-free DFMA micro-benchmark in this job",
                                      "algorithmic_flops_per_launch": flops // args.steps}
-        if capi.lib.fks_measure_gather_rate(local_rank, 64 << 20, C.byref(ga)) == 0 and \
-                capi.lib.fks_measure_gather_rate(local_rank, 2 << 30, C.byref(gh)) == 0:
-            gathers = (P * tot_local(stats, "total_microsteps") + 8 * P * tot_local(stats, "total_resolver_iterations")) / args.steps / k_s
-            line["gather"] = {"achieved_gathers_per_s": gathers, "l2_peak_gathers_per_s": ga.value, "hbm_peak_gathers_per_s": gh.value,
-                              "frac_of_l2_peak": gathers / ga.value}
+        if have_g:
+            line["gather_peaks"] = {"l2_resident_gathers_per_s": ga.value, "hbm_resident_gathers_per_s": gh.value}
+        if c5 is not None:
+            line["config5"] = {"workload": "arm_table", "particles_total": (args.config5_particles // world) * world, "scaling": "strong",
+                               "ms_per_step": c5_ms, "value": c5_micro / (c5_ms * 1e-3), "unit": UNIT,
+                               "collective": "ncclAllGather of end-state records" if world > 1 else "none (1 GPU)"}
         if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only
-            line["cpu_baseline"] = cpu_baseline(args, w, capi)
+            line["cpu_baseline"] = cpu_baseline(args, w)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def tot_local(stats, key):
-    return stats[key]
-
-
-def cpu_baseline(args, w, capi):
+def cpu_baseline(args, w):
     """The oracle port on this box's host cores, bounded sample of the same workload (rank 0, N = 1 shape)."""
-    from oracle import oracle_binding as OB
+    from fast_kinematic_simulator_b200 import abi
 
-    orc = OB.OracleSimulator(w.environment().desc, w.robot.to_c(), capi.default_solver_params(), 25.0, 42, host_threads())
+    orc = oracle_simulator(w, host_threads())
     n0 = min(256, w.n_particles)
     s0, t0 = w.subset(n0)
     t = time.perf_counter()
-    orc.forward_simulate(s0, t0, True, capi.NOISE_PHILOX)
+    orc.forward_simulate(s0, t0, True, abi.NOISE_PHILOX)
     dt = max(time.perf_counter() - t, 1e-3)
     n = int(max(n0, min(w.n_particles, n0 * args.cpu_seconds / dt)))
     starts, targets = w.subset(n)
     t = time.perf_counter()
-    rec = orc.forward_simulate(starts, targets, True, capi.NOISE_PHILOX)
+    rec = orc.forward_simulate(starts, targets, True, abi.NOISE_PHILOX)
     dt = time.perf_counter() - t
     return {"value": float(rec["n_microsteps"].sum()) / dt, "unit": UNIT, "cores": orc.num_threads, "kind": "port",
             "sample": "first %d of %d particles of %s, one call, Philox noise, %.1f s" % (n, w.n_particles, w.name, dt)}

@@ -115,6 +115,15 @@ struct fks_sim {
     char* d_results;
     size_t cap_starts, cap_targets, cap_tape, cap_tape_off, cap_results, cap_dec, cap_dec_off;
     size_t smem_limit;
+    // hand-over buffers of the free-flight / contact kernel pair (grown on demand)
+    char* d_park;
+    unsigned int *d_park_key, *d_park_order, *d_park_meta;
+    size_t cap_park, cap_park_key, cap_park_order;
+    int two_kernels;  // developer knob FKS_TWO_KERNELS (default 1)
+    // per-kernel device time of the last batch call (fks_sim_kernel_times): events around the free-flight kernel, the
+    // hand-over sort and the contact kernel, recorded only after fks_sim_enable_kernel_timing
+    cudaEvent_t tev[4];
+    int timing, timed_kernels;
     // launches of one simulator share its particle counter, scratch slots and statistics: a launch on another stream waits
     // for the previous one (fks_forward_simulate_device takes the caller's stream)
     cudaEvent_t last_done;
@@ -373,6 +382,11 @@ int fks_robot_create(int device, const fks_robot_desc* r, fks_robot** out) {
         if (d.active >= 0 && d.active < kMaxDof) h.active_joint[d.active] = j;
         link_parent_joint[jd.child_link] = j;
     }
+    for (int l = 1; l < L; l++)
+        if (link_parent_joint[l] < 0) {  // a link no joint leads to would keep an uninitialised transform on the device
+            delete rob;
+            return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: every link other than link 0 needs a parent joint");
+        }
     if (r->kind == FKS_ROBOT_LINKED && active != D) {  // tnuva.hpp:503-516 throws std::invalid_argument
         delete rob;
         return fail(FKS_ERR_INVALID_ARGUMENT, "fks_robot_create: number of axis parameter sets != number of active joints");
@@ -541,6 +555,14 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     s->d_tape_off = s->d_dec = s->d_dec_off = nullptr;
     s->d_results = nullptr;
     s->cap_starts = s->cap_targets = s->cap_tape = s->cap_tape_off = s->cap_results = s->cap_dec = s->cap_dec_off = 0;
+    s->d_park = nullptr;
+    s->d_park_key = s->d_park_order = s->d_park_meta = nullptr;
+    s->cap_park = s->cap_park_key = s->cap_park_order = 0;
+    s->two_kernels = 1;
+    if (const char* ev = std::getenv("FKS_TWO_KERNELS")) s->two_kernels = std::atoi(ev);
+    for (int i = 0; i < 4; i++) s->tev[i] = nullptr;
+    s->timing = 0;
+    s->timed_kernels = 0;
     s->last_done = nullptr;
     s->last_stream = nullptr;
     s->has_last = false;
@@ -598,9 +620,10 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     if ((err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (err = cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_scratch, scratch_bytes)) != cudaSuccess ||
-        (err = cudaMalloc((void**)&s->d_stats, 64 * sizeof(unsigned long long))) != cudaSuccess ||
-        (err = cudaMalloc((void**)&s->d_counter, sizeof(unsigned int))) != cudaSuccess ||
-        (err = cudaMemset(s->d_stats, 0, 64 * sizeof(unsigned long long))) != cudaSuccess) {
+        (err = cudaMalloc((void**)&s->d_stats, 128 * sizeof(unsigned long long))) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_counter, 4 * sizeof(unsigned int))) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_park_meta, (1 + 2 * kParkBuckets) * sizeof(unsigned int))) != cudaSuccess ||
+        (err = cudaMemset(s->d_stats, 0, 128 * sizeof(unsigned long long))) != cudaSuccess) {
         fks_sim_destroy(s);
         return cuda_fail(err, "fks_sim_create: allocation");
     }
@@ -629,8 +652,14 @@ void fks_sim_destroy(fks_sim* s) {
     cudaFree(s->d_tape_off);
     cudaFree(s->d_dec);
     cudaFree(s->d_dec_off);
+    cudaFree(s->d_park);
+    cudaFree(s->d_park_key);
+    cudaFree(s->d_park_order);
+    cudaFree(s->d_park_meta);
     cudaFree(s->d_results);
     if (s->last_done) cudaEventDestroy(s->last_done);
+    for (int i = 0; i < 4; i++)
+        if (s->tev[i]) cudaEventDestroy(s->tev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -682,10 +711,43 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
     const size_t blocks_needed = (n + (size_t)wpb - 1) / (size_t)wpb;
     const int grid = (int)std::min<size_t>((size_t)s->grid_max, blocks_needed);
     if (s->has_last && stream != s->last_stream) FKS_CUDA(cudaStreamWaitEvent(stream, s->last_done, 0));
-    FKS_CUDA(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned int), stream));
-    const int rc = launch_simulate(s->robot->host.kind, a, grid, dyn_smem, stream, s->env->l2_window_bytes ? s->env->d_sdf : nullptr,
-                                   s->env->l2_window_bytes);
-    if (rc != 0) return cuda_fail((cudaError_t)rc, "simulate kernel launch");
+    FKS_CUDA(cudaMemsetAsync(s->d_counter, 0, 4 * sizeof(unsigned int), stream));
+    const void* l2_base = s->env->l2_window_bytes ? s->env->d_sdf : nullptr;
+    const int kind = s->robot->host.kind;
+    if (s->two_kernels && a.allow_contacts && a.trace == nullptr) {
+        // batch path: free flight up to the first colliding microstep, then the contact regime (fks_device_types.h, kModeFree)
+        int rc;
+        a.park_stride = (int)park_record_bytes(a.wl);
+        if ((rc = ensure(&s->d_park, &s->cap_park, n * (size_t)a.park_stride)) != FKS_OK) return rc;
+        if ((rc = ensure(&s->d_park_key, &s->cap_park_key, n)) != FKS_OK) return rc;
+        if ((rc = ensure(&s->d_park_order, &s->cap_park_order, n)) != FKS_OK) return rc;
+        a.park = s->d_park;
+        a.park_key = s->d_park_key;
+        a.park_order = s->d_park_order;
+        a.park_meta = s->d_park_meta;
+        FKS_CUDA(cudaMemsetAsync(s->d_park_meta, 0, (1 + 2 * kParkBuckets) * sizeof(unsigned int), stream));
+        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[0], stream));
+        a.stats = s->d_stats + 40;  // the free-flight kernel counts apart (fks_debug_kernel_statistics); fks_get_statistics adds them up
+        rc = launch_simulate(kind, kModeFree, a, grid, dyn_smem, stream, l2_base, s->env->l2_window_bytes);
+        if (rc != 0) return cuda_fail((cudaError_t)rc, "free-flight kernel launch");
+        a.stats = s->d_stats;
+        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[1], stream));
+        rc = launch_park_order(a, std::max(1, std::min(2 * s->num_sms, (int)((n + 255) / 256))), stream);
+        if (rc != 0) return cuda_fail((cudaError_t)rc, "park order kernel launch");
+        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[2], stream));
+        a.counter = s->d_counter + 1;
+        rc = launch_simulate(kind, kModeContact, a, grid, dyn_smem, stream, l2_base, s->env->l2_window_bytes);
+        if (rc != 0) return cuda_fail((cudaError_t)rc, "contact kernel launch");
+        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[3], stream));
+        s->timed_kernels = s->timing ? 3 : 0;
+        s->launches += 2;
+    } else {
+        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[0], stream));
+        const int rc = launch_simulate(kind, kModeAll, a, grid, dyn_smem, stream, l2_base, s->env->l2_window_bytes);
+        if (rc != 0) return cuda_fail((cudaError_t)rc, "simulate kernel launch");
+        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[1], stream));
+        s->timed_kernels = s->timing ? 1 : 0;
+    }
     FKS_CUDA(cudaEventRecord(s->last_done, stream));
     s->last_stream = stream;
     s->has_last = true;
@@ -707,7 +769,7 @@ static int check_batch(const fks_sim* sim, const void* starts, const void* targe
     return FKS_OK;
 }
 
-int fks_forward_simulate(fks_sim* s, const double* starts, const double* targets, size_t n, size_t n_targets,
+int fks_forward_simulate_async(fks_sim* s, const double* starts, const double* targets, size_t n, size_t n_targets,
                          int allow_contacts, int noise_mode, const fks_noise_tape* tape, uint64_t first_particle_id,
                          void* results) {
     int rc = check_batch(s, starts, targets, n, n_targets, noise_mode, tape ? tape->draws : nullptr, tape ? tape->offsets : nullptr, results);
@@ -747,8 +809,23 @@ int fks_forward_simulate(fks_sim* s, const double* starts, const double* targets
                             with_decisions ? (const uint64_t*)s->d_dec_off : nullptr, first_particle_id, s->d_results, s->stream);
     if (rc != FKS_OK) return rc;
     FKS_CUDA(cudaMemcpyAsync(results, s->d_results, n * rec, cudaMemcpyDeviceToHost, s->stream));
+    return FKS_OK;
+}
+
+int fks_sim_synchronize(fks_sim* s) {
+    if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_synchronize: null simulator");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_sim_synchronize: cudaSetDevice failed");
     FKS_CUDA(cudaStreamSynchronize(s->stream));
     return FKS_OK;
+}
+
+int fks_forward_simulate(fks_sim* s, const double* starts, const double* targets, size_t n, size_t n_targets,
+                         int allow_contacts, int noise_mode, const fks_noise_tape* tape, uint64_t first_particle_id,
+                         void* results) {
+    const int rc = fks_forward_simulate_async(s, starts, targets, n, n_targets, allow_contacts, noise_mode, tape, first_particle_id, results);
+    if (rc != FKS_OK || n == 0) return rc;
+    return fks_sim_synchronize(s);
 }
 
 size_t fks_sim_trace_stride(const fks_sim* s) {
@@ -861,8 +938,47 @@ int fks_get_statistics(fks_sim* s, uint64_t* out) {
     DeviceGuard guard(s->device);
     int rc = sync_simulator(s);
     if (rc != FKS_OK) return rc;
-    FKS_CUDA(cudaMemcpyAsync(out, s->d_stats, FKS_NUM_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    uint64_t both[64];
+    FKS_CUDA(cudaMemcpyAsync(both, s->d_stats, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
     FKS_CUDA(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < FKS_NUM_STATS; k++) out[k] = both[k] + both[40 + k];  // contact (or single) kernel + free-flight kernel
+    return FKS_OK;
+}
+
+// Measurement aids (bench.py): device time of the kernels of the last batch call and their separate counters.
+int fks_sim_enable_kernel_timing(fks_sim* s, int enable) {
+    if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_enable_kernel_timing: null simulator");
+    DeviceGuard guard(s->device);
+    if (enable)
+        for (int i = 0; i < 4; i++)
+            if (!s->tev[i]) FKS_CUDA(cudaEventCreate(&s->tev[i]));
+    s->timing = enable ? 1 : 0;
+    s->timed_kernels = 0;
+    return FKS_OK;
+}
+
+// out_ms[0] = free-flight kernel, [1] = hand-over sort, [2] = contact kernel (a single-kernel call: [0] only); returns the
+// number of kernels timed in *n_kernels.  Waits for the call.
+int fks_sim_kernel_times(fks_sim* s, double* out_ms, int* n_kernels) {
+    if (!s || !out_ms || !n_kernels) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_kernel_times: null argument");
+    DeviceGuard guard(s->device);
+    *n_kernels = s->timed_kernels;
+    for (int i = 0; i < s->timed_kernels; i++) {
+        FKS_CUDA(cudaEventSynchronize(s->tev[i + 1]));
+        float ms = 0.f;
+        FKS_CUDA(cudaEventElapsedTime(&ms, s->tev[i], s->tev[i + 1]));
+        out_ms[i] = (double)ms;
+    }
+    return FKS_OK;
+}
+
+// counters of the free-flight kernel alone (out has FKS_NUM_STATS entries); fks_get_statistics minus these = the contact kernel
+int fks_sim_free_flight_statistics(fks_sim* s, uint64_t* out) {
+    if (!s || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_free_flight_statistics: null argument");
+    DeviceGuard guard(s->device);
+    int rc = sync_simulator(s);
+    if (rc != FKS_OK) return rc;
+    FKS_CUDA(cudaMemcpy(out, s->d_stats + 40, FKS_NUM_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return FKS_OK;
 }
 
@@ -871,7 +987,7 @@ int fks_reset_statistics(fks_sim* s) {
     DeviceGuard guard(s->device);
     int rc = sync_simulator(s);
     if (rc != FKS_OK) return rc;
-    FKS_CUDA(cudaMemsetAsync(s->d_stats, 0, 64 * sizeof(uint64_t), s->stream));
+    FKS_CUDA(cudaMemsetAsync(s->d_stats, 0, 128 * sizeof(uint64_t), s->stream));
     FKS_CUDA(cudaStreamSynchronize(s->stream));
     return FKS_OK;
 }

@@ -104,7 +104,7 @@ struct WarpVars {
     double scaling;
     unsigned step, micro, number_microsteps, resolver_iterations, flags, n_micro_total, n_iter_total, n_steps;
     int collided, any_resolve_failed, step_collided, step_failed, step_stopped;
-    int _pad;
+    int qr_rows;  // > 0: a tall stacked system (this many rows) is half factored and waits for the next solver slot
 };
 constexpr int kWarpVarsDoubles = (int)((sizeof(WarpVars) + 7) / 8);
 
@@ -115,17 +115,21 @@ constexpr int kWarpVarsDoubles = (int)((sizeof(WarpVars) + 7) / 8);
 // The stacked Jacobian of a contact solve lives in shared memory when it is small (jsm): the region aliases what is dead
 // between the collision check and the motion estimate of the correction -- the scratch state's transforms, the joint
 // matrices and the capsule end points (all rebuilt before they are read again) -- plus whatever shared memory the robot
-// leaves free (jsm_extra).  Taller systems use the warp's global scratch slot.
+// leaves free (jsm_extra).  Once the corrections are COLLECTED the world->voxel transforms, the joint axes / origins and the
+// candidate list are dead as well (the next apply rebuilds what is needed): a system that outgrew the small store is moved
+// from the warp's global scratch slot into this larger one (jsm_big_ld) for the solve.  Only systems taller than that are
+// factored in global memory, where every load of the in-place update is an L2 round trip.
 struct WarpLayout {
     int S;        // vector slot (doubles) >= max(cfg_stride, D), even
     int L12;      // 12 * links
     int cfg;      // 3 * S
     int T;        // 3 * L12; state 2 is the LAST one and starts the jsm region
-    int G;        // L12: per link, (1/res) * inverse_origin * T_link  (world -> voxel coordinates in one transform)
+    int G;        // L12: per link, (1/res) * inverse_origin * T_link  (world -> voxel coordinates in one transform); after the jsm store
     int caps;     // 6 * L: world end points of every link's bounding capsule
     int M;        // 16 * J: joint_transform * motion(value), by columns
     int jsm;      // start of the shared-memory Jacobian store (= T + 2 * L12)
     int jsm_ld;   // its leading dimension
+    int jsm_big_ld;  // leading dimension of the larger store that opens up once the corrections are collected (see below)
     int jaxis, jorig;  // 3 * J each
     int target, scfg, act, ru, du, raw, stepv;  // S each
     int tn;       // noise_batch * S: truncated-normal draws of the next noise_batch microsteps
@@ -147,28 +151,31 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.noise_batch = 32 / D < 1 ? 1 : (32 / D > 8 ? 8 : 32 / D);
     int o = 0;
     w.cfg = o; o += 3 * S;
-    // kinematics<LINKED> runs the T chain (lanes 0..11) and the G chain (lanes 12..23) in the same instructions: their row loads
-    // must not share banks, so T starts 2 doubles (mod 16 = one bank cycle) after a multiple of 16 from G
-    w.G = o; o += w.L12;
-    o += (2 + 16 - (o - w.G) % 16) % 16;
     w.T = o; o += 3 * w.L12;
     w.jsm = w.T + 2 * w.L12;
     w.M = o; o += 16 * J;  // joint matrices, TRANSPOSED and padded: element (row k, column c) of joint j at 16 j + 4 c + k
     w.caps = o; o += 6 * L;
     o += jsm_extra;
-    {
-        // (D + 1) columns of jsm_ld doubles.  The solver's lane 4 g + i reads rows = i (mod 4) of column g: a leading dimension
-        // = 4 (mod 16) puts the 16 lanes of a half warp on 16 different bank pairs; take it when it costs at most a quarter
-        // of the rows
-        const int cap = (o - w.jsm) / (D + 1);
+    // (D + 1) columns of ld doubles.  The solver's lane 4 g + i reads rows = i (mod 4) of column g: a leading dimension
+    // = 4 (mod 16) puts the 16 lanes of a half warp on 16 different bank pairs; take it when it costs at most a quarter
+    // of the rows
+    auto pick_ld = [](int doubles, int columns) {
+        const int cap = doubles / columns;
         int ld = cap;
         const int pref = cap - ((cap - 4) & 15);
         if (cap >= 20 && pref >= 20 && pref * 4 >= cap * 3) ld = pref;
-        w.jsm_ld = ld < 0 ? 0 : ld;
-    }
+        return ld < 0 ? 0 : ld;
+    };
+    w.jsm_ld = pick_ld(o - w.jsm, D + 1);
+    // kinematics<LINKED> runs the T chain (lanes 0..11) and the G chain (lanes 12..23) in the same instructions: their row loads
+    // must not share banks, so T starts 2 doubles (mod 16 = one bank cycle) after a multiple of 16 from G
+    o += (14 + 16 - (o - w.T) % 16) % 16;
+    w.G = o; o += w.L12;
     w.jaxis = o; o += 3 * J;
     w.jorig = o; o += 3 * J;
     o = (o + 1) & ~1;
+    w.cand = o; o += 32;
+    w.jsm_big_ld = pick_ld(o - w.jsm, D + 1);
     w.target = o; o += S;
     w.scfg = o; o += S;
     w.act = o; o += S;
@@ -178,7 +185,6 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.stepv = o; o += S;
     w.tn = o; o += w.noise_batch * S;
     w.qr = o; o += S;
-    w.cand = o; o += 32;
     w.vars = o; o += kWarpVarsDoubles + 2 * S;
     w.stats = o; o += FKS_NUM_STATS;
     w.flags = o; o += 1;
@@ -242,6 +248,14 @@ struct LaunchArgs {
     unsigned long long* stats;
     unsigned int* counter;
     char* scratch;                   // per-warp-slot global scratch
+    // hand-over between the free-flight kernel and the contact kernel (kModeFree / kModeContact): parked particle states
+    // (park_stride bytes each, in arrival order), their sort keys, the processing order of the contact kernel, and
+    // park_meta = {count, histogram of the keys [kParkBuckets], scatter cursors [kParkBuckets]}
+    char* park;
+    unsigned int* park_key;
+    unsigned int* park_order;
+    unsigned int* park_meta;
+    int park_stride, _pad_park;
     unsigned long long n_particles, n_targets, seed, first_id;
     int allow_contacts, noise_mode, cfg_stride, rec_stride;
     int P, warps_per_block;
@@ -254,6 +268,14 @@ struct LaunchArgs {
     unsigned int trace_capacity;
     int trace_width;                 // doubles per record = max(cfg_stride, D)
 };
+
+// Simulate-kernel modes.  kModeAll: every particle from start to end in one kernel (step traces, allow_contacts == false).
+// The batch path runs two kernels back to back: kModeFree flies every particle until its first colliding microstep (or
+// to its end) and PARKS the colliding ones; kModeContact takes the parked particles -- earliest contact first, they have
+// the most work left -- and runs them to the end.  The CTAs of either kernel then hold particles of ONE regime: free
+// flight never waits for a contact solve, and a contact CTA's solver slots are full.
+enum { kModeAll = 0, kModeFree = 1, kModeContact = 2 };
+constexpr int kParkBuckets = 64;
 
 struct Frame {
     LaunchArgs a;
@@ -270,8 +292,12 @@ struct KernelInfo {
     size_t dyn_smem;
 };
 int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelInfo* out);
-int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
+int launch_simulate(int kind, int mode, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
                     const void* l2_window_base, size_t l2_window_bytes);
+// bytes of one parked particle state for this layout
+size_t park_record_bytes(const WarpLayout& wl);
+// turns the keys of the parked particles into the contact kernel's processing order (counting sort by key)
+int launch_park_order(const LaunchArgs& args, int grid, void* stream);
 // fills args.wl / pts_off / warps_off / warps_per_block and returns the dynamic shared memory size
 size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block, size_t smem_limit);
 int launch_check_config(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream, double inflation_ratio, unsigned char* out);

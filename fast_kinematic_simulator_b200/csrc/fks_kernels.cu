@@ -58,6 +58,16 @@ __device__ __forceinline__ void raise_flag(int wb, unsigned bits) {
 __device__ __forceinline__ void add_stat(int wb, int which, unsigned long long v) {  // lane 0 only
     reinterpret_cast<unsigned long long*>(wsd(wb) + frame().a.wl.stats)[which] += v;
 }
+// Read-modify-write of a per-warp bookkeeping word (WarpVars, shared memory, one copy per warp, every lane holds the same
+// view): all lanes read, THEN all lanes store the same new value -- under independent thread scheduling a lane that ran
+// ahead could otherwise have its store read back by a lagging lane and applied twice.
+template <class T>
+__device__ __forceinline__ T wv_add(T* field, T inc) {
+    const T v = *field + inc;
+    __syncwarp();
+    *field = v;
+    return v;
+}
 // global scratch of this warp
 __device__ __forceinline__ char* scratch_slot() {
     const LaunchArgs& a = frame().a;
@@ -94,6 +104,26 @@ __device__ __forceinline__ bool named_barrier_or(int id, int threads, bool pred)
     unsigned out;
     asm volatile(
         "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(out)
+        : "r"(id), "r"(threads), "r"((unsigned)pred)
+        : "memory");
+    return out != 0u;
+}
+
+// count / conjunction of a predicate over the threads of a named barrier
+__device__ __forceinline__ int named_barrier_popc(int id, int threads, bool pred) {
+    unsigned out;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.popc.u32 %0, %1, %2, q;\n\t}"
+        : "=r"(out)
+        : "r"(id), "r"(threads), "r"((unsigned)pred)
+        : "memory");
+    return (int)out;
+}
+__device__ __forceinline__ bool named_barrier_and(int id, int threads, bool pred) {
+    unsigned out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.and.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(out)
         : "r"(id), "r"(threads), "r"((unsigned)pred)
         : "memory");
@@ -680,9 +710,10 @@ __device__ __forceinline__ void select_normal(int wb, const DevEnv& e, uint2 ran
 // ------------------------------------------------------------------------------------------------
 // self collisions: CollectSelfCollisions (spcs:1183-1275) + ExtractSelfCollidingPoints (spcs:983-1171)
 //
-// Two points share a cell of edge map_res only if they are within sqrt(3)*map_res of each other, so a
-// capsule test over the DISALLOWED link pairs decides exactly when the hash-grid pass can be skipped (the
-// common case).  The exact pass keeps the reference's per-cell semantics.  Returns true when at least one
+// The cell keys truncate toward zero (LocationToExtendedGridIndex, spcs:1173-1181: (int64_t)(coordinate / resolution)), so
+// the cells at index 0 are TWICE as wide per axis (-res .. +res): two points share a cell only if they are within
+// 2 sqrt(3) map_res of each other.  A capsule test over the DISALLOWED link pairs with that bound decides exactly when the
+// hash-grid pass can be skipped (the common case).  The exact pass keeps the reference's per-cell semantics.  Returns true when at least one
 // point received a correction (self_collision_map non-empty); corrections are left in the scratch slot's
 // selfcorr array, per-point flags in sflag (bit 0).
 // ------------------------------------------------------------------------------------------------
@@ -991,7 +1022,7 @@ __device__ __forceinline__ bool collect_self(int wb, int Xprev, int Xcur) {
     if (rb.n_pairs == 0) return false;  // one link, or every pair allowed (spcs:1186-1197)
     const int lane = lane_id();
     const double* caps = wsd(wb) + fr.a.wl.caps;
-    const double diag = 1.7320508075688772 * fr.a.env.map_res * (1.0 + 1e-6) + 1e-9;
+    const double diag = 2.0 * 1.7320508075688772 * fr.a.env.map_res * (1.0 + 1e-6) + 1e-9;  // cells at index 0 are two cells wide
     unsigned cp[kPairChunks] = {0u, 0u, 0u, 0u};
     bool anyc = false;
     const int nch = (rb.n_pairs + 31) >> 5;
@@ -1037,9 +1068,9 @@ __device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur,
 
 // ------------------------------------------------------------------------------------------------
 // CollectPointCorrectionsAndJacobians (spcs:1818-1939): fills the stacked Jacobian (column major,
-// column D holds the corrections), rows in link-major point-minor order, into *store (leading dimension
-// *store_ld): the warp's shared-memory store when the candidate count fits it, else its global scratch slot.
-// Returns the number of rows.
+// column D holds the corrections), rows in link-major point-minor order: the first rows into the warp's
+// shared-memory store (leading dimension wl.jsm_ld), the rows beyond its capacity into the global scratch slot
+// (leading dimension sl.ldj, same row indices).  Returns the number of rows; place_system() decides where it is solved.
 //
 // Two passes.  Pass 1 is the cheap voxel test of check_env over all points, kBatch gathers in flight per
 // lane: EstimateDistance4d = f -/+ res/2 + (|.| <= sqrt(3)/2 res) cannot be negative when the raw cell value
@@ -1048,7 +1079,7 @@ __device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur,
 // normal lookup, the Jacobian row -- on the survivors only.
 // ------------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, bool has_self, double** store, int* store_ld) {
+__device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, bool has_self) {
     const Frame& fr = frame();
     const DevRobot& rb = fr.rb;
     const DevEnv& e = fr.a.env;
@@ -1124,12 +1155,11 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
         }
     }
     __syncwarp();
-    // the stacked system has at most 3 * ncand rows: small ones are built (and solved) in shared memory
-    const bool in_smem = 3 * ncand <= wl.jsm_ld;
-    double* A = in_smem ? ws + wl.jsm : Ag;
-    const int ld = in_smem ? wl.jsm_ld : fr.a.sl.ldj;
-    *store = A;
-    *store_ld = ld;
+    // Optimistic placement: rows go to the shared-memory store while they fit it (cap_s rows, a multiple of 3, so a point's
+    // three rows never straddle) and to the global store beyond; most candidates turn out not to penetrate, so most systems
+    // end up entirely in shared memory.  The caller completes the global copy when the system outgrew the small store.
+    double* As = ws + wl.jsm;
+    const int lds = wl.jsm_ld, cap_s = (wl.jsm_ld / 3) * 3, ldg = fr.a.sl.ldj;
     // ---- pass 2 -----------------------------------------------------------------------------------
     int npts = 0;
     for (int base = 0; base < ncand; base += 32) {
@@ -1183,6 +1213,9 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
         const unsigned mask = __ballot_sync(FKS_FULL, have);
         if (have) {
             const int row0 = 3 * (npts + __popc(mask & ((1u << lane) - 1u)));
+            const bool small = row0 < cap_s;
+            double* A = small ? As : Ag;
+            const int ld = small ? lds : ldg;
             double* b = A + (size_t)D * ld + row0;
             b[0] = cx;
             b[1] = cy;
@@ -1238,6 +1271,37 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     return 3 * npts;
 }
 
+// Where a collected system is solved: in the small shared-memory store when it fitted (nothing to do), in the larger one
+// that the end of the collection frees (world->voxel transforms, joint axes / origins, candidate list: all rebuilt before
+// they are read again) when it fits that, in the global scratch slot otherwise.
+__device__ __forceinline__ void place_system(int wb, int rows, int cols, double** store, int* store_ld) {
+    const Frame& fr = frame();
+    const WarpLayout& wl = fr.a.wl;
+    const int lane = lane_id();
+    double* ws = wsd(wb);
+    double* As = ws + wl.jsm;
+    double* Ag = reinterpret_cast<double*>(scratch_slot() + fr.a.sl.jstore);
+    const int lds = wl.jsm_ld, cap_s = (wl.jsm_ld / 3) * 3, ldg = fr.a.sl.ldj, ldb = wl.jsm_big_ld;
+    if (rows <= cap_s) {
+        *store = As;
+        *store_ld = lds;
+        return;
+    }
+    // complete the global copy (rows < cap_s were written to shared memory) ...
+    for (int c = 0; c <= cols; c++)
+        for (int r = lane; r < cap_s; r += 32) Ag[(size_t)c * ldg + r] = As[c * lds + r];
+    __syncwarp();
+    *store = Ag;
+    *store_ld = ldg;
+    if (rows > ldb) return;
+    // ... and bring the whole system into the larger shared-memory store
+    for (int c = 0; c <= cols; c++)
+        for (int r = lane; r < rows; r += 32) As[c * ldb + r] = Ag[(size_t)c * ldg + r];
+    __syncwarp();
+    *store = As;
+    *store_ld = ldb;
+}
+
 // ------------------------------------------------------------------------------------------------
 // ComputeResolverCorrectionStepStackedJacobian (spcs:1990-1998): x = J.colPivHouseholderQr().solve(c).
 //
@@ -1269,6 +1333,11 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
 // Parity mode (decision tape, fksgpu.h): the pivot order and the rank are taken from the tape, the solver's own are
 // still computed and a difference raises FKS_FLAG_DECISION_OVERRIDDEN; a record flagged OVERRIDE_SOLUTION replaces the
 // solve altogether.
+//
+// Resumable: the slowest solver warp gates its CTA's lock step, and a 90-row system costs four times a 24-row one.  A
+// system in the global store (= a tall one) therefore works off at most `budget` row-steps per call, parks the per-lane
+// state of the factorisation in the (then unused) shared-memory store and returns false; the caller comes back in the
+// next solver slot with resume = true.  Same operations in the same order: the result does not depend on the budget.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
@@ -1280,8 +1349,11 @@ __device__ __forceinline__ double quad_sum(unsigned mask, double p) {
     return add_rn(p, __shfl_xor_sync(mask, p, 1));
 }
 
+#ifndef FKS_QR_BUDGET
+#define FKS_QR_BUDGET (1 << 30)
+#endif
 template <int SLOTS>  // columns per quad: 1 for up to 8 columns (every robot of the reference), 2 for up to 16
-__device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows, int cols, int x_off) {
+__device__ __noinline__ bool colpiv_qr_lanes(int wb, double* A, int ld, int rows, int cols, int x_off, bool resume) {
     const Frame& fr = frame();
     const int lane = lane_id();
     double* ws = wsd(wb);
@@ -1289,11 +1361,13 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
     double* x = ws + x_off;
     const int g = lane >> 2, i = lane & 3;
     const unsigned quad = 0xFu << (lane & ~3);
+    double* park = ws + fr.a.wl.jsm;  // 4 doubles per lane + 8 uniform ones, only while a factorisation is paused
+    const bool pausable = SLOTS == 1 && A != park && fr.a.wl.jsm_ld * (cols + 1) >= 4 * 32 + 8;
     // ---- decision tape (parity mode only) ----------------------------------------------------------------------
     bool forced = false;
     int f_rank = 0;
     unsigned long long f_order = 0ull;
-    if (fr.a.dec_tape != nullptr) {
+    if (!resume && fr.a.dec_tape != nullptr) {
         const unsigned long long dp = wv->dec_pos;
         bool desync = true, replaced = false;
         if (dp < wv->dec_end) {
@@ -1317,42 +1391,86 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
             if (replaced) raise_flag(wb, FKS_FLAG_DECISION_OVERRIDDEN);
         }
         __syncwarp();
-        if (replaced) return;
+        if (replaced) return true;
     }
     const int size = rows < cols ? rows : cols;
     // per column slot of this quad: colNormsUpdated / colNormsDirect, the position in Eigen's permuted order, and this
     // lane's partial of sum_{r > k} a_r^2 for the coming step (= the tail's squared norm should the column be the pivot)
     double nu[SLOTS], nd[SLOTS], tailp[SLOTS];
     int pos[SLOTS];
-    double max_norm = 0.0;
-#pragma unroll
-    for (int sl = 0; sl < SLOTS; sl++) {
-        const int c = g + 8 * sl;
-        nu[sl] = nd[sl] = tailp[sl] = 0.0;
-        pos[sl] = c;
-        if (c < cols) {  // uniform inside the quad
-            const double* mine = A + (size_t)c * ld;
-            double pf = 0.0, pt = 0.0;
-            for (int r = i; r < rows; r += 4) {
-                const double a = mine[r];
-                const double sq = mul_rn(a, a);
-                pf = add_rn(pf, sq);
-                if (r >= 1) pt = add_rn(pt, sq);
-            }
-            nd[sl] = nu[sl] = sqrt(quad_sum(quad, pf));
-            tailp[sl] = pt;
-            max_norm = fmax(max_norm, nu[sl]);
-        }
-    }
-    max_norm = warp_max(max_norm);
-    const double me = mul_rn(max_norm, DBL_EPSILON);
-    const double threshold_helper = div_rn(mul_rn(me, me), (double)rows);
-    const double norm_downdate_threshold = 1.4901161193847656e-08;  // sqrt(epsilon)
-    int own_rank = size, nonzero_pivots = size;
+    double max_norm = 0.0, threshold_helper = 0.0;
+    int own_rank = size, nonzero_pivots = size, k0 = 0;
     unsigned long long order = 0ull;  // 4 bits per position: the column sitting there
     bool differed = false, near_cut = false;
+    if (!resume) {
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; sl++) {
+            const int c = g + 8 * sl;
+            nu[sl] = nd[sl] = tailp[sl] = 0.0;
+            pos[sl] = c;
+            if (c < cols) {  // uniform inside the quad
+                const double* mine = A + (size_t)c * ld;
+                double pf = 0.0, pt = 0.0;
+                for (int r = i; r < rows; r += 4) {
+                    const double a = mine[r];
+                    const double sq = mul_rn(a, a);
+                    pf = add_rn(pf, sq);
+                    if (r >= 1) pt = add_rn(pt, sq);
+                }
+                nd[sl] = nu[sl] = sqrt(quad_sum(quad, pf));
+                tailp[sl] = pt;
+                max_norm = fmax(max_norm, nu[sl]);
+            }
+        }
+        max_norm = warp_max(max_norm);
+        const double me = mul_rn(max_norm, DBL_EPSILON);
+        threshold_helper = div_rn(mul_rn(me, me), (double)rows);
+    } else {
+        // pick the factorisation up where the previous solver slot left it
+        nu[0] = park[4 * lane];
+        nd[0] = park[4 * lane + 1];
+        tailp[0] = park[4 * lane + 2];
+        pos[0] = __double2loint(park[4 * lane + 3]);
+#pragma unroll
+        for (int sl = 1; sl < SLOTS; sl++) nu[sl] = nd[sl] = tailp[sl] = 0.0, pos[sl] = 0;
+        const double* u = park + 4 * 32;
+        max_norm = u[0];
+        threshold_helper = u[1];
+        order = (unsigned long long)__double_as_longlong(u[2]);
+        f_order = (unsigned long long)__double_as_longlong(u[3]);
+        k0 = __double2loint(u[4]);
+        own_rank = __double2hiint(u[4]);
+        nonzero_pivots = __double2loint(u[5]);
+        f_rank = __double2hiint(u[5]);
+        const int bits = __double2loint(u[6]);
+        forced = (bits & 1) != 0;
+        differed = (bits & 2) != 0;
+        near_cut = (bits & 4) != 0;
+        __syncwarp();
+    }
+    const double norm_downdate_threshold = 1.4901161193847656e-08;  // sqrt(epsilon)
+    int work = 0;
 #pragma unroll 1
-    for (int k = 0; k < size; k++) {
+    for (int k = k0; k < size; k++) {
+        if (pausable && work >= FKS_QR_BUDGET) {
+            park[4 * lane] = nu[0];
+            park[4 * lane + 1] = nd[0];
+            park[4 * lane + 2] = tailp[0];
+            park[4 * lane + 3] = __hiloint2double(0, pos[0]);
+            if (lane == 0) {
+                double* u = park + 4 * 32;
+                u[0] = max_norm;
+                u[1] = threshold_helper;
+                u[2] = __longlong_as_double((long long)order);
+                u[3] = __longlong_as_double((long long)f_order);
+                u[4] = __hiloint2double(own_rank, k);
+                u[5] = __hiloint2double(f_rank, nonzero_pivots);
+                u[6] = __hiloint2double(0, (forced ? 1 : 0) | (differed ? 2 : 0) | (near_cut ? 4 : 0));
+            }
+            __syncwarp();
+            return false;
+        }
+        work += rows - k;
         // biggest updated norm among the positions k .. cols-1, the first position wins (Eigen's maxCoeff scan)
         double bv = -1.0;
         int bp = 0x7fffffff, bc = 0;
@@ -1401,6 +1519,14 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
         if (own_rank == size && big_sq < cut) own_rank = k;
         if (max_norm > 0.0 && big_sq > 0.0 && big_sq < cut * 1e6) near_cut = true;
         nonzero_pivots = forced ? (f_rank < size ? f_rank : size) : own_rank;
+        // Eigen carries the factorisation on after the cut ("to make sure that the initial matrix is properly reproduced"), but
+        // its solve reads the first nonzero_pivots reflectors and the leading nonzero_pivots x nonzero_pivots triangle only,
+        // and nonzero_pivots never changes once set: nothing computed from here on reaches the solution.
+        if (k >= nonzero_pivots) {
+            if (forced && own_rank != nonzero_pivots) differed = true;
+            own_rank = nonzero_pivots;
+            break;
+        }
         // the column that sat at position k takes the pivot's old position (m_qr.col(k).swap(m_qr.col(biggest)))
         double tail_sq = 0.0;
 #pragma unroll
@@ -1434,13 +1560,16 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
         // applyHouseholderOnTheLeft to the remaining columns; to the right-hand side only below the rank cut (Eigen's solve
         // applies the first nonzero_pivots reflectors to c).  The loop that updates a column also accumulates the squared
         // norms of its rows > k (a downdate may need it) and > k + 1 (the next tail).
+        // In the LAST step the remaining columns end up at positions >= size, which the solve never reads: only the
+        // right-hand side is reflected.
         const bool last_row = rows - k == 1;
+        const bool last_step = k == size - 1;
         const int r0 = k + 1 + ((i - (k + 1)) & 3);  // first row > k that is = i (mod 4)
 #pragma unroll
         for (int sl = 0; sl < SLOTS; sl++) {
             const int c = g + 8 * sl;
             const bool is_col = c < cols;
-            if (!((is_col && pos[sl] > k) || (c == cols && nonzero_pivots > k))) continue;  // uniform inside the quad
+            if (!((is_col && pos[sl] > k && !last_step) || (c == cols && nonzero_pivots > k))) continue;  // uniform inside the quad
             double* mine = A + (size_t)c * ld;
             double ak = mine[k];
             double tmp = 0.0;
@@ -1488,25 +1617,34 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
         if (near_cut) raise_flag(wb, FKS_FLAG_NEAR_RANK_CUT);
         if (forced && (differed || own_rank != nonzero_pivots)) raise_flag(wb, FKS_FLAG_DECISION_OVERRIDDEN);
     }
-    // solve: back substitution on the leading nonzero_pivots x nonzero_pivots triangle, the other unknowns zero
+    // solve: back substitution on the leading nonzero_pivots x nonzero_pivots triangle, the other unknowns zero.  Lane j holds
+    // position j: its column, c_j, then x_j.  Row ii: the products R(ii, j) x_j are formed by their lanes, lane ii subtracts them
+    // in ascending j (Eigen's triangular solve, the oracle's order) and divides by the diagonal.
     if (lane < cols) x[lane] = 0.0;
     __syncwarp();
-    if (lane == 0 && nonzero_pivots > 0) {
-        double* rhs = A + (size_t)cols * ld;
+    {
+        const double* rhs = A + (size_t)cols * ld;
+        const bool mine_pos = lane < nonzero_pivots;
+        const int my_col = (int)((order >> (4 * (mine_pos ? lane : 0))) & 0xFull);
+        const double* colp = A + (size_t)my_col * ld;
+        double xj = mine_pos ? rhs[lane] : 0.0;  // c_j until row j is solved
+#pragma unroll 1
         for (int ii = nonzero_pivots - 1; ii >= 0; ii--) {
-            double s = rhs[ii];
-            for (int j = ii + 1; j < nonzero_pivots; j++)
-                s = sub_rn(s, mul_rn(A[(size_t)((order >> (4 * j)) & 0xFull) * ld + ii], rhs[j]));
-            rhs[ii] = div_rn(s, A[(size_t)((order >> (4 * ii)) & 0xFull) * ld + ii]);
+            const double prod = (mine_pos && lane > ii) ? mul_rn(colp[ii], xj) : 0.0;
+            double sacc = xj;  // meaningful in lane ii
+            for (int j = ii + 1; j < nonzero_pivots; j++) sacc = sub_rn(sacc, __shfl_sync(FKS_FULL, prod, j));
+            if (lane == ii) xj = div_rn(sacc, colp[ii]);
         }
-        for (int ii = 0; ii < nonzero_pivots; ii++) x[(order >> (4 * ii)) & 0xFull] = rhs[ii];
+        if (mine_pos) x[my_col] = xj;
     }
     __syncwarp();
+    return true;
 }
-// the solver for `cols` unknowns (+ the right-hand side): one column per quad when they fit 8 quads
-__device__ __forceinline__ void colpiv_qr_solve(int wb, double* A, int ld, int rows, int cols, int x_off) {
-    if (cols + 1 <= 8) colpiv_qr_lanes<1>(wb, A, ld, rows, cols, x_off);
-    else colpiv_qr_lanes<2>(wb, A, ld, rows, cols, x_off);
+// the solver for `cols` unknowns (+ the right-hand side): one column per quad when they fit 8 quads.  Returns false when
+// the factorisation was paused (call again with resume = true in the next solver slot).
+__device__ __forceinline__ bool colpiv_qr_solve(int wb, double* A, int ld, int rows, int cols, int x_off, bool resume) {
+    if (cols + 1 <= 8) return colpiv_qr_lanes<1>(wb, A, ld, rows, cols, x_off, resume);
+    return colpiv_qr_lanes<2>(wb, A, ld, rows, cols, x_off, resume);
 }
 
 // actuator noise of the next `count` microsteps, one truncated-normal draw per axis in axis order
@@ -1564,6 +1702,14 @@ __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned
 #ifndef FKS_G1_ROUNDS
 #define FKS_G1_ROUNDS(kind) ((kind) == FKS_ROBOT_LINKED ? 3 : 4)
 #endif
+#ifndef FKS_GROUPS
+#define FKS_GROUPS 1
+#endif
+// 0: a warp that needs a contact solve waits for the next super-cycle's slot; 1: it joins the running slot while any solver
+// of it is still busy; 2: while fewer than half of the slot's original solvers have finished
+#ifndef FKS_LATE_JOIN
+#define FKS_LATE_JOIN 0
+#endif
 #ifndef FKS_SLOT_ITERATIONS
 #define FKS_SLOT_ITERATIONS(kind) ((kind) == FKS_ROBOT_SE2 ? 1 : 0)
 #endif
@@ -1581,13 +1727,14 @@ enum {
     AF_FAIL_KIN,        // previous configuration restored after a failed resolve
     AF_STOP_KIN,        // previous configuration restored after a collision with allow_contacts == false
     AF_NOCONTACT_KIN,   // step-start configuration restored -> the particle ends
+    AF_RESUME,          // contact kernel: the previous state of a parked particle is rebuilt -> rebuild and check the current one
     AF_DONE             // no particles left
 };
 }  // namespace
 
 // TRACE = true is the single-particle instantiation that records the step trace (fks_forward_simulate_traced); the batch
 // kernel carries none of it.
-template <int KIND, bool TRACE = false>
+template <int KIND, bool TRACE = false, int MODE = kModeAll>
 __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_kernel(const __grid_constant__ LaunchArgs args) {
     // ---- stage parameters, robot and points into shared memory, once per CTA ---------------------
     {
@@ -1621,7 +1768,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 ha += da * da;
                 hb += db * db;
             }
-            const double diag = 1.7320508075688772 * args.env.map_res * (1.0 + 1e-6) + 1e-9;
+            const double diag = 2.0 * 1.7320508075688772 * args.env.map_res * (1.0 + 1e-6) + 1e-9;
             const double reach = (0.5 * sqrt(ha) + 0.5 * sqrt(hb) + r->cap_radius[la] + r->cap_radius[lb] + diag) * (1.0 + 1e-9);
             f->pair_reach_sq[q] = reach * reach;
         }
@@ -1666,12 +1813,18 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
     // contact solve (group 2: collect + QR, barrier 2), the others (group 1) do not wait for them: they keep
     // running lock-step A / B / T rounds among themselves on barrier 1 until group 2 is finished.  Two code
     // regions are live at any time instead of one -- still a few KB each.
-    const int n_warps = a.warps_per_block;
-    volatile unsigned* g2_done = reinterpret_cast<volatile unsigned*>(smem_raw + a.sync_off);
+    // The CTA's warps form FKS_GROUPS independent lock-step groups (named barriers 1 + 2 g / 2 + 2 g): while one group is
+    // in a solver slot another one is usually in a round, which evens out the number of warps that can issue.
+    const int wpg = (a.warps_per_block + FKS_GROUPS - 1) / FKS_GROUPS;
+    const int grp = (int)(threadIdx.x >> 5) / wpg;
+    const int n_warps = min(wpg, a.warps_per_block - grp * wpg);
+    const int bar_full = 1 + 2 * grp, bar_g1 = 2 + 2 * grp;
+    volatile unsigned* g2_done = reinterpret_cast<volatile unsigned*>(smem_raw + a.sync_off) + 2 * grp;  // solvers that finished
+    volatile unsigned* g2_late = g2_done + 1;  // warps that joined the running slot late (FKS_LATE_JOIN)
     bool want_solve = false;
     int free_rounds = 0, free_streak = 0;  // rounds the next super-cycle runs before its first CTA barrier (free flight only)
     for (;;) {
-        int bar_id = 0, bar_threads = 32 * n_warps, n_solvers = 0;
+        int bar_id = bar_full, bar_threads = 32 * n_warps, n_solvers = 0;
         bool counted_solver = false;
         int slot_iter = 0;
         constexpr int kSlotIters = FKS_SLOT_ITERATIONS(KIND);
@@ -1712,6 +1865,30 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         unsigned long long next_id = 0ull;
                         if (lane == 0) next_id = (unsigned long long)atomicAdd(a.counter, 1u);
                         next_id = __shfl_sync(FKS_FULL, next_id, 0);
+                        if (MODE == kModeContact) {
+                            // a particle the free-flight kernel parked at its first colliding microstep
+                            if (next_id >= (unsigned long long)a.park_meta[0]) {
+                                after = AF_DONE;
+                                break;
+                            }
+                            const double* rec = reinterpret_cast<const double*>(a.park + (size_t)a.park_order[next_id] * a.park_stride);
+                            const int span = wl.stats - wl.target;
+                            for (int e = lane; e < 3 * S; e += 32) ws[wl.cfg + e] = rec[e];
+                            for (int e = lane; e < span; e += 32) ws[wl.target + e] = rec[3 * S + e];
+                            const int2 hdr = *reinterpret_cast<const int2*>(rec + 3 * S + span);
+                            if (lane == 0) *reinterpret_cast<unsigned*>(ws + wl.flags) = *reinterpret_cast<const unsigned*>(rec + 3 * S + span + 1);
+                            cur = hdr.x;
+                            prev = hdr.y;
+                            cc = 0u;
+                            __syncwarp();
+                            // the link transforms are not parked: rebuild the previous state, then the current one with its check
+                            // (the same check that sent the particle here: it ends in AF_MICRO_CHECK with the same answer)
+                            op = OP_KIN;
+                            op_out = prev;
+                            op_derive = 0;
+                            after = AF_RESUME;
+                            break;
+                        }
                         wv->pid = next_id;  // every lane stores the same value
                         if (next_id >= a.n_particles) {
                             after = AF_DONE;
@@ -1742,6 +1919,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             wv->dec_end = a.dec_off[wv->pid + 1];
                         }
                         wv->collided = wv->any_resolve_failed = false;
+                        wv->qr_rows = 0;
                         wv->flags = wv->n_micro_total = wv->n_iter_total = wv->n_steps = 0u;
                         wv->step = 0u;
                         op = OP_KIN;
@@ -1750,6 +1928,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         after = AF_INIT;
                         break;
                     }
+                    case AF_RESUME:
+                        op = OP_KIN;
+                        op_out = cur;
+                        op_derive = 1;
+                        measure = M_CHECK;
+                        after = AF_MICRO_CHECK;
+                        break;
                     case AF_INIT:
                         ev = 1;
                         break;
@@ -1788,7 +1973,28 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             if (in_collision && !a.allow_contacts)
                                 trace_append(FKS_TRACE_RETURNED_PREVIOUS, wv->step, wv->micro, 0u, ws + wl.cfg + prev * S, stride);  // spcs:1778
                         }
-                        if (in_collision && a.allow_contacts) {
+                        if (in_collision && a.allow_contacts && MODE == kModeFree) {
+                            // free-flight kernel: the particle leaves for the contact kernel as it is (configurations, control
+                            // vectors, noise batch, bookkeeping; transforms are rebuilt there), keyed by how early it got here
+                            unsigned slot = 0u;
+                            const unsigned key = wv->step < (unsigned)(kParkBuckets - 1) ? wv->step : (unsigned)(kParkBuckets - 1);
+                            if (lane == 0) {
+                                slot = atomicAdd(a.park_meta, 1u);
+                                atomicAdd(a.park_meta + 1 + key, 1u);
+                                a.park_key[slot] = key;
+                            }
+                            slot = __shfl_sync(FKS_FULL, slot, 0);
+                            double* rec = reinterpret_cast<double*>(a.park + (size_t)slot * a.park_stride);
+                            const int span = wl.stats - wl.target;
+                            for (int e = lane; e < 3 * S; e += 32) rec[e] = ws[wl.cfg + e];
+                            for (int e = lane; e < span; e += 32) rec[3 * S + e] = ws[wl.target + e];
+                            if (lane == 0) {
+                                *reinterpret_cast<int2*>(rec + 3 * S + span) = make_int2(cur, prev);
+                                *reinterpret_cast<unsigned*>(rec + 3 * S + span + 1) = *reinterpret_cast<const unsigned*>(ws + wl.flags);
+                            }
+                            __syncwarp();
+                            after = AF_FETCH;
+                        } else if (in_collision && a.allow_contacts) {
                             wv->resolver_iterations = 0u;
                             wv->scaling = sp.initial_step;
                             want_solve = true;
@@ -1799,8 +2005,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             op = OP_KIN; op_out = cur; op_derive = 1;
                             after = AF_STOP_KIN;
                         } else {
-                            wv->micro++;
-                            ev = (wv->micro < wv->number_microsteps) ? 2 : 3;
+                            ev = (wv_add(&wv->micro, 1u) < wv->number_microsteps) ? 2 : 3;
                         }
                         break;
                     }
@@ -1815,8 +2020,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                     }
                     case AF_RESOLVE_CHECK: {  // spcs:1694-1761
                         const bool in_collision = (cc & 1u) != 0u;
-                        wv->resolver_iterations++;
-                        wv->n_iter_total++;
+                        wv_add(&wv->resolver_iterations, 1u);
+                        wv_add(&wv->n_iter_total, 1u);
+                        __syncwarp();
                         if (TRACE) {
                             __syncwarp();
                             trace_append(FKS_TRACE_RESOLUTION_STEP, wv->step, wv->micro, wv->resolver_iterations, ws + wl.cfg + cur * S, stride);  // spcs:1703
@@ -1836,18 +2042,20 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             break;
                         }
                         if ((wv->resolver_iterations % sp.decay_iters) == 0u) {  // spcs:1747-1761
-                            if (wv->scaling >= 0.0) {
-                                wv->scaling = wv->scaling * sp.decay_rate;
-                                if (wv->scaling < sp.min_scaling) wv->scaling = -sp.min_scaling;
+                            double sc = wv->scaling;
+                            if (sc >= 0.0) {
+                                sc = sc * sp.decay_rate;
+                                if (sc < sp.min_scaling) sc = -sp.min_scaling;
                             } else {
-                                wv->scaling = -sp.min_scaling;
+                                sc = -sp.min_scaling;
                             }
+                            __syncwarp();
+                            wv->scaling = sc;
                         }
                         if (in_collision) {
                             want_solve = true;
                         } else {
-                            wv->micro++;
-                            ev = (wv->micro < wv->number_microsteps) ? 2 : 3;
+                            ev = (wv_add(&wv->micro, 1u) < wv->number_microsteps) ? 2 : 3;
                         }
                         break;
                     }
@@ -1864,7 +2072,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             } else if (ev == 1) {
                 // ---- begin controller step: GenerateControlAction (tnuva:179-198, :384-412, :598-614) --------
                 ev = 0;
-                wv->n_steps++;
+                wv_add(&wv->n_steps, 1u);
                 double* cfg = ws + wl.cfg + cur * S;
                 if (!a.allow_contacts) {  // a colliding wv->step is discarded as a whole: keep the wv->step's start (spcs:904-909)
                     if (lane < stride) ws[wl.scfg + lane] = cfg[lane];
@@ -1916,7 +2124,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             } else if (ev == 2) {
                 // ---- begin microstep (spcs:1590-1608) ---------------------------------------------------------
                 ev = 0;
-                wv->n_micro_total++;
+                wv_add(&wv->n_micro_total, 1u);
                 const int nb = wl.noise_batch;
                 const int slot = (int)(wv->micro % (unsigned)nb);
                 if (slot == 0) {
@@ -1924,7 +2132,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                     fill_noise(wb, wv->pid, wv->step, wv->micro, left < (unsigned)nb ? (int)left : nb, wv->tape_pos, wv->tape_end);
                 }
                 if (a.noise_mode == FKS_NOISE_INJECTED && wv->tape_pos + (unsigned long long)D > wv->tape_end) wv->flags |= FKS_FLAG_TAPE_EXHAUSTED;
-                wv->tape_pos += (unsigned long long)D;
+                wv_add(&wv->tape_pos, (unsigned long long)D);
                 // previous_configuration (spcs:1597) is the old current state; the new one is built in the other buffer
                 prev = cur;
                 cur ^= 1;
@@ -1988,8 +2196,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             ends = true;
                         }
                     }
-                    wv->step++;
-                    if (!ends && wv->step < sp.n_steps) ev = 1;
+                    const unsigned next_step = wv_add(&wv->step, 1u);
+                    if (!ends && next_step < sp.n_steps) ev = 1;
                     else ev = 4;
                 } else {
                     // robot->SetPosition(resolved_configuration) is skipped: the particle stays where the wv->step began
@@ -2030,7 +2238,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         } else {
             if (round < free_rounds) continue;  // free flight: a CTA barrier every (free_rounds + 1) rounds only
             if (round == free_rounds) {
-                n_solvers = __syncthreads_count(want_solve) >> 5;  // full barrier; the count is in threads
+                n_solvers = named_barrier_popc(bar_full, 32 * n_warps, want_solve) >> 5;  // barrier of the whole group; the count is in threads
                 FKS_TICK(5)
 #ifdef FKS_PHASE_TIMERS
                 textra[0] += 1;
@@ -2039,14 +2247,35 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 if (n_solvers == 0) break;         // nobody solves: next super-cycle
                 counted_solver = want_solve;       // group 2 goes to collect + solve (below)
                 if (!counted_solver) {
-                    bar_id = 1;                    // group 1 keeps going on its own barrier
+                    bar_id = bar_g1;               // group 1 keeps going on its own barrier
                     bar_threads = 32 * (n_warps - n_solvers);
                 }
             }
+#if FKS_LATE_JOIN
+            if (!counted_solver && round > free_rounds) {
+                // LATE JOINERS.  A group-1 warp whose round ended in a collision would otherwise idle until the next super-cycle's
+                // slot; while the slot of this one is still running it leaves group 1 (the others learn how many left from the
+                // barrier's count) and runs its own collect + solve + estimate right away.
+                bool leave = false;
+                if (want_solve) {
+                    unsigned ok = 0u;
+                    if (lane == 0)
+                        ok = (FKS_LATE_JOIN == 1) ? (*g2_done < (unsigned)n_solvers + *g2_late) : (2u * *g2_done < (unsigned)n_solvers);
+                    leave = __shfl_sync(FKS_FULL, ok, 0) != 0u;
+                }
+                const int n_leave = named_barrier_popc(bar_g1, bar_threads, leave) >> 5;
+                if (leave) {
+                    counted_solver = true;
+                    if (lane == 0) atomicAdd(const_cast<unsigned*>(g2_late), 1u);
+                } else {
+                    bar_threads -= 32 * n_leave;
+                }
+            }
+#endif
             if (!counted_solver) {
                 // group 1 only: another round while group 2 is still busy (decision made uniform by the barrier reduction)
-                const bool keep = (*g2_done < (unsigned)n_solvers) && (round < FKS_G1_ROUNDS(KIND) * (kSlotIters > 1 ? kSlotIters : 1));
-                const bool go_on = named_barrier_or(1, bar_threads, keep);
+                const bool keep = (*g2_done < (unsigned)n_solvers + *g2_late) && (round < FKS_G1_ROUNDS(KIND) * (kSlotIters > 1 ? kSlotIters : 1));
+                const bool go_on = named_barrier_or(bar_g1, bar_threads, keep);
                 FKS_TICK(1)
 #ifdef FKS_PHASE_TIMERS
                 textra[2] += 1;
@@ -2056,15 +2285,22 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             }
         }
         // =========================== solver slot: phase C, collect corrections (spcs:1627) ==============
+        if (MODE == kModeFree) break;  // (never reached: the free-flight kernel parks a particle instead of solving)
         {
             int rows = 0;
 #ifdef FKS_PHASE_TIMERS
             const long long tc0 = clock64();
 #endif
-            double* jstore = nullptr;
-            int jld = 0;
-            rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u, &jstore, &jld);
-            if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
+            double* jstore = reinterpret_cast<double*>(scratch_slot() + a.sl.jstore);
+            int jld = a.sl.ldj;
+            const bool resumed = wv->qr_rows > 0;  // a tall system whose factorisation was paused in the previous slot
+            if (resumed) {
+                rows = wv->qr_rows;
+            } else {
+                rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
+                if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
+                if (rows > 0) place_system(wb, rows, D, &jstore, &jld);
+            }
 #ifdef FKS_PHASE_TIMERS
             tacc[10] += clock64() - tc0;
             tacc[11] += 1;
@@ -2075,6 +2311,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #ifdef FKS_PHASE_TIMERS
             const long long tq0 = clock64();
 #endif
+            bool solved = true;
             if (rows == 0) {
                 // Eigen would return an empty vector and ApplyControlInput would assert; documented device
                 // behaviour: zero correction wv->step
@@ -2082,14 +2319,17 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 if (lane < D) ws[wl.raw + lane] = 0.0;
                 __syncwarp();
             } else {
-                colpiv_qr_solve(wb, jstore, jld, rows, D, wl.raw);
+                solved = colpiv_qr_solve(wb, jstore, jld, rows, D, wl.raw, resumed);
+                __syncwarp();
+                if (lane == 0) wv->qr_rows = solved ? 0 : rows;
+                __syncwarp();
             }
 #ifdef FKS_PHASE_TIMERS
-            if (rows <= 64) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
+            if (jstore == ws + wl.jsm) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
 #endif
             // motion estimate of the raw correction (spcs:1630) in the same solver slot: one lock-step round per
             // resolver iteration instead of two
-            {
+            if (solved) {
 #ifdef FKS_PHASE_TIMERS
             const long long te0 = clock64();
 #endif
@@ -2107,9 +2347,9 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             measure = M_CHECK;
             after = AF_RESOLVE_CHECK;
             want_solve = false;
-            }
+            }  // a paused warp keeps want_solve: it is a solver of the next slot again and skips the rounds until then
             slot_iter++;
-            if (kSlotIters == 0) break;
+            if (!solved || kSlotIters == 0) break;
         }
         }  // rounds
         if (counted_solver) {
@@ -2121,10 +2361,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         // not delay the next slot)
         free_streak = (n_solvers == 0) ? free_streak + 1 : 0;
         free_rounds = (free_streak >= 4) ? FKS_FREE_ROUNDS : 0;
-        const bool all_done = __syncthreads_and(after == AF_DONE && !want_solve);
+        const bool all_done = named_barrier_and(bar_full, 32 * n_warps, after == AF_DONE && !want_solve);
         FKS_TICK(9)
         if (all_done) break;
-        if (threadIdx.x == 0) *g2_done = 0u;  // next read is at least two full barriers away
+        if ((int)threadIdx.x == 32 * grp * wpg) {  // next read is at least two full barriers away
+            *g2_done = 0u;
+            *g2_late = 0u;
+        }
     }
 #ifdef FKS_PHASE_TIMERS
     if (lane == 0)
@@ -2162,7 +2405,7 @@ __device__ __noinline__ bool self_collision_bool(int wb, int X, double check_res
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch_slot() + fr.a.sl.keys);
-    const double diag = 1.7320508075688772 * check_resolution * (1.0 + 1e-6) + 1e-9;
+    const double diag = 2.0 * 1.7320508075688772 * check_resolution * (1.0 + 1e-6) + 1e-9;  // cells at index 0 are two cells wide
     bool found = false;
     bool keys_ready = false;
     const int nch = (rb.n_pairs + 31) >> 5;
@@ -2244,7 +2487,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) check_config
                 ha += da * da;
                 hb += db * db;
             }
-            const double diag = 1.7320508075688772 * args.env.map_res * (1.0 + 1e-6) + 1e-9;
+            const double diag = 2.0 * 1.7320508075688772 * args.env.map_res * (1.0 + 1e-6) + 1e-9;
             const double reach = (0.5 * sqrt(ha) + 0.5 * sqrt(hb) + r->cap_radius[la] + r->cap_radius[lb] + diag) * (1.0 + 1e-9);
             f->pair_reach_sq[q] = reach * reach;
         }
@@ -2283,7 +2526,7 @@ __global__ void __launch_bounds__(128) qr_solve_kernel(double* work, const unsig
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        f->a.wl = make_warp_layout(1, 0, cols, cols);
+        f->a.wl = make_warp_layout(1, 0, cols, cols, 160);  // room for the state of a paused factorisation
         f->a.warps_off = (int)((sizeof(Frame) + 15) & ~(size_t)15);
     }
     __syncthreads();
@@ -2295,7 +2538,8 @@ __global__ void __launch_bounds__(128) qr_solve_kernel(double* work, const unsig
     for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps_total) {
         if (lane == 0) *reinterpret_cast<unsigned*>(ws + fr.a.wl.flags) = 0u;
         __syncwarp();
-        colpiv_qr_solve(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw);
+        bool done = colpiv_qr_solve(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw, false);
+        while (!done) done = colpiv_qr_solve(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw, true);  // tall systems pause
         if (lane < cols) x_out[(size_t)i * cols + lane] = ws[fr.a.wl.raw + lane];
         if (lane == 0) flags_out[i] = *reinterpret_cast<const unsigned*>(ws + fr.a.wl.flags);
         __syncwarp();
@@ -2353,6 +2597,8 @@ size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stri
         long long e = want < spare ? want : spare;
         if (e < 0) e = 0;
         extra = (int)(e & ~1ll);
+        // (the layout pads for alignment: step back until the CTA fits again)
+        while (extra > 0 && warps_off + (size_t)warps_per_block * make_warp_layout(L, J, D, stride, extra).total * 8 + 16 > smem_limit) extra -= 2;
     }
     args->wl = make_warp_layout(L, J, D, stride, extra);
     args->pts_off = (int)pts_off;
@@ -2363,13 +2609,43 @@ size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stri
     return off;
 }
 
-static const void* kernel_ptr(int kind, bool trace = false) {
+template <int KIND>
+static const void* kernel_ptr_of(bool trace, int mode) {
+    if (trace) return (const void*)simulate_kernel<KIND, true, kModeAll>;
+    if (mode == kModeFree) return (const void*)simulate_kernel<KIND, false, kModeFree>;
+    if (mode == kModeContact) return (const void*)simulate_kernel<KIND, false, kModeContact>;
+    return (const void*)simulate_kernel<KIND, false, kModeAll>;
+}
+static const void* kernel_ptr(int kind, bool trace = false, int mode = kModeAll) {
     switch (kind) {
-        case FKS_ROBOT_SE2: return trace ? (const void*)simulate_kernel<FKS_ROBOT_SE2, true> : (const void*)simulate_kernel<FKS_ROBOT_SE2>;
-        case FKS_ROBOT_SE3: return trace ? (const void*)simulate_kernel<FKS_ROBOT_SE3, true> : (const void*)simulate_kernel<FKS_ROBOT_SE3>;
-        case FKS_ROBOT_LINKED: return trace ? (const void*)simulate_kernel<FKS_ROBOT_LINKED, true> : (const void*)simulate_kernel<FKS_ROBOT_LINKED>;
+        case FKS_ROBOT_SE2: return kernel_ptr_of<FKS_ROBOT_SE2>(trace, mode);
+        case FKS_ROBOT_SE3: return kernel_ptr_of<FKS_ROBOT_SE3>(trace, mode);
+        case FKS_ROBOT_LINKED: return kernel_ptr_of<FKS_ROBOT_LINKED>(trace, mode);
     }
     return nullptr;
+}
+
+size_t park_record_bytes(const WarpLayout& wl) { return (size_t)(3 * wl.S + (wl.stats - wl.target) + 2) * 8; }
+
+// Counting sort of the parked particles by key (the controller step of their first contact: the earlier, the more work is
+// left): order[base[key] + i] = arrival index.  The order inside a bucket does not matter (it only schedules).
+__global__ void park_order_kernel(unsigned* meta, const unsigned* key, unsigned* order) {
+    __shared__ unsigned base[kParkBuckets];
+    const unsigned count = meta[0];
+    if (threadIdx.x < kParkBuckets) {
+        unsigned b = 0u;
+        for (int i = 0; i < (int)threadIdx.x; i++) b += meta[1 + i];
+        base[threadIdx.x] = b;
+    }
+    __syncthreads();
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        const unsigned b = key[e];
+        order[base[b] + atomicAdd(meta + 1 + kParkBuckets + b, 1u)] = e;
+    }
+}
+int launch_park_order(const LaunchArgs& args, int grid, void* stream) {
+    park_order_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(args.park_meta, args.park_key, args.park_order);
+    return (int)cudaGetLastError();
 }
 
 int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelInfo* out) {
@@ -2391,10 +2667,10 @@ int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelI
     return 0;
 }
 
-int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
+int launch_simulate(int kind, int mode, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
                     const void* l2_window_base, size_t l2_window_bytes) {
     const int block_threads = 32 * args.warps_per_block;
-    const void* fn = kernel_ptr(kind, args.trace != nullptr);
+    const void* fn = kernel_ptr(kind, args.trace != nullptr, mode);
     if (!fn) return (int)cudaErrorInvalidValue;
     {
         // the attribute is per function and per device, and simulators of the same robot kind share the function: set it for
@@ -2449,7 +2725,7 @@ int launch_check_config(int kind, const LaunchArgs& args, int grid, size_t dyn_s
 int launch_qr_solve(double* work, const unsigned long long* offsets, const int* rows, int cols, int n, double* x_out, unsigned* flags_out,
                     void* stream) {
     const int warps = 4;
-    const WarpLayout wl = make_warp_layout(1, 0, cols, cols);
+    const WarpLayout wl = make_warp_layout(1, 0, cols, cols, 160);
     const size_t smem = ((sizeof(Frame) + 15) & ~(size_t)15) + (size_t)warps * wl.total * 8;
     cudaError_t err = cudaFuncSetAttribute(qr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import capi
 from .capi import lib, check
+from .robots import IDENTITY12, RobotDescription, make_transform  # noqa: F401
 
 
 def _as_f64(a):
@@ -26,17 +27,6 @@ def _as_f64(a):
 
 def _dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
-
-
-IDENTITY12 = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float64)
-
-
-def make_transform(translation=(0.0, 0.0, 0.0), rotation=None):
-    """Row-major 3x4 [R|t] as 12 doubles."""
-    T = np.zeros((3, 4))
-    T[:, :3] = np.eye(3) if rotation is None else np.asarray(rotation, dtype=np.float64)
-    T[:, 3] = translation
-    return T.reshape(12).copy()
 
 
 class BuiltEnvironment:
@@ -109,69 +99,6 @@ def build_complete_environment_on_device(obstacles, resolution, device=0):
     h = C.c_void_p()
     check(lib.fks_env_build_device(int(device), arr, n, float(resolution), C.byref(h)))
     return GpuEnvironment(None, device, _handle=h)
-
-
-class RobotDescription:
-    """Flat description of a Tnuva{SE2,SE3,Linked}Robot (tnuva_robot_models.hpp:26,201,415): collision
-    points per link (link-major), one PID + velocity actuator per axis, joints for the linked robot."""
-
-    def __init__(self, kind, points_xyz, point_link, axes, n_links=1, joints=(), base_transform=None,
-                 allowed_self_collision=None, position_distance_weight=1.0, rotation_distance_weight=1.0):
-        self.kind = int(kind)
-        self.points = _as_f64(points_xyz).reshape(-1, 3)
-        self.point_link = np.ascontiguousarray(point_link, dtype=np.int32)
-        self.axes = [dict(a) for a in axes]
-        self.n_links = int(n_links)
-        self.joints = [dict(j) for j in joints]
-        self.base = _as_f64(IDENTITY12 if base_transform is None else base_transform)
-        self.allowed = None if allowed_self_collision is None else np.ascontiguousarray(allowed_self_collision, dtype=np.uint8)
-        self.pos_w = float(position_distance_weight)
-        self.rot_w = float(rotation_distance_weight)
-        self.n_dof = len(self.axes)
-        self._keep = None
-
-    @property
-    def config_stride(self):
-        return 3 if self.kind == capi.ROBOT_SE2 else (12 if self.kind == capi.ROBOT_SE3 else self.n_dof)
-
-    def to_c(self):
-        d = capi.RobotDesc()
-        d.kind = self.kind
-        d.n_links = self.n_links
-        d.n_joints = len(self.joints)
-        d.n_dof = self.n_dof
-        d.n_points = self.points.shape[0]
-        d.points_xyz = _dptr(self.points)
-        d.point_link = self.point_link.ctypes.data_as(C.POINTER(C.c_int32))
-        axes = (capi.AxisParams * self.n_dof)()
-        for i, a in enumerate(self.axes):
-            axes[i].kp = a.get("kp", 1.0)
-            axes[i].ki = a.get("ki", 0.0)
-            axes[i].kd = a.get("kd", 0.0)
-            axes[i].integral_clamp = a.get("integral_clamp", 0.0)
-            axes[i].velocity_limit = a["velocity_limit"]
-            axes[i].proportional_noise = a.get("proportional_noise", 0.0)
-            axes[i].minimum_noise = a.get("minimum_noise", 0.0)
-            axes[i].noise_sigma = a.get("noise_sigma", 0.5)  # tnuva.hpp:128-130
-        d.axes = axes
-        d.base_transform = (C.c_double * 12)(*self.base.tolist())
-        joints = (capi.JointDesc * max(len(self.joints), 1))()
-        for i, j in enumerate(self.joints):
-            joints[i].parent_link = j["parent"]
-            joints[i].child_link = j["child"]
-            joints[i].type = j["type"]
-            joints[i].transform = (C.c_double * 12)(*_as_f64(j["transform"]).tolist())
-            joints[i].axis = (C.c_double * 3)(*[float(v) for v in j["axis"]])
-            joints[i].lower_limit = j.get("lower", -np.pi)
-            joints[i].upper_limit = j.get("upper", np.pi)
-            joints[i].distance_weight = j.get("weight", 1.0)
-        d.joints = joints
-        if self.allowed is not None:
-            d.allowed_self_collision = self.allowed.ctypes.data_as(C.POINTER(C.c_uint8))
-        d.position_distance_weight = self.pos_w
-        d.rotation_distance_weight = self.rot_w
-        self._keep = (axes, joints)
-        return d
 
 
 class GpuEnvironment:
@@ -373,6 +300,21 @@ class GpuParticleContactSimulator:
     def reset_statistics(self):
         check(lib.fks_reset_statistics(self._h))
 
+    def enable_kernel_timing(self, enable=True):
+        check(lib.fks_sim_enable_kernel_timing(self._h, int(bool(enable))))
+
+    def kernel_times_ms(self):
+        """Device time of the kernels of the last batch call: [free flight, hand-over sort, contact] or [the single kernel]."""
+        out = (C.c_double * 4)()
+        n = C.c_int(0)
+        check(lib.fks_sim_kernel_times(self._h, out, C.byref(n)))
+        return [float(out[i]) for i in range(n.value)]
+
+    def free_flight_statistics(self):
+        out = (C.c_uint64 * capi.NUM_STATS)()
+        check(lib.fks_sim_free_flight_statistics(self._h, out))
+        return {k: int(out[i]) for i, k in enumerate(capi.STAT_NAMES)}
+
     @property
     def launch_count(self):
         return int(lib.fks_sim_launch_count(self._h))
@@ -438,3 +380,67 @@ def debug_qr_solve(systems, device=0):
     check(lib.fks_debug_qr_solve(int(device), flat.ctypes.data, offsets.ctypes.data, rows.ctypes.data, cols, n, x.ctypes.data,
                                  flags.ctypes.data))
     return x, flags
+
+
+class MultiGpuParticleContactSimulator:
+    """ForwardSimulateRobots over several GPUs of one box behind one call (fks_multi_*): contiguous particle shards,
+    environment and robot replicated per device, records independent of the device count."""
+
+    def __init__(self, built_env, robot_description, devices, solver_params=None, simulation_controller_frequency=25.0,
+                 prng_seed=42, debug_level=0):
+        self.params = solver_params if solver_params is not None else capi.default_solver_params()
+        self.robot_description = robot_description
+        desc = built_env.desc if isinstance(built_env, BuiltEnvironment) else built_env
+        devices = list(range(devices)) if isinstance(devices, int) else list(devices)
+        dev = (C.c_int32 * len(devices))(*devices)
+        rd = robot_description.to_c()
+        self._h = C.c_void_p()
+        check(lib.fks_multi_sim_create(dev, len(devices), C.byref(desc), C.byref(rd), C.byref(self.params),
+                                       float(simulation_controller_frequency), int(prng_seed), int(debug_level), C.byref(self._h)))
+        self.devices = devices
+        self.config_stride = robot_description.config_stride
+        self.result_stride = lib.fks_multi_sim_result_stride(self._h)
+        self.dtype = result_dtype(self.config_stride)
+
+    def forward_simulate_robots(self, starts, targets, allow_contacts=True, noise_mode=capi.NOISE_PHILOX, tape=None,
+                                first_particle_id=0, out=None):
+        starts = _as_f64(starts).reshape(-1, self.config_stride)
+        targets = _as_f64(targets).reshape(-1, self.config_stride)
+        n = starts.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=self.dtype)
+        ctape, keep = (None, None)
+        if tape is not None:
+            ctape, keep = make_tape(*tape)
+        check(lib.fks_multi_forward_simulate(self._h, starts.ctypes.data, targets.ctypes.data, n, targets.shape[0],
+                                             int(bool(allow_contacts)), int(noise_mode), C.byref(ctape) if ctape is not None else None,
+                                             int(first_particle_id), out.ctypes.data))
+        return SimulationResults(out)
+
+    def forward_simulate_device(self, d_starts, d_targets, n, n_targets, d_results, allow_contacts=True, first_particle_id=0):
+        """d_starts / d_targets / d_results: one device pointer (or torch tensor) per device; every d_results[d] ends up
+        holding all n records (ncclAllGather)."""
+        def arr(xs):
+            return (C.c_void_p * len(xs))(*[x.data_ptr() if hasattr(x, "data_ptr") else int(x) for x in xs])
+
+        check(lib.fks_multi_forward_simulate_device(self._h, arr(d_starts), arr(d_targets), int(n), int(n_targets),
+                                                    int(bool(allow_contacts)), int(first_particle_id), arr(d_results)))
+
+    def get_statistics(self):
+        out = (C.c_uint64 * capi.NUM_STATS)()
+        check(lib.fks_multi_get_statistics(self._h, out))
+        return {k: int(out[i]) for i, k in enumerate(capi.STAT_NAMES)}
+
+    def reset_statistics(self):
+        check(lib.fks_multi_reset_statistics(self._h))
+
+    def close(self):
+        if self._h:
+            lib.fks_multi_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -8,8 +8,8 @@ forward_simulation_time 1.0 s (25 steps), allow_contacts = true, actuator noise 
 """
 import numpy as np
 
-from . import capi
-from .simulator import RobotDescription, build_complete_environment, make_transform
+from . import abi as capi
+from .robots import RobotDescription, make_transform
 
 CONTROLLER_HZ = 25.0
 PRNG_SEED = 42
@@ -44,8 +44,11 @@ class Workload:
         return self.starts.shape[0]
 
     def environment(self):
+        """BuildCompleteEnvironment by the product's host builder (libfksgpu.so)."""
         if self._env is None:
-            self._env = build_complete_environment(self.obstacles, self.resolution)
+            from . import simulator as S
+
+            self._env = S.build_complete_environment(self.obstacles, self.resolution)
         return self._env
 
     def device_environment(self, device=0):

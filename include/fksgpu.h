@@ -264,6 +264,14 @@ int fks_reverse_simulate(fks_sim* sim, const double* starts, const double* targe
                          int noise_mode, const fks_noise_tape* tape, uint64_t first_particle_id,
                          void* results);
 
+/* fks_forward_simulate without the final wait: returns once the copies and the kernels are enqueued on the simulator's own
+ * stream; `results` (pinned memory makes the copy truly asynchronous) is complete after fks_sim_synchronize. */
+int fks_forward_simulate_async(fks_sim* sim, const double* starts, const double* targets,
+                               size_t n_particles, size_t n_targets, int allow_contacts,
+                               int noise_mode, const fks_noise_tape* tape, uint64_t first_particle_id,
+                               void* results);
+int fks_sim_synchronize(fks_sim* sim);
+
 /* Same with DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream).
  * d_tape_draws / d_tape_offsets may be NULL unless noise_mode == FKS_NOISE_INJECTED. */
 int fks_forward_simulate_device(fks_sim* sim, const double* d_starts, const double* d_targets,
@@ -308,11 +316,51 @@ int fks_forward_simulate_traced(fks_sim* sim, const double* start, const double*
 int fks_get_statistics(fks_sim* sim, uint64_t* out);
 int fks_reset_statistics(fks_sim* sim);
 
+/* Measurement aids.  A batch call with contacts allowed runs a free-flight kernel (every particle up to its first colliding
+ * microstep), a small hand-over sort, and a contact kernel (the parked particles to their end).
+ * fks_sim_enable_kernel_timing: record CUDA events around them from now on; fks_sim_kernel_times: device milliseconds of the
+ * kernels of the LAST call (out_ms[0] free flight, [1] hand-over sort, [2] contact; a single-kernel call fills [0] only) and
+ * how many were timed; fks_sim_free_flight_statistics: the counters of the free-flight kernels alone (fks_get_statistics
+ * minus these = the contact kernels). */
+int fks_sim_enable_kernel_timing(fks_sim* sim, int enable);
+int fks_sim_kernel_times(fks_sim* sim, double* out_ms, int* n_kernels);
+int fks_sim_free_flight_statistics(fks_sim* sim, uint64_t* out);
+
 /* number of kernel launches issued by this simulator so far (bench "gpu_launches") */
 uint64_t fks_sim_launch_count(const fks_sim* sim);
 /* kernel attributes of the simulate kernel for this robot kind (regs, smem, occupancy) as a
  * short human-readable string owned by the sim */
 const char* fks_sim_kernel_info(fks_sim* sim);
+
+/* -------------------------------------------------------------------------------------------
+ * Several GPUs of one box behind the same call.  ForwardSimulateRobots is data parallel over particles
+ * (spcs.hpp:795-802): the batch is cut into contiguous shards, one per device, environment and robot are replicated per
+ * device at creation (what the factories fks.hpp:18-22 + the constructor spcs.hpp:420-444 do once), Philox noise is keyed
+ * by the global particle id, so the records do not depend on the device count.
+ *   fks_multi_forward_simulate         host buffers; every device copies its records straight into `results`: all N
+ *                                      records return to the caller, no collective needed.  Tapes (parity mode) are sharded too.
+ *   fks_multi_forward_simulate_device  device buffers: d_starts[d] / d_targets[d] hold device d's SHARD (n / n_devices
+ *                                      particles; one target or one per particle of the shard), d_results[d] is a full
+ *                                      n-record array on device d; after the call every device holds ALL n records,
+ *                                      exchanged by one ncclAllGather over NVLink (libnccl.so.2 bound at run time).  Philox noise.
+ *   fks_multi_get_statistics           the counters summed over the devices.
+ * devices == NULL selects devices 0 .. n_devices-1.
+ * ----------------------------------------------------------------------------------------- */
+typedef struct fks_multi_sim fks_multi_sim;
+int fks_multi_sim_create(const int32_t* devices, int32_t n_devices, const fks_env_desc* env, const fks_robot_desc* robot,
+                         const fks_solver_params* params, double simulation_controller_frequency, uint64_t prng_seed,
+                         int32_t debug_level, fks_multi_sim** out);
+void fks_multi_sim_destroy(fks_multi_sim* sim);
+int fks_multi_sim_device_count(const fks_multi_sim* sim);
+size_t fks_multi_sim_result_stride(const fks_multi_sim* sim);
+int fks_multi_forward_simulate(fks_multi_sim* sim, const double* starts, const double* targets, size_t n_particles,
+                               size_t n_targets, int allow_contacts, int noise_mode, const fks_noise_tape* tape,
+                               uint64_t first_particle_id, void* results);
+int fks_multi_forward_simulate_device(fks_multi_sim* sim, const double* const* d_starts, const double* const* d_targets,
+                                      size_t n_particles, size_t n_targets, int allow_contacts, uint64_t first_particle_id,
+                                      void* const* d_results);
+int fks_multi_get_statistics(fks_multi_sim* sim, uint64_t* out);
+int fks_multi_reset_statistics(fks_multi_sim* sim);
 
 /* -------------------------------------------------------------------------------------------
  * Environment builder (host C++; replaces simulator_environment_builder::BuildCompleteEnvironment,

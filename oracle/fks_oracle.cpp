@@ -700,9 +700,24 @@ constexpr double kRoundoffPivotBand = 1e8;
 // partial sum), which is what makes it return these bits (tests/test_gpu_qr_solver.py).
 template <class Term>
 inline double sum4(int lo, int hi, Term term) {
-    double p[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int r = lo; r < hi; r++) p[r & 3] += term(r);
-    return (p[0] + p[2]) + (p[1] + p[3]);
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+    int r = lo;
+    for (; r < hi && (r & 3) != 0; r++) {  // rows up to the next multiple of 4, each into the partial sum of its residue
+        const double t = term(r);
+        if ((r & 3) == 1) p1 += t;
+        else if ((r & 3) == 2) p2 += t;
+        else p3 += t;
+    }
+    for (; r + 3 < hi; r += 4) {
+        p0 += term(r);
+        p1 += term(r + 1);
+        p2 += term(r + 2);
+        p3 += term(r + 3);
+    }
+    if (r < hi) p0 += term(r);
+    if (r + 1 < hi) p1 += term(r + 1);
+    if (r + 2 < hi) p2 += term(r + 2);
+    return (p0 + p2) + (p1 + p3);
 }
 
 void colpiv_qr_solve(double* A, double* b, int rows, int cols, double* x, uint32_t* sens, QrInfo* info = nullptr) {

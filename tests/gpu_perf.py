@@ -42,7 +42,7 @@ def run(name, n, free=False, reps=3):
         if sum(ph[:10]):
             names = ["A apply", "group-1 barrier", "B measure", "-", "T trans", "full barrier", "C collect", "solver barrier", "D solve+estimate", "end barrier"]
             print("    warp clocks: " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(names, ph)), flush=True)
-            print("    per call: collect %.0f clk (n=%d), qr<=64rows %.0f clk (n=%d), qr>64rows %.0f clk (n=%d), estimate %.0f clk" % (
+            print("    per call: collect %.0f clk (n=%d), solve in shared memory %.0f clk (n=%d), solve in the global store %.0f clk (n=%d), estimate %.0f clk" % (
                 ph[10] / max(ph[11], 1), ph[11], ph[12] / max(ph[13], 1), ph[13], ph[14] / max(ph[15], 1), ph[15],
                 ph[19] / max(ph[11], 1)), flush=True)
             nw = 148 * 32  # counters are summed over all warps

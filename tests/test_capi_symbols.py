@@ -38,6 +38,27 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(capi.NoiseTape) == 32
 
 
+def test_pure_python_defaults_equal_the_librarys():
+    from fast_kinematic_simulator_b200 import abi
+
+    a, b = abi.default_solver_params(), capi.default_solver_params()
+    for name, _ in abi.SolverParams._fields_:
+        assert getattr(a, name) == getattr(b, name), name
+
+
+def test_workloads_import_without_the_product_library():
+    """bench.py --impl reference describes robots / environments with the package's pure modules: importing them must not
+    load libfksgpu.so (checked in a fresh interpreter)."""
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r); import fast_kinematic_simulator_b200.workloads as W; w = W.arm_table(4); "
+            "w.robot.to_c(); import ctypes; "
+            "maps = open('/proc/self/maps').read(); assert 'libfksgpu' not in maps, 'product library loaded'; print('ok')" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
 def test_no_device_is_an_error_not_a_fallback():
     """Without a GPU every compute entry point must fail loudly (there is no CPU path in the product)."""
     import torch
