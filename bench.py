@@ -16,7 +16,7 @@ e2e     = the same metric with HOST buffers (pinned) through the C ABI: H2D of s
           read back on every rank inside it.
 config5 = BASELINE config 5 in the same line: 1,048,576 arm particles IN TOTAL split over the N GPUs (strong scaling),
           all-gather of the end states included, device-timed.
-roofline= the contact kernel (the dominant one of the call's two) against the unit ncu shows binding for the workload.
+roofline= the simulate kernel against the unit ncu shows binding for the workload.
 --impl reference times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample; that arm
 never loads libfksgpu.so.
 """
@@ -241,7 +241,7 @@ def main():
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms = []  # per step: device time of [free flight, hand-over sort, contact] (or of the single kernel)
+    kernel_ms = []  # per step: device time of the simulate kernel
     barrier()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the timed events)
@@ -252,7 +252,6 @@ def main():
     barrier()
     step_ms = sum(a.elapsed_time(b) for a, b in ev)
     stats = sim.get_statistics()
-    free_stats = sim.free_flight_statistics()
     launches = sim.launch_count - launches0
     if rank == 0:
         sampler.stop_flag.set()
@@ -324,13 +323,10 @@ def main():
     if rank == 0:
         value = tot["total_microsteps"] / (step_ms * 1e-3)
         e2e_value = micro_e2e_total * args.steps / e2e_s
-        # Roofline of the dominant kernel of the call, per launch, from THIS rank's counters and the device time of that kernel:
-        # the contact kernel when the call ran the free-flight / contact pair, else the single kernel.
-        two = len(kms) == 3
-        dom_stats = {k: stats[k] - (free_stats[k] if two else 0) for k in capi.STAT_NAMES}
-        nbytes, flops, gathers = algorithmic_work(dom_stats, P, D, J)
-        k_s = (kms[2] if two else kms[0]) * 1e-3
-        kname = "simulate_kernel<%d, false, %s>" % (w.kind, "kModeContact" if two else "kModeAll")
+        # Roofline of the (single) kernel of the call, per launch, from THIS rank's counters and the device time of the kernel
+        nbytes, flops, gathers = algorithmic_work(stats, P, D, J)
+        k_s = kms[0] * 1e-3
+        kname = "simulate_kernel<%d, false>" % w.kind
         peak, how = measured_peaks()
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -374,7 +370,7 @@ def main():
                     "d2h_bytes_per_step": int(world * n_local * rec * (world if world > 1 else 1)), "ms_per_step": 1e3 * e2e_s / args.steps,
                     "includes": "H2D of starts/targets, kernels, %sD2H of the records" % ("ncclAllGather of all ranks' records, " if world > 1 else "")},
             "gpu_launches": int(launches),
-            "kernels_ms_per_step": dict(zip(("free_flight", "handover_sort", "contact"), kms)) if two else {"single": kms[0]},
+            "kernel_ms_per_step": kms[0],
             "roofline": roofline,
             "roofline_hbm": roof_hbm,
             "kernel_info": sim.kernel_info,

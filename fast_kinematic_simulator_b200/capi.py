@@ -61,7 +61,6 @@ EXPORTS = (
     "fks_reset_statistics",
     "fks_sim_enable_kernel_timing",
     "fks_sim_kernel_times",
-    "fks_sim_free_flight_statistics",
     "fks_sim_launch_count",
     "fks_sim_kernel_info",
     "fks_build_environment",
@@ -124,7 +123,6 @@ lib.fks_get_statistics.argtypes = [C.c_void_p, P(C.c_uint64)]
 lib.fks_reset_statistics.argtypes = [C.c_void_p]
 lib.fks_sim_enable_kernel_timing.argtypes = [C.c_void_p, C.c_int]
 lib.fks_sim_kernel_times.argtypes = [C.c_void_p, P(C.c_double), P(C.c_int)]
-lib.fks_sim_free_flight_statistics.argtypes = [C.c_void_p, P(C.c_uint64)]
 lib.fks_sim_launch_count.argtypes = [C.c_void_p]
 lib.fks_sim_launch_count.restype = C.c_uint64
 lib.fks_sim_kernel_info.argtypes = [C.c_void_p]

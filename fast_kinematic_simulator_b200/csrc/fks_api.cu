@@ -115,14 +115,12 @@ struct fks_sim {
     char* d_results;
     size_t cap_starts, cap_targets, cap_tape, cap_tape_off, cap_results, cap_dec, cap_dec_off;
     size_t smem_limit;
-    // hand-over buffers of the free-flight / contact kernel pair (grown on demand)
-    char* d_park;
-    unsigned int *d_park_key, *d_park_order, *d_park_meta;
-    size_t cap_park, cap_park_key, cap_park_order;
-    int two_kernels;  // developer knob FKS_TWO_KERNELS (default 1)
-    // per-kernel device time of the last batch call (fks_sim_kernel_times): events around the free-flight kernel, the
-    // hand-over sort and the contact kernel, recorded only after fks_sim_enable_kernel_timing
-    cudaEvent_t tev[4];
+    // context pool of the simulate kernel: global store of parked particle contexts and their scratch slots
+    char* d_ctx_store;
+    int pool;
+    // device time of the simulate kernel of the last batch call (fks_sim_kernel_times), recorded only after
+    // fks_sim_enable_kernel_timing
+    cudaEvent_t tev[2];
     int timing, timed_kernels;
     // launches of one simulator share its particle counter, scratch slots and statistics: a launch on another stream waits
     // for the previous one (fks_forward_simulate_device takes the caller's stream)
@@ -555,12 +553,9 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     s->d_tape_off = s->d_dec = s->d_dec_off = nullptr;
     s->d_results = nullptr;
     s->cap_starts = s->cap_targets = s->cap_tape = s->cap_tape_off = s->cap_results = s->cap_dec = s->cap_dec_off = 0;
-    s->d_park = nullptr;
-    s->d_park_key = s->d_park_order = s->d_park_meta = nullptr;
-    s->cap_park = s->cap_park_key = s->cap_park_order = 0;
-    s->two_kernels = 1;
-    if (const char* ev = std::getenv("FKS_TWO_KERNELS")) s->two_kernels = std::atoi(ev);
-    for (int i = 0; i < 4; i++) s->tev[i] = nullptr;
+    s->d_ctx_store = nullptr;
+    s->pool = 0;
+    for (int i = 0; i < 2; i++) s->tev[i] = nullptr;
     s->timing = 0;
     s->timed_kernels = 0;
     s->last_done = nullptr;
@@ -616,13 +611,18 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     if (err != cudaSuccess) { delete s; return cuda_fail(err, "cudaGetDeviceProperties"); }
     s->grid_max = prop.multiProcessorCount * s->kinfo.max_blocks_per_sm;
     s->num_sms = prop.multiProcessorCount;
-    const size_t scratch_bytes = (size_t)s->grid_max * wpb * s->plan.sl.total;
+    s->pool = std::min(2 * wpb, kMaxPool);
+    const size_t scratch_bytes = (size_t)s->grid_max * s->pool * s->plan.sl.total;  // one slot per context
+    s->plan.pool = s->pool;
+    s->plan.ctx_stride = (int)context_bytes(s->plan.wl);
+    const size_t ctx_bytes = (size_t)s->grid_max * s->pool * (size_t)s->plan.ctx_stride;
+
     if ((err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (err = cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_scratch, scratch_bytes)) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_ctx_store, ctx_bytes)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_stats, 128 * sizeof(unsigned long long))) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_counter, 4 * sizeof(unsigned int))) != cudaSuccess ||
-        (err = cudaMalloc((void**)&s->d_park_meta, (1 + 2 * kParkBuckets) * sizeof(unsigned int))) != cudaSuccess ||
         (err = cudaMemset(s->d_stats, 0, 128 * sizeof(unsigned long long))) != cudaSuccess) {
         fks_sim_destroy(s);
         return cuda_fail(err, "fks_sim_create: allocation");
@@ -630,7 +630,7 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     char buf[512];
     std::snprintf(buf, sizeof(buf),
                   "simulate_kernel<kind=%d>: %d regs/thread, %zu B dynamic smem/CTA, %d B local/thread, %d threads/CTA, "
-                  "%d CTAs/SM x %d SMs (persistent grid %d), scratch %llu B/warp, L2 window %zu B",
+                  "%d CTAs/SM x %d SMs (persistent grid %d), scratch %llu B/context, L2 window %zu B",
                   h.kind, s->kinfo.regs, s->dyn_smem, s->kinfo.local_bytes, 32 * wpb, s->kinfo.max_blocks_per_sm,
                   prop.multiProcessorCount, s->grid_max, (unsigned long long)s->plan.sl.total, env->l2_window_bytes);
     s->info = buf;
@@ -652,13 +652,10 @@ void fks_sim_destroy(fks_sim* s) {
     cudaFree(s->d_tape_off);
     cudaFree(s->d_dec);
     cudaFree(s->d_dec_off);
-    cudaFree(s->d_park);
-    cudaFree(s->d_park_key);
-    cudaFree(s->d_park_order);
-    cudaFree(s->d_park_meta);
+    cudaFree(s->d_ctx_store);
     cudaFree(s->d_results);
     if (s->last_done) cudaEventDestroy(s->last_done);
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 2; i++)
         if (s->tev[i]) cudaEventDestroy(s->tev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -707,47 +704,19 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->plan.warps_per_block, per_sm));
     a.warps_per_block = wpb;
     a.sync_off = a.warps_off + wpb * a.wl.total * 8;
-    const size_t dyn_smem = (size_t)a.sync_off + 16;
+    const size_t dyn_smem = (size_t)a.sync_off + kSyncBytes;
     const size_t blocks_needed = (n + (size_t)wpb - 1) / (size_t)wpb;
     const int grid = (int)std::min<size_t>((size_t)s->grid_max, blocks_needed);
     if (s->has_last && stream != s->last_stream) FKS_CUDA(cudaStreamWaitEvent(stream, s->last_done, 0));
     FKS_CUDA(cudaMemsetAsync(s->d_counter, 0, 4 * sizeof(unsigned int), stream));
     const void* l2_base = s->env->l2_window_bytes ? s->env->d_sdf : nullptr;
-    const int kind = s->robot->host.kind;
-    if (s->two_kernels && a.allow_contacts && a.trace == nullptr) {
-        // batch path: free flight up to the first colliding microstep, then the contact regime (fks_device_types.h, kModeFree)
-        int rc;
-        a.park_stride = (int)park_record_bytes(a.wl);
-        if ((rc = ensure(&s->d_park, &s->cap_park, n * (size_t)a.park_stride)) != FKS_OK) return rc;
-        if ((rc = ensure(&s->d_park_key, &s->cap_park_key, n)) != FKS_OK) return rc;
-        if ((rc = ensure(&s->d_park_order, &s->cap_park_order, n)) != FKS_OK) return rc;
-        a.park = s->d_park;
-        a.park_key = s->d_park_key;
-        a.park_order = s->d_park_order;
-        a.park_meta = s->d_park_meta;
-        FKS_CUDA(cudaMemsetAsync(s->d_park_meta, 0, (1 + 2 * kParkBuckets) * sizeof(unsigned int), stream));
-        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[0], stream));
-        a.stats = s->d_stats + 40;  // the free-flight kernel counts apart (fks_debug_kernel_statistics); fks_get_statistics adds them up
-        rc = launch_simulate(kind, kModeFree, a, grid, dyn_smem, stream, l2_base, s->env->l2_window_bytes);
-        if (rc != 0) return cuda_fail((cudaError_t)rc, "free-flight kernel launch");
-        a.stats = s->d_stats;
-        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[1], stream));
-        rc = launch_park_order(a, std::max(1, std::min(2 * s->num_sms, (int)((n + 255) / 256))), stream);
-        if (rc != 0) return cuda_fail((cudaError_t)rc, "park order kernel launch");
-        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[2], stream));
-        a.counter = s->d_counter + 1;
-        rc = launch_simulate(kind, kModeContact, a, grid, dyn_smem, stream, l2_base, s->env->l2_window_bytes);
-        if (rc != 0) return cuda_fail((cudaError_t)rc, "contact kernel launch");
-        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[3], stream));
-        s->timed_kernels = s->timing ? 3 : 0;
-        s->launches += 2;
-    } else {
-        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[0], stream));
-        const int rc = launch_simulate(kind, kModeAll, a, grid, dyn_smem, stream, l2_base, s->env->l2_window_bytes);
-        if (rc != 0) return cuda_fail((cudaError_t)rc, "simulate kernel launch");
-        if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[1], stream));
-        s->timed_kernels = s->timing ? 1 : 0;
-    }
+    a.ctx_store = s->d_ctx_store;
+    a.pool = std::min(2 * wpb, s->pool);
+    if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[0], stream));
+    const int rc = launch_simulate(s->robot->host.kind, a, grid, dyn_smem, stream, l2_base, s->env->l2_window_bytes);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "simulate kernel launch");
+    if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[1], stream));
+    s->timed_kernels = s->timing ? 1 : 0;
     FKS_CUDA(cudaEventRecord(s->last_done, stream));
     s->last_stream = stream;
     s->has_last = true;
@@ -910,13 +879,15 @@ int fks_check_config_collision(fks_sim* s, const double* configs, size_t n, doub
     a.pzl = s->robot->d_pzl;
     a.starts = s->d_starts;
     a.scratch = s->d_scratch;
+    a.ctx_store = s->d_ctx_store;
     a.n_particles = n;
     a.cfg_stride = s->robot->stride;
     const size_t per_sm = (n + (size_t)s->num_sms - 1) / (size_t)s->num_sms;
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->plan.warps_per_block, per_sm));
     a.warps_per_block = wpb;
+    a.pool = wpb;  // one context (= one scratch slot) per warp
     a.sync_off = a.warps_off + wpb * a.wl.total * 8;
-    const size_t dyn_smem = (size_t)a.sync_off + 16;
+    const size_t dyn_smem = (size_t)a.sync_off + kSyncBytes;
     const int grid = (int)std::min<size_t>((size_t)s->grid_max, (n + (size_t)wpb - 1) / (size_t)wpb);
     rc = launch_check_config(s->robot->host.kind, a, grid, dyn_smem, s->stream, inflation_ratio, (unsigned char*)s->d_results);
     if (rc != 0) return cuda_fail((cudaError_t)rc, "check_config kernel launch");
@@ -938,27 +909,24 @@ int fks_get_statistics(fks_sim* s, uint64_t* out) {
     DeviceGuard guard(s->device);
     int rc = sync_simulator(s);
     if (rc != FKS_OK) return rc;
-    uint64_t both[64];
-    FKS_CUDA(cudaMemcpyAsync(both, s->d_stats, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    FKS_CUDA(cudaMemcpyAsync(out, s->d_stats, FKS_NUM_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
     FKS_CUDA(cudaStreamSynchronize(s->stream));
-    for (int k = 0; k < FKS_NUM_STATS; k++) out[k] = both[k] + both[40 + k];  // contact (or single) kernel + free-flight kernel
     return FKS_OK;
 }
 
-// Measurement aids (bench.py): device time of the kernels of the last batch call and their separate counters.
+// Measurement aid (bench.py): device time of the simulate kernel of the last batch call.
 int fks_sim_enable_kernel_timing(fks_sim* s, int enable) {
     if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_enable_kernel_timing: null simulator");
     DeviceGuard guard(s->device);
     if (enable)
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 2; i++)
             if (!s->tev[i]) FKS_CUDA(cudaEventCreate(&s->tev[i]));
     s->timing = enable ? 1 : 0;
     s->timed_kernels = 0;
     return FKS_OK;
 }
 
-// out_ms[0] = free-flight kernel, [1] = hand-over sort, [2] = contact kernel (a single-kernel call: [0] only); returns the
-// number of kernels timed in *n_kernels.  Waits for the call.
+// out_ms[0] = device milliseconds of the simulate kernel of the last call; *n_kernels = 1 when it was timed.  Waits for the call.
 int fks_sim_kernel_times(fks_sim* s, double* out_ms, int* n_kernels) {
     if (!s || !out_ms || !n_kernels) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_kernel_times: null argument");
     DeviceGuard guard(s->device);
@@ -969,16 +937,6 @@ int fks_sim_kernel_times(fks_sim* s, double* out_ms, int* n_kernels) {
         FKS_CUDA(cudaEventElapsedTime(&ms, s->tev[i], s->tev[i + 1]));
         out_ms[i] = (double)ms;
     }
-    return FKS_OK;
-}
-
-// counters of the free-flight kernel alone (out has FKS_NUM_STATS entries); fks_get_statistics minus these = the contact kernel
-int fks_sim_free_flight_statistics(fks_sim* s, uint64_t* out) {
-    if (!s || !out) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_free_flight_statistics: null argument");
-    DeviceGuard guard(s->device);
-    int rc = sync_simulator(s);
-    if (rc != FKS_OK) return rc;
-    FKS_CUDA(cudaMemcpy(out, s->d_stats + 40, FKS_NUM_STATS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return FKS_OK;
 }
 

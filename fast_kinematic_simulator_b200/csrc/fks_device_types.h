@@ -102,9 +102,16 @@ struct WarpVars {
     unsigned long long pid, tape_pos, tape_end;
     unsigned long long dec_pos, dec_end;  // decision tape (parity mode): next / one-past-last record of this particle
     double scaling;
+    double m_result;  // last motion estimate
     unsigned step, micro, number_microsteps, resolver_iterations, flags, n_micro_total, n_iter_total, n_steps;
     int collided, any_resolve_failed, step_collided, step_failed, step_stopped;
-    int qr_rows;  // > 0: a tall stacked system (this many rows) is half factored and waits for the next solver slot
+    // control state of the particle's state machine (registers while a phase runs, here in between: the context may be
+    // picked up by another warp): what to do next (after), the pending operation of phase A / B, the ping-pong indices of
+    // the current / previous kinematic state, the last collision bits, and whether the next thing it needs is a contact solve
+    int after, op, op_in, op_out, op_u, op_tn, op_derive, measure, cur, prev, want_solve;
+    unsigned cc;
+    int ctx;        // index of this context in the CTA's pool (fixed; selects its global scratch slot)
+    int pend_rows;  // rows of a stacked system that was collected but is too tall for the small store: it waits for a TALL cycle
 };
 constexpr int kWarpVarsDoubles = (int)((sizeof(WarpVars) + 7) / 8);
 
@@ -136,8 +143,9 @@ struct WarpLayout {
     int qr;       // S doubles: the actuated twist of the SE(3) robot (apply_control)
     int cand;     // 32 doubles = 32 candidate records of collect_corrections
     int vars;     // WarpVars (kWarpVarsDoubles) + 2 * S doubles of PID state
-    int stats;    // FKS_NUM_STATS u64 counters of this warp
     int flags;    // 1 (u32 FKS_FLAG_* bits raised by any lane)
+    int save2_end;  // a particle's context = [cfg, T + 2 L12) + [G, G + L12) + [target, save2_end): what has to survive between phases
+    int stats;    // FKS_NUM_STATS u64 counters of this WARP (not part of a context)
     int total;
     int noise_batch;
 };
@@ -184,15 +192,19 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     w.raw = o; o += S;
     w.stepv = o; o += S;
     w.tn = o; o += w.noise_batch * S;
-    w.qr = o; o += S;
     w.vars = o; o += kWarpVarsDoubles + 2 * S;
-    w.stats = o; o += FKS_NUM_STATS;
     w.flags = o; o += 1;
+    w.save2_end = o;  // [target, save2_end): third saved range of a context
+    w.qr = o; o += S;
+    w.stats = o; o += FKS_NUM_STATS;
     w.total = (o + 1) & ~1;
     return w;
 }
 
-// ---- per-warp global scratch layout (bytes) --------------------------------------------------
+// ---- global scratch (bytes), one slot per particle CONTEXT --------------------------------------
+// the global store of a stacked Jacobian too tall for shared memory (collected in one solve phase, factored in a later
+// one -- possibly by another warp) and the self-collision corrections (found by a collision check, consumed by the next
+// solve phase)
 struct ScratchLayout {
     unsigned long long jstore;    // (D+1) * ldj doubles, then P u64 (candidate list of collect_corrections)
     unsigned long long selfcorr;  // 3*P doubles
@@ -247,15 +259,11 @@ struct LaunchArgs {
     char* results;
     unsigned long long* stats;
     unsigned int* counter;
-    char* scratch;                   // per-warp-slot global scratch
-    // hand-over between the free-flight kernel and the contact kernel (kModeFree / kModeContact): parked particle states
-    // (park_stride bytes each, in arrival order), their sort keys, the processing order of the contact kernel, and
-    // park_meta = {count, histogram of the keys [kParkBuckets], scatter cursors [kParkBuckets]}
-    char* park;
-    unsigned int* park_key;
-    unsigned int* park_order;
-    unsigned int* park_meta;
-    int park_stride, _pad_park;
+    char* scratch;                   // global scratch, one slot per context (pool per CTA)
+    // Context pool: every CTA keeps `pool` particles in flight for its warps_per_block warps (fks_kernels.cu, simulate_kernel).
+    // A context that no warp has loaded lives in ctx_store (ctx_stride bytes each, pool per CTA).
+    char* ctx_store;
+    int pool, ctx_stride;
     unsigned long long n_particles, n_targets, seed, first_id;
     int allow_contacts, noise_mode, cfg_stride, rec_stride;
     int P, warps_per_block;
@@ -269,13 +277,7 @@ struct LaunchArgs {
     int trace_width;                 // doubles per record = max(cfg_stride, D)
 };
 
-// Simulate-kernel modes.  kModeAll: every particle from start to end in one kernel (step traces, allow_contacts == false).
-// The batch path runs two kernels back to back: kModeFree flies every particle until its first colliding microstep (or
-// to its end) and PARKS the colliding ones; kModeContact takes the parked particles -- earliest contact first, they have
-// the most work left -- and runs them to the end.  The CTAs of either kernel then hold particles of ONE regime: free
-// flight never waits for a contact solve, and a contact CTA's solver slots are full.
-enum { kModeAll = 0, kModeFree = 1, kModeContact = 2 };
-constexpr int kParkBuckets = 64;
+constexpr int kMaxPool = 64;  // contexts per CTA (two per warp)
 
 struct Frame {
     LaunchArgs a;
@@ -292,12 +294,12 @@ struct KernelInfo {
     size_t dyn_smem;
 };
 int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelInfo* out);
-int launch_simulate(int kind, int mode, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
+int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
                     const void* l2_window_base, size_t l2_window_bytes);
-// bytes of one parked particle state for this layout
-size_t park_record_bytes(const WarpLayout& wl);
-// turns the keys of the parked particles into the contact kernel's processing order (counting sort by key)
-int launch_park_order(const LaunchArgs& args, int grid, void* stream);
+// bytes of one particle context in the global context store for this layout
+size_t context_bytes(const WarpLayout& wl);
+// bytes of CTA-level scheduling state behind the warp blocks in dynamic shared memory
+constexpr size_t kSyncBytes = 16 + 2 * kMaxPool + 4 * kMaxPool;
 // fills args.wl / pts_off / warps_off / warps_per_block and returns the dynamic shared memory size
 size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stride, int warps_per_block, size_t smem_limit);
 int launch_check_config(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream, double inflation_ratio, unsigned char* out);

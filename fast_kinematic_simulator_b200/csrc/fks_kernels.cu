@@ -68,10 +68,11 @@ __device__ __forceinline__ T wv_add(T* field, T inc) {
     *field = v;
     return v;
 }
-// global scratch of this warp
-__device__ __forceinline__ char* scratch_slot() {
+// global scratch slot of the particle context this warp has loaded
+__device__ __forceinline__ char* context_scratch(int wb) {
     const LaunchArgs& a = frame().a;
-    return a.scratch + (size_t)(blockIdx.x * a.warps_per_block + (threadIdx.x >> 5)) * a.sl.total;
+    const int ctx = reinterpret_cast<const WarpVars*>(wsd(wb) + a.wl.vars)->ctx;
+    return a.scratch + ((size_t)blockIdx.x * a.pool + ctx) * a.sl.total;
 }
 
 // ForwardSimulationStepTrace (spcs:1583-1617, :1703, :1714, :1778), flat: one record per assignment / push_back of the
@@ -571,14 +572,44 @@ __device__ __forceinline__ unsigned active_links(const DevEnv& e, const DevRobot
 #endif
 constexpr int kCandShared = FKS_CAND_SHARED;  // candidate points of collect_corrections kept in shared memory (<= 32)
 
-// CheckEnvironmentCollision (spcs:921-981) of the CURRENT state (G and T[X]); collision_threshold = 0.0 on the simulation
-// path (spcs:424), inflation_ratio * resolution for CheckConfigCollision (spcs:1403)
-__device__ __noinline__ bool check_env(int wb, int X, int use_cull, double collision_threshold) {
+// second tier of the environment check (spcs:967-975) for the listed points {point index, raw cell value}: one point per
+// lane, so the six extra gathers of every EstimateDistance4d are in flight together
+__device__ __noinline__ bool check_env_second_tier(int wb, int X, const uint2* list, int n, double thr) {
     const Frame& fr = frame();
     const DevEnv& e = fr.a.env;
     const WarpLayout& wl = fr.a.wl;
     const int lane = lane_id();
     const double* ws = wsd(wb);
+    const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
+    const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
+    bool hit = false;
+    if (lane < n) {
+        const uint2 rec = list[lane];
+        const double2 xy = pxy[rec.x];
+        const PointZL zl = pzl[rec.x];
+        const Voxel v = voxel_of(e, ws + wl.G + 12 * zl.link, xy.x, xy.y, zl.z);  // same arithmetic as the first tier: same voxel
+        if (!v.inb) {
+            hit = true;  // an out-of-bounds value this low: EstimateDistance4d returns it too
+        } else {
+            double wx, wy, wz;
+            apply_T(ws + wl.T + X * wl.L12 + 12 * zl.link, xy.x, xy.y, zl.z, wx, wy, wz);
+            hit = estimate_distance(wx, wy, wz, v.x, v.y, v.z, __uint_as_float(rec.y)) < thr;
+        }
+    }
+    return __any_sync(FKS_FULL, hit);
+}
+
+// CheckEnvironmentCollision (spcs:921-981) of the CURRENT state (G and T[X]); collision_threshold = 0.0 on the simulation
+// path (spcs:424), inflation_ratio * resolution for CheckConfigCollision (spcs:1403).  The result is an OR over the points
+// (the reference returns at the first hit, spcs:963,974): a point deep inside ends the check at once; points in the second
+// tier (raw value between the two thresholds: their cell touches the surface) are only LISTED -- a link resting on a
+// surface has dozens of them -- and evaluated a warp-load at a time.
+__device__ __noinline__ bool check_env(int wb, int X, int use_cull, double collision_threshold) {
+    const Frame& fr = frame();
+    const DevEnv& e = fr.a.env;
+    const WarpLayout& wl = fr.a.wl;
+    const int lane = lane_id();
+    double* ws = wsd(wb);
     const double* G = ws + wl.G;
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
@@ -586,7 +617,8 @@ __device__ __noinline__ bool check_env(int wb, int X, int use_cull, double colli
     const double thr = collision_threshold - (fr.a.sp.check_tolerance * res);
     const double thr_deep = thr - res;
     const float oob = e.oob;
-    bool hit = false;
+    uint2* list = reinterpret_cast<uint2*>(ws + wl.cand);  // the candidate records of collect_corrections are not live here
+    int nlist = 0;
     // points of culled links cannot collide (and an out-of-bounds value below the threshold disables culling)
     const DevRobot& rb = fr.rb;
     unsigned links = (!use_cull || !e.cull || (double)oob < thr) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, thr > 0.0 ? thr : 0.0);
@@ -610,30 +642,27 @@ __device__ __noinline__ bool check_env(int wb, int X, int use_cull, double colli
                     f[k] = v.inb ? sdf_cell(e, v.x, v.y, v.z) : oob;
                 }
             }
+            bool deep = false;
+#pragma unroll
+            for (int k = 0; k < kBatch; k++) deep = deep || ((double)f[k] < thr_deep);
+            if (__any_sync(FKS_FULL, deep)) return true;  // deep inside (or an oob value this low, spcs:943-964)
 #pragma unroll
             for (int k = 0; k < kBatch; k++) {
-                if ((double)f[k] < thr) {
-                    if ((double)f[k] < thr_deep) {
-                        hit = true;  // deep inside (or an oob value this low: EstimateDistance4d would return it too, spcs:943-975)
-                    } else {
-                        // second tier (rare): redo the voxel (same arithmetic, same result) and estimate the distance
-                        const int p = pos + 32 * k + lane;
-                        const double2 xy = pxy[p];
-                        const PointZL zl = pzl[p];
-                        const Voxel v = voxel_of(e, G + 12 * zl.link, xy.x, xy.y, zl.z);
-                        if (!v.inb) {
-                            hit = true;
-                        } else {
-                            double wx, wy, wz;
-                            apply_T(ws + wl.T + X * wl.L12 + 12 * zl.link, xy.x, xy.y, zl.z, wx, wy, wz);
-                            if (estimate_distance(wx, wy, wz, v.x, v.y, v.z, f[k]) < thr) hit = true;
-                        }
-                    }
+                const bool second = (double)f[k] < thr;
+                const unsigned m = __ballot_sync(FKS_FULL, second);
+                if (m == 0u) continue;
+                if (nlist + __popc(m) > 32) {  // the list is full: evaluate it before it grows
+                    __syncwarp();
+                    if (check_env_second_tier(wb, X, list, nlist, thr)) return true;
+                    nlist = 0;
                 }
+                if (second) list[nlist + __popc(m & ((1u << lane) - 1u))] = make_uint2((unsigned)(pos + 32 * k + lane), __float_as_uint(f[k]));
+                nlist += __popc(m);
             }
         }
     }
-    return __any_sync(FKS_FULL, hit);
+    __syncwarp();
+    return nlist > 0 && check_env_second_tier(wb, X, list, nlist, thr);
 }
 
 // EstimateMaxControlInputWorkspaceMotion(start_robot, end_robot) (spcs:1492-1527) between states Xa and Xb
@@ -816,7 +845,7 @@ __device__ __noinline__ bool self_collisions_exact(int wb, int Xprev, int Xcur, 
     const double* Tcur = ws + wl.T + Xcur * wl.L12;
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
-    char* slot = scratch_slot();
+    char* slot = context_scratch(wb);
     SelfCtx sc;
     sc.cand_pairs[0] = cp0;
     sc.cand_pairs[1] = cp1;
@@ -1092,10 +1121,10 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     const double* G = ws + wl.G;
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
-    char* slot = scratch_slot();
-    double* Ag = reinterpret_cast<double*>(slot + fr.a.sl.jstore);
-    const unsigned char* sflag = reinterpret_cast<const unsigned char*>(slot + fr.a.sl.sflag);
-    const double* selfcorr = reinterpret_cast<const double*>(slot + fr.a.sl.selfcorr);
+    const char* cslot = context_scratch(wb);
+    double* Ag = reinterpret_cast<double*>(context_scratch(wb) + fr.a.sl.jstore);
+    const unsigned char* sflag = reinterpret_cast<const unsigned char*>(cslot + fr.a.sl.sflag);
+    const double* selfcorr = reinterpret_cast<const double*>(cslot + fr.a.sl.selfcorr);
     // candidate list: {point index | bit 31 = needs the environment estimate, raw cell value}; the first kCandShared
     // live in shared memory, the rest behind the Jacobian columns of the global store
     uint2* cand_s = reinterpret_cast<uint2*>(ws + wl.cand);
@@ -1271,32 +1300,34 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     return 3 * npts;
 }
 
-// Where a collected system is solved: in the small shared-memory store when it fitted (nothing to do), in the larger one
-// that the end of the collection frees (world->voxel transforms, joint axes / origins, candidate list: all rebuilt before
-// they are read again) when it fits that, in the global scratch slot otherwise.
-__device__ __forceinline__ void place_system(int wb, int rows, int cols, double** store, int* store_ld) {
+// A collected system that outgrew the small shared-memory store: complete its copy in the context's global store (the
+// rows < cap_s were written to shared memory).  It is factored in a later TALL cycle.
+__device__ __forceinline__ void spill_system(int wb, int cols) {
     const Frame& fr = frame();
     const WarpLayout& wl = fr.a.wl;
     const int lane = lane_id();
-    double* ws = wsd(wb);
-    double* As = ws + wl.jsm;
-    double* Ag = reinterpret_cast<double*>(scratch_slot() + fr.a.sl.jstore);
-    const int lds = wl.jsm_ld, cap_s = (wl.jsm_ld / 3) * 3, ldg = fr.a.sl.ldj, ldb = wl.jsm_big_ld;
-    if (rows <= cap_s) {
-        *store = As;
-        *store_ld = lds;
-        return;
-    }
-    // complete the global copy (rows < cap_s were written to shared memory) ...
+    const double* As = wsd(wb) + wl.jsm;
+    double* Ag = reinterpret_cast<double*>(context_scratch(wb) + fr.a.sl.jstore);
+    const int lds = wl.jsm_ld, cap_s = (wl.jsm_ld / 3) * 3, ldg = fr.a.sl.ldj;
     for (int c = 0; c <= cols; c++)
         for (int r = lane; r < cap_s; r += 32) Ag[(size_t)c * ldg + r] = As[c * lds + r];
     __syncwarp();
+}
+// Where a spilled system is factored: in the larger shared-memory store (what a solve may overwrite once the corrections are
+// collected: world->voxel transforms, joint axes / origins, candidate list -- all rebuilt before they are read again) when
+// it fits, else in place in the global store, where every load of the in-place update is an L2 round trip.
+__device__ __forceinline__ void place_tall_system(int wb, int rows, int cols, double** store, int* store_ld) {
+    const Frame& fr = frame();
+    const WarpLayout& wl = fr.a.wl;
+    const int lane = lane_id();
+    double* As = wsd(wb) + wl.jsm;
+    double* Ag = reinterpret_cast<double*>(context_scratch(wb) + fr.a.sl.jstore);
+    const int ldg = fr.a.sl.ldj, ldb = wl.jsm_big_ld;
     *store = Ag;
     *store_ld = ldg;
     if (rows > ldb) return;
-    // ... and bring the whole system into the larger shared-memory store
     for (int c = 0; c <= cols; c++)
-        for (int r = lane; r < rows; r += 32) As[c * ldb + r] = Ag[(size_t)c * ldg + r];
+        for (int r = lane; r < rows; r += 32) As[c * ldb + r] = __ldcg(Ag + (size_t)c * ldg + r);
     __syncwarp();
     *store = As;
     *store_ld = ldb;
@@ -1333,11 +1364,6 @@ __device__ __forceinline__ void place_system(int wb, int rows, int cols, double*
 // Parity mode (decision tape, fksgpu.h): the pivot order and the rank are taken from the tape, the solver's own are
 // still computed and a difference raises FKS_FLAG_DECISION_OVERRIDDEN; a record flagged OVERRIDE_SOLUTION replaces the
 // solve altogether.
-//
-// Resumable: the slowest solver warp gates its CTA's lock step, and a 90-row system costs four times a 24-row one.  A
-// system in the global store (= a tall one) therefore works off at most `budget` row-steps per call, parks the per-lane
-// state of the factorisation in the (then unused) shared-memory store and returns false; the caller comes back in the
-// next solver slot with resume = true.  Same operations in the same order: the result does not depend on the budget.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
@@ -1349,11 +1375,8 @@ __device__ __forceinline__ double quad_sum(unsigned mask, double p) {
     return add_rn(p, __shfl_xor_sync(mask, p, 1));
 }
 
-#ifndef FKS_QR_BUDGET
-#define FKS_QR_BUDGET (1 << 30)
-#endif
 template <int SLOTS>  // columns per quad: 1 for up to 8 columns (every robot of the reference), 2 for up to 16
-__device__ __noinline__ bool colpiv_qr_lanes(int wb, double* A, int ld, int rows, int cols, int x_off, bool resume) {
+__device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows, int cols, int x_off) {
     const Frame& fr = frame();
     const int lane = lane_id();
     double* ws = wsd(wb);
@@ -1361,13 +1384,11 @@ __device__ __noinline__ bool colpiv_qr_lanes(int wb, double* A, int ld, int rows
     double* x = ws + x_off;
     const int g = lane >> 2, i = lane & 3;
     const unsigned quad = 0xFu << (lane & ~3);
-    double* park = ws + fr.a.wl.jsm;  // 4 doubles per lane + 8 uniform ones, only while a factorisation is paused
-    const bool pausable = SLOTS == 1 && A != park && fr.a.wl.jsm_ld * (cols + 1) >= 4 * 32 + 8;
     // ---- decision tape (parity mode only) ----------------------------------------------------------------------
     bool forced = false;
     int f_rank = 0;
     unsigned long long f_order = 0ull;
-    if (!resume && fr.a.dec_tape != nullptr) {
+    if (fr.a.dec_tape != nullptr) {
         const unsigned long long dp = wv->dec_pos;
         bool desync = true, replaced = false;
         if (dp < wv->dec_end) {
@@ -1391,86 +1412,42 @@ __device__ __noinline__ bool colpiv_qr_lanes(int wb, double* A, int ld, int rows
             if (replaced) raise_flag(wb, FKS_FLAG_DECISION_OVERRIDDEN);
         }
         __syncwarp();
-        if (replaced) return true;
+        if (replaced) return;
     }
     const int size = rows < cols ? rows : cols;
     // per column slot of this quad: colNormsUpdated / colNormsDirect, the position in Eigen's permuted order, and this
     // lane's partial of sum_{r > k} a_r^2 for the coming step (= the tail's squared norm should the column be the pivot)
     double nu[SLOTS], nd[SLOTS], tailp[SLOTS];
     int pos[SLOTS];
-    double max_norm = 0.0, threshold_helper = 0.0;
-    int own_rank = size, nonzero_pivots = size, k0 = 0;
+    double max_norm = 0.0;
+    int own_rank = size, nonzero_pivots = size;
     unsigned long long order = 0ull;  // 4 bits per position: the column sitting there
     bool differed = false, near_cut = false;
-    if (!resume) {
 #pragma unroll
-        for (int sl = 0; sl < SLOTS; sl++) {
-            const int c = g + 8 * sl;
-            nu[sl] = nd[sl] = tailp[sl] = 0.0;
-            pos[sl] = c;
-            if (c < cols) {  // uniform inside the quad
-                const double* mine = A + (size_t)c * ld;
-                double pf = 0.0, pt = 0.0;
-                for (int r = i; r < rows; r += 4) {
-                    const double a = mine[r];
-                    const double sq = mul_rn(a, a);
-                    pf = add_rn(pf, sq);
-                    if (r >= 1) pt = add_rn(pt, sq);
-                }
-                nd[sl] = nu[sl] = sqrt(quad_sum(quad, pf));
-                tailp[sl] = pt;
-                max_norm = fmax(max_norm, nu[sl]);
+    for (int sl = 0; sl < SLOTS; sl++) {
+        const int c = g + 8 * sl;
+        nu[sl] = nd[sl] = tailp[sl] = 0.0;
+        pos[sl] = c;
+        if (c < cols) {  // uniform inside the quad
+            const double* mine = A + (size_t)c * ld;
+            double pf = 0.0, pt = 0.0;
+            for (int r = i; r < rows; r += 4) {
+                const double a = mine[r];
+                const double sq = mul_rn(a, a);
+                pf = add_rn(pf, sq);
+                if (r >= 1) pt = add_rn(pt, sq);
             }
+            nd[sl] = nu[sl] = sqrt(quad_sum(quad, pf));
+            tailp[sl] = pt;
+            max_norm = fmax(max_norm, nu[sl]);
         }
-        max_norm = warp_max(max_norm);
-        const double me = mul_rn(max_norm, DBL_EPSILON);
-        threshold_helper = div_rn(mul_rn(me, me), (double)rows);
-    } else {
-        // pick the factorisation up where the previous solver slot left it
-        nu[0] = park[4 * lane];
-        nd[0] = park[4 * lane + 1];
-        tailp[0] = park[4 * lane + 2];
-        pos[0] = __double2loint(park[4 * lane + 3]);
-#pragma unroll
-        for (int sl = 1; sl < SLOTS; sl++) nu[sl] = nd[sl] = tailp[sl] = 0.0, pos[sl] = 0;
-        const double* u = park + 4 * 32;
-        max_norm = u[0];
-        threshold_helper = u[1];
-        order = (unsigned long long)__double_as_longlong(u[2]);
-        f_order = (unsigned long long)__double_as_longlong(u[3]);
-        k0 = __double2loint(u[4]);
-        own_rank = __double2hiint(u[4]);
-        nonzero_pivots = __double2loint(u[5]);
-        f_rank = __double2hiint(u[5]);
-        const int bits = __double2loint(u[6]);
-        forced = (bits & 1) != 0;
-        differed = (bits & 2) != 0;
-        near_cut = (bits & 4) != 0;
-        __syncwarp();
     }
+    max_norm = warp_max(max_norm);
+    const double me = mul_rn(max_norm, DBL_EPSILON);
+    const double threshold_helper = div_rn(mul_rn(me, me), (double)rows);
     const double norm_downdate_threshold = 1.4901161193847656e-08;  // sqrt(epsilon)
-    int work = 0;
 #pragma unroll 1
-    for (int k = k0; k < size; k++) {
-        if (pausable && work >= FKS_QR_BUDGET) {
-            park[4 * lane] = nu[0];
-            park[4 * lane + 1] = nd[0];
-            park[4 * lane + 2] = tailp[0];
-            park[4 * lane + 3] = __hiloint2double(0, pos[0]);
-            if (lane == 0) {
-                double* u = park + 4 * 32;
-                u[0] = max_norm;
-                u[1] = threshold_helper;
-                u[2] = __longlong_as_double((long long)order);
-                u[3] = __longlong_as_double((long long)f_order);
-                u[4] = __hiloint2double(own_rank, k);
-                u[5] = __hiloint2double(f_rank, nonzero_pivots);
-                u[6] = __hiloint2double(0, (forced ? 1 : 0) | (differed ? 2 : 0) | (near_cut ? 4 : 0));
-            }
-            __syncwarp();
-            return false;
-        }
-        work += rows - k;
+    for (int k = 0; k < size; k++) {
         // biggest updated norm among the positions k .. cols-1, the first position wins (Eigen's maxCoeff scan)
         double bv = -1.0;
         int bp = 0x7fffffff, bc = 0;
@@ -1638,13 +1615,11 @@ __device__ __noinline__ bool colpiv_qr_lanes(int wb, double* A, int ld, int rows
         if (mine_pos) x[my_col] = xj;
     }
     __syncwarp();
-    return true;
 }
-// the solver for `cols` unknowns (+ the right-hand side): one column per quad when they fit 8 quads.  Returns false when
-// the factorisation was paused (call again with resume = true in the next solver slot).
-__device__ __forceinline__ bool colpiv_qr_solve(int wb, double* A, int ld, int rows, int cols, int x_off, bool resume) {
-    if (cols + 1 <= 8) return colpiv_qr_lanes<1>(wb, A, ld, rows, cols, x_off, resume);
-    return colpiv_qr_lanes<2>(wb, A, ld, rows, cols, x_off, resume);
+// the solver for `cols` unknowns (+ the right-hand side): one column per quad when they fit 8 quads
+__device__ __forceinline__ void colpiv_qr_solve(int wb, double* A, int ld, int rows, int cols, int x_off) {
+    if (cols + 1 <= 8) colpiv_qr_lanes<1>(wb, A, ld, rows, cols, x_off);
+    else colpiv_qr_lanes<2>(wb, A, ld, rows, cols, x_off);
 }
 
 // actuator noise of the next `count` microsteps, one truncated-normal draw per axis in axis order
@@ -1671,47 +1646,54 @@ __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// The kernel: a persistent grid, ONE CTA of kWarpsPerBlock warps per SM, one particle per warp.
+// The kernel: a persistent grid, ONE CTA of up to 32 warps per SM; a warp works on one particle at a time.
 //
-// The nested loops of the reference (controller step -> microstep -> resolver iteration) are flattened into
-// a per-warp state machine whose every cycle has the same shape:
+// The nested loops of the reference (controller step -> microstep -> resolver iteration) are flattened into a per-PARTICLE
+// state machine with two kinds of phases:
 //
-//     phase A   advance a kinematic state      apply_control / kinematics        (one call site)
-//     phase B   measure it                     max_motion  or  check_collision   (one call site each)
-//     phase T   bookkeeping, next operation    scalar code, noise draws
-//     phase C   collect corrections            only warps inside a contact resolution
-//     phase D   stacked-Jacobian QR solve      idem
+//     ROUND   A  advance a kinematic state      apply_control / kinematics
+//             B  measure it                     max_motion  or  check_collision
+//             T  bookkeeping, next operation    scalar code, noise draws, particle fetch / result record
+//     SOLVE   C  collect corrections            -- only for a particle whose last check found a collision --
+//             D  stacked-Jacobian QR solve
+//             E  motion estimate of the raw correction
 //
-// with CTA barriers between phases, so the warps of an SM execute the SAME building block at the same
-// time.  The profile of the free-running version (profiles/) showed 60 % of the issue slots lost to
-// instruction fetch: ~200 KB of SASS walked by 16 warps at unrelated places against a 32 KB instruction
-// cache.  In lock step the working set of a phase is a few KB.
+// LOCK STEP.  All warps of the CTA run the SAME phase at the same time (a CTA barrier per cycle).  The profile of a
+// free-running version showed 60 % of the issue slots lost to instruction fetch (a few hundred KB of SASS walked by the
+// warps at unrelated places against a 32 KB instruction cache), and every relaxation tried since -- private rounds, late
+// joiners, independent lock-step groups -- cost 5-40 % (profiles/r2_kernel_experiments.md).
+//
+// CONTEXT POOL.  Lock step alone wastes warps: in the contact regime a third of the rounds ends in a collision, and a warp
+// tied to its particle then waits for the others' rounds while they wait for its solve.  So warps are NOT tied to
+// particles: the CTA keeps `pool` (two per warp) particle CONTEXTS in flight -- configurations, link transforms,
+// control vectors, noise batch, bookkeeping: ~3.5 KB for the arm, in global memory (L2) unless a warp has them loaded --
+// and every cycle
+//     1. takes the census: how many contexts need a ROUND, how many a SOLVE;
+//     2. picks the phase: SOLVE as soon as a full batch (one per warp) is waiting or nothing else can run, else ROUND;
+//     3. every warp keeps its loaded context when that needs the chosen phase, else swaps it for one that does (store
+//        3.5 KB, load 3.5 KB), admitting a fresh particle when a ROUND has no taker;
+//     4. the phase runs once, and the census is updated.
+// Solve phases are full batches, round phases are full batches, and the only idle warps are those of the last cycles.
 // ------------------------------------------------------------------------------------------------
-// Resolver iterations a solver warp may chain inside one solver slot, each followed by a PRIVATE round (apply the correction,
-// check, transition) instead of waiting for round 0 of the next super-cycle.  0 = leave the slot right after the solve.
-// Measured (profiles/r1_kernel_experiments.md): chaining 2 / 4 / 8 iterations makes the arm 20-85 % slower (solver warps
-// drift apart in a 60 KB code region: instruction fetch), one private round gains 12 % on SE(2) (small kernel) and loses
-// 3-6 % on the arm -> 1 for SE(2), 0 otherwise.
-// Lock-step rounds a CTA runs between two CTA barriers while none of its warps is in contact (0 = a barrier every round).
+// Lock-step rounds a ROUND cycle runs while no context of the CTA is waiting for a solve (pure free flight: 3 extra).
 #ifndef FKS_FREE_ROUNDS
 #define FKS_FREE_ROUNDS 3
 #endif
-// Rounds group 1 may run while the solvers of a super-cycle are busy (it stops earlier when they finish).  The solvers are the
-// critical path and share the schedulers with group 1: measured 1 / 2 / 3 / 4 / 8 / 16 / 32 rounds on the arm contact workload
-// 107.6 / 101.5 / 100.4 / 102.3 / 105.4 / 105.5 / 107.4 ms, on SE(3) 58.7 / 51.8 / 50.9 / 49.4 / 49.9 / 50.0 / 50.4 ms.
-#ifndef FKS_G1_ROUNDS
-#define FKS_G1_ROUNDS(kind) ((kind) == FKS_ROBOT_LINKED ? 3 : 4)
+// ... and while some are (a warp whose particle collides sits out the rest of the cycle)
+#ifndef FKS_CONTACT_ROUNDS
+#define FKS_CONTACT_ROUNDS 1
 #endif
-#ifndef FKS_GROUPS
-#define FKS_GROUPS 1
+// waiting contexts that make the CTA switch to a SOLVE cycle, as a fraction (numerator / 8) of its warps
+#ifndef FKS_SOLVE_BATCH_EIGHTHS
+#define FKS_SOLVE_BATCH_EIGHTHS 8
 #endif
-// 0: a warp that needs a contact solve waits for the next super-cycle's slot; 1: it joins the running slot while any solver
-// of it is still busy; 2: while fewer than half of the slot's original solvers have finished
-#ifndef FKS_LATE_JOIN
-#define FKS_LATE_JOIN 0
+// ... and to a TALL cycle (the deferred solves of systems too tall for the small shared-memory store).  FKS_DEFER_TALL = 0
+// factors them in the solve cycle that collected them (the whole batch then waits for them).
+#ifndef FKS_TALL_BATCH_EIGHTHS
+#define FKS_TALL_BATCH_EIGHTHS 4
 #endif
-#ifndef FKS_SLOT_ITERATIONS
-#define FKS_SLOT_ITERATIONS(kind) ((kind) == FKS_ROBOT_SE2 ? 1 : 0)
+#ifndef FKS_DEFER_TALL
+#define FKS_DEFER_TALL 0
 #endif
 namespace {
 enum { OP_NONE = 0, OP_KIN = 1, OP_APPLY = 2 };
@@ -1727,14 +1709,31 @@ enum {
     AF_FAIL_KIN,        // previous configuration restored after a failed resolve
     AF_STOP_KIN,        // previous configuration restored after a collision with allow_contacts == false
     AF_NOCONTACT_KIN,   // step-start configuration restored -> the particle ends
-    AF_RESUME,          // contact kernel: the previous state of a parked particle is rebuilt -> rebuild and check the current one
     AF_DONE             // no particles left
 };
+enum { NEED_EMPTY = 0, NEED_ROUND = 1, NEED_SOLVE = 2, NEED_DEAD = 3, NEED_TALL = 4 };  // what a context of the pool waits for
+
+// a context's three ranges (fks_device_types.h) between the warp's shared block and its slot of the global context store
+__device__ __forceinline__ void context_copy(double* ws, double* g, const WarpLayout& wl, bool to_global) {
+    const int lane = lane_id();
+    const int n0 = wl.T + 2 * wl.L12 - wl.cfg, n1 = wl.L12, n2 = wl.save2_end - wl.target;
+    // (cache-global loads / stores: the slot is written and read by different warps of the CTA, the L1 is not coherent)
+    if (to_global) {
+        for (int e = lane; e < n0; e += 32) __stcg(g + e, ws[wl.cfg + e]);
+        for (int e = lane; e < n1; e += 32) __stcg(g + n0 + e, ws[wl.G + e]);
+        for (int e = lane; e < n2; e += 32) __stcg(g + n0 + n1 + e, ws[wl.target + e]);
+    } else {
+        for (int e = lane; e < n0; e += 32) ws[wl.cfg + e] = __ldcg(g + e);
+        for (int e = lane; e < n1; e += 32) ws[wl.G + e] = __ldcg(g + n0 + e);
+        for (int e = lane; e < n2; e += 32) ws[wl.target + e] = __ldcg(g + n0 + n1 + e);
+    }
+    __syncwarp();
+}
 }  // namespace
 
 // TRACE = true is the single-particle instantiation that records the step trace (fks_forward_simulate_traced); the batch
 // kernel carries none of it.
-template <int KIND, bool TRACE = false, int MODE = kModeAll>
+template <int KIND, bool TRACE = false>
 __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_kernel(const __grid_constant__ LaunchArgs args) {
     // ---- stage parameters, robot and points into shared memory, once per CTA ---------------------
     {
@@ -1772,7 +1771,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             const double reach = (0.5 * sqrt(ha) + 0.5 * sqrt(hb) + r->cap_radius[la] + r->cap_radius[lb] + diag) * (1.0 + 1e-9);
             f->pair_reach_sq[q] = reach * reach;
         }
-        if (threadIdx.x < 4) reinterpret_cast<unsigned*>(smem_raw + args.sync_off)[threadIdx.x] = 0u;
     }
     __syncthreads();
     const Frame& fr = frame();
@@ -1781,74 +1779,177 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
     const WarpLayout& wl = a.wl;
     const DevSolver& sp = a.sp;
     const int lane = lane_id();
-    const int wb = a.warps_off + (threadIdx.x >> 5) * wl.total * 8;
+    const int warp = (int)(threadIdx.x >> 5);
+    const int wb = a.warps_off + warp * wl.total * 8;
     double* ws = wsd(wb);
     const int D = rb.D, S = wl.S, stride = a.cfg_stride;
     if (lane < FKS_NUM_STATS) reinterpret_cast<unsigned long long*>(ws + wl.stats)[lane] = 0ull;
     __syncwarp();
     const double target_microstep_distance = a.env.map_res * 0.125;
     const double allowed_microstep_distance = a.env.map_res * 1.0;
-
-    // ---- warp state -----------------------------------------------------------------------------------
-    // Hot control variables stay in registers; the bookkeeping of the particle lives in the warp's shared block
-    // (WarpVars: one copy per warp instead of one per lane -- at 64 registers per thread it would otherwise spill).
-    int after = AF_FETCH;
-    int op = OP_NONE, op_in = 0, op_out = 0, op_u = 0, op_tn = -1, op_derive = 0, measure = M_NONE;
-    int cur = 0, prev = 0;
     WarpVars* wv = reinterpret_cast<WarpVars*>(ws + wl.vars);
     double* pid_state = ws + wl.vars + kWarpVarsDoubles;  // [0..S) integral, [S..2S) last error: lane i owns axis i
-    double m_result = 0.0;
-    unsigned cc = 0u;
+
+    // ---- the CTA's context pool: scheduling state in shared memory behind the warp blocks ------------------------------
+    const int n_warps = a.warps_per_block, pool = a.pool;
+    unsigned char* need = smem_raw + a.sync_off + 16;                     // [pool] NEED_*
+    signed char* holds = reinterpret_cast<signed char*>(need + kMaxPool); // [warps] the context in the warp's block, -1: none
+    volatile unsigned* exhausted = reinterpret_cast<volatile unsigned*>(smem_raw + a.sync_off);  // no particles left to admit
+    char* store = a.ctx_store + (size_t)blockIdx.x * pool * a.ctx_stride;
+    for (int c = threadIdx.x; c < kMaxPool; c += blockDim.x) {
+        need[c] = c < n_warps ? NEED_ROUND : (c < pool ? NEED_EMPTY : NEED_DEAD);  // context w starts out in warp w, about to fetch
+        holds[c] = c < n_warps ? (signed char)c : (signed char)-1;
+    }
+    if (threadIdx.x == 0) *exhausted = 0u;
+    if (lane == 0) {
+        wv->after = AF_FETCH;
+        wv->op = OP_NONE;
+        wv->measure = M_NONE;
+        wv->want_solve = 0;
+        wv->cc = 0u;
+        wv->cur = wv->prev = 0;
+        wv->m_result = 0.0;
+        wv->ctx = warp;
+    }
+    __syncwarp();
 
 #ifdef FKS_PHASE_TIMERS
     long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tqr[4] = {0, 0, 0, 0};
-    long long textra[4] = {0, 0, 0, 0};  // super-cycles, sum of solver warps, group-1 extra rounds, estimate clocks
+    long long textra[4] = {0, 0, 0, 0};  // cycles, sum of solver warps over the solve cycles, solve cycles, estimate clocks
     long long t0 = clock64(), t1;
 #define FKS_TICK(i) { t1 = clock64(); tacc[i] += t1 - t0; t0 = t1; }
+    long long tcyc[4] = {0, 0, 0, 0};  // warp 0: clocks of round cycles, their number, clocks of solve cycles, their number
+    long long tc_start = clock64();
+    int last_kind = -1;
+    __shared__ unsigned cyc_max[8];     // per cycle: longest A, B, T, swap, collect, solve, estimate of any warp
+    long long tmax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (threadIdx.x < 8) cyc_max[threadIdx.x] = 0u;
+#define FKS_MAXTICK(i, since) { if (lane == 0) atomicMax(&cyc_max[i], (unsigned)(clock64() - (since))); }
 #else
 #define FKS_TICK(i)
+#define FKS_MAXTICK(i, since)
 #endif
-    // Barriers.  Round 0 of a super-cycle is run by the whole CTA (barrier 0).  If some warps then need a
-    // contact solve (group 2: collect + QR, barrier 2), the others (group 1) do not wait for them: they keep
-    // running lock-step A / B / T rounds among themselves on barrier 1 until group 2 is finished.  Two code
-    // regions are live at any time instead of one -- still a few KB each.
-    // The CTA's warps form FKS_GROUPS independent lock-step groups (named barriers 1 + 2 g / 2 + 2 g): while one group is
-    // in a solver slot another one is usually in a round, which evens out the number of warps that can issue.
-    const int wpg = (a.warps_per_block + FKS_GROUPS - 1) / FKS_GROUPS;
-    const int grp = (int)(threadIdx.x >> 5) / wpg;
-    const int n_warps = min(wpg, a.warps_per_block - grp * wpg);
-    const int bar_full = 1 + 2 * grp, bar_g1 = 2 + 2 * grp;
-    volatile unsigned* g2_done = reinterpret_cast<volatile unsigned*>(smem_raw + a.sync_off) + 2 * grp;  // solvers that finished
-    volatile unsigned* g2_late = g2_done + 1;  // warps that joined the running slot late (FKS_LATE_JOIN)
-    bool want_solve = false;
-    int free_rounds = 0, free_streak = 0;  // rounds the next super-cycle runs before its first CTA barrier (free flight only)
     for (;;) {
-        int bar_id = bar_full, bar_threads = 32 * n_warps, n_solvers = 0;
-        bool counted_solver = false;
-        int slot_iter = 0;
-        constexpr int kSlotIters = FKS_SLOT_ITERATIONS(KIND);
-        for (int round = 0;; round++) {
-        // =========================== phase A: advance a kinematic state ===============================
-        if (!want_solve) {
-            if (op == OP_KIN) kinematics<KIND>(wb, op_out, op_derive);
-            else if (op == OP_APPLY) apply_control<KIND>(wb, op_in, op_out, op_u, op_tn, op_derive);
+        __syncthreads();  // the census of the previous cycle is complete (and what it parked is in global memory)
+#ifdef FKS_PHASE_TIMERS
+        {
+            const long long now = clock64();
+            if (last_kind >= 0) {
+                tcyc[2 * last_kind] += now - tc_start;
+                tcyc[2 * last_kind + 1] += 1;
+            }
+            tc_start = now;
+            for (int i = 0; i < 8; i++) tmax[i] += cyc_max[i];
         }
-        FKS_TICK(0)
-#ifdef FKS_BARRIER_AB
-        named_barrier(bar_id, bar_threads);
+        __syncthreads();
+        if (threadIdx.x < 8) cyc_max[threadIdx.x] = 0u;
+        __syncthreads();
+        const long long tm_swap = clock64();
 #endif
+        FKS_TICK(5)
+        // ---- 1. census: every warp reads the same snapshot and derives the same plan, so one barrier per cycle is enough ----
+        const int n_lo = need[lane], n_hi = need[32 + lane];  // lane c / c + 32 looks at context c / c + 32 (NEED_DEAD beyond the pool)
+        const int h = lane < n_warps ? (int)holds[lane] : -1; // lane w looks at warp w
+        const int ns = __popc(__ballot_sync(FKS_FULL, n_lo == NEED_SOLVE)) + __popc(__ballot_sync(FKS_FULL, n_hi == NEED_SOLVE));
+        const int nt = __popc(__ballot_sync(FKS_FULL, n_lo == NEED_TALL)) + __popc(__ballot_sync(FKS_FULL, n_hi == NEED_TALL));
+        const int nr = __popc(__ballot_sync(FKS_FULL, n_lo == NEED_ROUND)) + __popc(__ballot_sync(FKS_FULL, n_hi == NEED_ROUND));
+        const unsigned e_lo = __ballot_sync(FKS_FULL, n_lo == NEED_EMPTY), e_hi = __ballot_sync(FKS_FULL, n_hi == NEED_EMPTY);
+        const bool can_admit = (e_lo | e_hi) != 0u && *exhausted == 0u;
+        if (ns + nt + nr == 0 && !can_admit) break;  // every particle of this CTA has ended and there is none left to fetch
+        // ---- 2. phase: a batch of solves (or of deferred tall solves) as soon as it is big enough, or when the rounds run out
+        //         of takers; else a round ----------------------------------------------------------------------------------
+        const int round_supply = nr + (can_admit ? __popc(e_lo) + __popc(e_hi) : 0);
+        int want = NEED_ROUND;
+        if (ns > 0 && 8 * ns >= FKS_SOLVE_BATCH_EIGHTHS * n_warps) want = NEED_SOLVE;
+        else if (nt > 0 && 8 * nt >= FKS_TALL_BATCH_EIGHTHS * n_warps) want = NEED_TALL;
+        else if (2 * round_supply < n_warps && (ns > round_supply || nt > round_supply)) want = ns >= nt ? NEED_SOLVE : NEED_TALL;
+        else if (round_supply == 0) want = ns >= nt ? NEED_SOLVE : NEED_TALL;
+        const bool solve_phase = want != NEED_ROUND;
+#ifdef FKS_PHASE_TIMERS
+        last_kind = solve_phase ? 1 : 0;
+#endif
+        // ---- 3. contexts: a warp keeps the one in its block when that wants this phase; the others share out, in warp
+        //         order, the waiting contexts nobody holds, then (ROUND only) the empty ones, which admit fresh particles ----
+        const bool keeps = h >= 0 && need[h] == want;                       // does warp `lane` keep its context?
+        const unsigned keep_mask = __ballot_sync(FKS_FULL, keeps);
+        const unsigned held_lo = __reduce_or_sync(FKS_FULL, (h >= 0 && h < 32) ? (1u << h) : 0u);
+        const unsigned held_hi = __reduce_or_sync(FKS_FULL, (h >= 32) ? (1u << (h - 32)) : 0u);
+        const unsigned r_lo = __ballot_sync(FKS_FULL, n_lo == want) & ~held_lo, r_hi = __ballot_sync(FKS_FULL, n_hi == want) & ~held_hi;
+        const int my = (int)holds[warp];
+        const bool keep = (keep_mask >> warp) & 1u;
+        bool active = keep;
+        int got = -1;
+        bool fresh = false;
+        if (!keep) {
+            const int rank = __popc(~keep_mask & ((1u << warp) - 1u));      // my place among the warps that look for work
+            const int n_r_lo = __popc(r_lo), n_ready = n_r_lo + __popc(r_hi);
+            if (rank < n_ready) {
+                got = rank < n_r_lo ? (int)__fns(r_lo, 0, rank + 1) : 32 + (int)__fns(r_hi, 0, rank - n_r_lo + 1);
+            } else if (!solve_phase && can_admit) {
+                const int k = rank - n_ready, n_e_lo = __popc(e_lo);
+                if (k < n_e_lo + __popc(e_hi)) {
+                    got = k < n_e_lo ? (int)__fns(e_lo, 0, k + 1) : 32 + (int)__fns(e_hi, 0, k - n_e_lo + 1);
+                    fresh = true;
+                }
+            }
+            if (got >= 0) {
+                // the context in the block (if any) is not needed in this phase: it waits in the global store
+                if (my >= 0) context_copy(ws, reinterpret_cast<double*>(store + (size_t)my * a.ctx_stride), wl, true);
+                if (fresh) {
+                    // a fresh context: its first round fetches a particle
+                    if (lane == 0) {
+                        wv->after = AF_FETCH;
+                        wv->op = OP_NONE;
+                        wv->measure = M_NONE;
+                        wv->want_solve = 0;
+                        wv->cc = 0u;
+                        wv->cur = wv->prev = 0;
+                        wv->m_result = 0.0;
+                        wv->ctx = got;
+                    }
+                    __syncwarp();
+                } else {
+                    context_copy(ws, reinterpret_cast<double*>(store + (size_t)got * a.ctx_stride), wl, false);
+                }
+                if (lane == 0) holds[warp] = (signed char)got;
+                active = true;
+            }
+        }
+        const int ctx = keep ? my : got;  // the context this warp runs in this cycle (when active)
+        FKS_MAXTICK(3, tm_swap)
         FKS_TICK(1)
-        // =========================== phase B: measure =================================================
-        if (!want_solve) {
-            if (measure == M_MOTION) m_result = max_motion(wb, op_in, op_out);  // spcs:1492-1527
-            else if (measure == M_CHECK) cc = check_collision<KIND>(wb, prev, cur, a.cull_mode == 2 ? ((cc & 1u) ? 0 : 1) : a.cull_mode);  // spcs:1418-1436
-        }
-        FKS_TICK(2)
-#ifdef FKS_BARRIER_BT
-        named_barrier(bar_id, bar_threads);
+        // ---- 4. the phase ----------------------------------------------------------------------------------------------
+        if (active) {
+        int after = wv->after, op = wv->op, op_in = wv->op_in, op_out = wv->op_out, op_u = wv->op_u, op_tn = wv->op_tn,
+            op_derive = wv->op_derive, measure = wv->measure, cur = wv->cur, prev = wv->prev;
+        bool want_solve = wv->want_solve != 0, tall_pending = false;
+        unsigned cc = wv->cc;
+        double m_result = wv->m_result;
+        __syncwarp();
+        if (!solve_phase) {
+        // pure free flight (no context of the CTA waits for a solve): several rounds per cycle, a barrier every fourth round only
+        const int n_rounds = (ns == 0) ? 1 + FKS_FREE_ROUNDS : FKS_CONTACT_ROUNDS;
+        for (int round = 0; round < n_rounds && !want_solve && after != AF_DONE; round++) {
+        // =========================== phase A: advance a kinematic state ===============================
+#ifdef FKS_PHASE_TIMERS
+        const long long tmA = clock64();
 #endif
-        FKS_TICK(3)
+        if (op == OP_KIN) kinematics<KIND>(wb, op_out, op_derive);
+        else if (op == OP_APPLY) apply_control<KIND>(wb, op_in, op_out, op_u, op_tn, op_derive);
+        FKS_MAXTICK(0, tmA)
+        FKS_TICK(0)
+        // =========================== phase B: measure =================================================
+#ifdef FKS_PHASE_TIMERS
+        const long long tmB = clock64();
+#endif
+        if (measure == M_MOTION) m_result = max_motion(wb, op_in, op_out);  // spcs:1492-1527
+        else if (measure == M_CHECK) cc = check_collision<KIND>(wb, prev, cur, a.cull_mode == 2 ? ((cc & 1u) ? 0 : 1) : a.cull_mode);  // spcs:1418-1436
+        FKS_MAXTICK(1, tmB)
+        FKS_TICK(2)
+#ifdef FKS_PHASE_TIMERS
+        const long long tmT = clock64();
+#endif
         // =========================== phase T: transitions =============================================
         if (!want_solve) {
         op = OP_NONE;
@@ -1865,30 +1966,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         unsigned long long next_id = 0ull;
                         if (lane == 0) next_id = (unsigned long long)atomicAdd(a.counter, 1u);
                         next_id = __shfl_sync(FKS_FULL, next_id, 0);
-                        if (MODE == kModeContact) {
-                            // a particle the free-flight kernel parked at its first colliding microstep
-                            if (next_id >= (unsigned long long)a.park_meta[0]) {
-                                after = AF_DONE;
-                                break;
-                            }
-                            const double* rec = reinterpret_cast<const double*>(a.park + (size_t)a.park_order[next_id] * a.park_stride);
-                            const int span = wl.stats - wl.target;
-                            for (int e = lane; e < 3 * S; e += 32) ws[wl.cfg + e] = rec[e];
-                            for (int e = lane; e < span; e += 32) ws[wl.target + e] = rec[3 * S + e];
-                            const int2 hdr = *reinterpret_cast<const int2*>(rec + 3 * S + span);
-                            if (lane == 0) *reinterpret_cast<unsigned*>(ws + wl.flags) = *reinterpret_cast<const unsigned*>(rec + 3 * S + span + 1);
-                            cur = hdr.x;
-                            prev = hdr.y;
-                            cc = 0u;
-                            __syncwarp();
-                            // the link transforms are not parked: rebuild the previous state, then the current one with its check
-                            // (the same check that sent the particle here: it ends in AF_MICRO_CHECK with the same answer)
-                            op = OP_KIN;
-                            op_out = prev;
-                            op_derive = 0;
-                            after = AF_RESUME;
-                            break;
-                        }
                         wv->pid = next_id;  // every lane stores the same value
                         if (next_id >= a.n_particles) {
                             after = AF_DONE;
@@ -1919,7 +1996,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             wv->dec_end = a.dec_off[wv->pid + 1];
                         }
                         wv->collided = wv->any_resolve_failed = false;
-                        wv->qr_rows = 0;
                         wv->flags = wv->n_micro_total = wv->n_iter_total = wv->n_steps = 0u;
                         wv->step = 0u;
                         op = OP_KIN;
@@ -1928,13 +2004,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         after = AF_INIT;
                         break;
                     }
-                    case AF_RESUME:
-                        op = OP_KIN;
-                        op_out = cur;
-                        op_derive = 1;
-                        measure = M_CHECK;
-                        after = AF_MICRO_CHECK;
-                        break;
                     case AF_INIT:
                         ev = 1;
                         break;
@@ -1973,28 +2042,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                             if (in_collision && !a.allow_contacts)
                                 trace_append(FKS_TRACE_RETURNED_PREVIOUS, wv->step, wv->micro, 0u, ws + wl.cfg + prev * S, stride);  // spcs:1778
                         }
-                        if (in_collision && a.allow_contacts && MODE == kModeFree) {
-                            // free-flight kernel: the particle leaves for the contact kernel as it is (configurations, control
-                            // vectors, noise batch, bookkeeping; transforms are rebuilt there), keyed by how early it got here
-                            unsigned slot = 0u;
-                            const unsigned key = wv->step < (unsigned)(kParkBuckets - 1) ? wv->step : (unsigned)(kParkBuckets - 1);
-                            if (lane == 0) {
-                                slot = atomicAdd(a.park_meta, 1u);
-                                atomicAdd(a.park_meta + 1 + key, 1u);
-                                a.park_key[slot] = key;
-                            }
-                            slot = __shfl_sync(FKS_FULL, slot, 0);
-                            double* rec = reinterpret_cast<double*>(a.park + (size_t)slot * a.park_stride);
-                            const int span = wl.stats - wl.target;
-                            for (int e = lane; e < 3 * S; e += 32) rec[e] = ws[wl.cfg + e];
-                            for (int e = lane; e < span; e += 32) rec[3 * S + e] = ws[wl.target + e];
-                            if (lane == 0) {
-                                *reinterpret_cast<int2*>(rec + 3 * S + span) = make_int2(cur, prev);
-                                *reinterpret_cast<unsigned*>(rec + 3 * S + span + 1) = *reinterpret_cast<const unsigned*>(ws + wl.flags);
-                            }
-                            __syncwarp();
-                            after = AF_FETCH;
-                        } else if (in_collision && a.allow_contacts) {
+                        if (in_collision && a.allow_contacts) {
                             wv->resolver_iterations = 0u;
                             wv->scaling = sp.initial_step;
                             want_solve = true;
@@ -2228,116 +2276,71 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                 after = AF_FETCH;
             }
         }
-        }  // if (!want_solve): end of phase T
+        }  // end of phase T
+        FKS_MAXTICK(2, tmT)
         FKS_TICK(4)
-        if (counted_solver) {
-            // A solver warp has just run a PRIVATE round (kSlotIters > 0): the phases above applied its correction step, checked it
-            // and made the transition.  Still in collision and iterations left in this slot -> the next resolver iteration right
-            // away; resolved (or budget used) -> out, the pending operation runs in round 0 of the next super-cycle.
-            if (!want_solve || slot_iter >= kSlotIters) break;
+        }  // rounds
         } else {
-            if (round < free_rounds) continue;  // free flight: a CTA barrier every (free_rounds + 1) rounds only
-            if (round == free_rounds) {
-                n_solvers = named_barrier_popc(bar_full, 32 * n_warps, want_solve) >> 5;  // barrier of the whole group; the count is in threads
-                FKS_TICK(5)
-#ifdef FKS_PHASE_TIMERS
-                textra[0] += 1;
-                textra[1] += n_solvers;
-#endif
-                if (n_solvers == 0) break;         // nobody solves: next super-cycle
-                counted_solver = want_solve;       // group 2 goes to collect + solve (below)
-                if (!counted_solver) {
-                    bar_id = bar_g1;               // group 1 keeps going on its own barrier
-                    bar_threads = 32 * (n_warps - n_solvers);
-                }
-            }
-#if FKS_LATE_JOIN
-            if (!counted_solver && round > free_rounds) {
-                // LATE JOINERS.  A group-1 warp whose round ended in a collision would otherwise idle until the next super-cycle's
-                // slot; while the slot of this one is still running it leaves group 1 (the others learn how many left from the
-                // barrier's count) and runs its own collect + solve + estimate right away.
-                bool leave = false;
-                if (want_solve) {
-                    unsigned ok = 0u;
-                    if (lane == 0)
-                        ok = (FKS_LATE_JOIN == 1) ? (*g2_done < (unsigned)n_solvers + *g2_late) : (2u * *g2_done < (unsigned)n_solvers);
-                    leave = __shfl_sync(FKS_FULL, ok, 0) != 0u;
-                }
-                const int n_leave = named_barrier_popc(bar_g1, bar_threads, leave) >> 5;
-                if (leave) {
-                    counted_solver = true;
-                    if (lane == 0) atomicAdd(const_cast<unsigned*>(g2_late), 1u);
-                } else {
-                    bar_threads -= 32 * n_leave;
-                }
-            }
-#endif
-            if (!counted_solver) {
-                // group 1 only: another round while group 2 is still busy (decision made uniform by the barrier reduction)
-                const bool keep = (*g2_done < (unsigned)n_solvers + *g2_late) && (round < FKS_G1_ROUNDS(KIND) * (kSlotIters > 1 ? kSlotIters : 1));
-                const bool go_on = named_barrier_or(bar_g1, bar_threads, keep);
-                FKS_TICK(1)
-#ifdef FKS_PHASE_TIMERS
-                textra[2] += 1;
-#endif
-                if (!go_on) break;
-                continue;
-            }
-        }
-        // =========================== solver slot: phase C, collect corrections (spcs:1627) ==============
-        if (MODE == kModeFree) break;  // (never reached: the free-flight kernel parks a particle instead of solving)
-        {
+        // =========================== SOLVE: phase C, collect corrections (spcs:1627) ====================
+        // (TALL: the corrections were collected in an earlier solve cycle and wait in the context's global store)
             int rows = 0;
 #ifdef FKS_PHASE_TIMERS
             const long long tc0 = clock64();
+            textra[1] += 1;
 #endif
-            double* jstore = reinterpret_cast<double*>(scratch_slot() + a.sl.jstore);
-            int jld = a.sl.ldj;
-            const bool resumed = wv->qr_rows > 0;  // a tall system whose factorisation was paused in the previous slot
-            if (resumed) {
-                rows = wv->qr_rows;
+            double* jstore = ws + wl.jsm;
+            int jld = wl.jsm_ld;
+            bool deferred = false;
+            if (want == NEED_TALL) {
+                rows = wv->pend_rows;
+                place_tall_system(wb, rows, D, &jstore, &jld);
             } else {
                 rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
                 if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
-                if (rows > 0) place_system(wb, rows, D, &jstore, &jld);
+                if (rows > (wl.jsm_ld / 3) * 3) {
+                    spill_system(wb, D);
+                    if (FKS_DEFER_TALL) {
+                        deferred = true;
+                        if (lane == 0) wv->pend_rows = rows;
+                        __syncwarp();
+                    } else {
+                        place_tall_system(wb, rows, D, &jstore, &jld);
+                    }
+                }
             }
 #ifdef FKS_PHASE_TIMERS
             tacc[10] += clock64() - tc0;
             tacc[11] += 1;
 #endif
+            FKS_MAXTICK(4, tc0)
             FKS_TICK(6)
-            FKS_TICK(7)
+            if (!deferred) {
             // ======================= phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
 #ifdef FKS_PHASE_TIMERS
             const long long tq0 = clock64();
 #endif
-            bool solved = true;
             if (rows == 0) {
                 // Eigen would return an empty vector and ApplyControlInput would assert; documented device
-                // behaviour: zero correction wv->step
+                // behaviour: zero correction step
                 wv->flags |= FKS_FLAG_EMPTY_JACOBIAN;
                 if (lane < D) ws[wl.raw + lane] = 0.0;
                 __syncwarp();
             } else {
-                solved = colpiv_qr_solve(wb, jstore, jld, rows, D, wl.raw, resumed);
-                __syncwarp();
-                if (lane == 0) wv->qr_rows = solved ? 0 : rows;
+                colpiv_qr_solve(wb, jstore, jld, rows, D, wl.raw);
                 __syncwarp();
             }
 #ifdef FKS_PHASE_TIMERS
             if (jstore == ws + wl.jsm) { tqr[0] += clock64() - tq0; tqr[1] += 1; } else { tqr[2] += clock64() - tq0; tqr[3] += 1; }
-#endif
-            // motion estimate of the raw correction (spcs:1630) in the same solver slot: one lock-step round per
-            // resolver iteration instead of two
-            if (solved) {
-#ifdef FKS_PHASE_TIMERS
+            FKS_MAXTICK(5, tq0)
             const long long te0 = clock64();
 #endif
+            // ======================= phase E: motion estimate of the raw correction (spcs:1630) =========
             apply_control<KIND>(wb, cur, 2, wl.raw, -1, 0);
             m_result = max_motion(wb, cur, 2);
 #ifdef FKS_PHASE_TIMERS
             textra[3] += clock64() - te0;
 #endif
+            FKS_MAXTICK(6, te0)
             {  // spcs:1681-1689
                 const double step_fraction = fmax(m_result / allowed_microstep_distance, 1.0);
                 if (lane < D) ws[wl.stepv + lane] = (ws[wl.raw + lane] / step_fraction) * fabs(wv->scaling);
@@ -2347,27 +2350,28 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             measure = M_CHECK;
             after = AF_RESOLVE_CHECK;
             want_solve = false;
-            }  // a paused warp keeps want_solve: it is a solver of the next slot again and skips the rounds until then
-            slot_iter++;
-            if (!solved || kSlotIters == 0) break;
+            }  // !deferred
+            tall_pending = deferred;
+            FKS_TICK(8)
         }
-        }  // rounds
-        if (counted_solver) {
-            __syncwarp();
-            if (lane == 0) atomicAdd(const_cast<unsigned*>(g2_done), 1u);
+        // the context's control state goes back to its block, its need into the census
+        __syncwarp();
+        if (lane == 0) {
+            wv->after = after; wv->op = op; wv->op_in = op_in; wv->op_out = op_out; wv->op_u = op_u; wv->op_tn = op_tn;
+            wv->op_derive = op_derive; wv->measure = measure; wv->cur = cur; wv->prev = prev;
+            wv->want_solve = want_solve ? 1 : 0;
+            wv->cc = cc;
+            wv->m_result = m_result;
+            need[ctx] = tall_pending ? NEED_TALL : (want_solve ? NEED_SOLVE : (after == AF_DONE ? NEED_DEAD : NEED_ROUND));
+            if (after == AF_DONE) *exhausted = 1u;
         }
-        FKS_TICK(8)
-        // (only after several solver-free super-cycles in a row: in the contact regime an occasional empty super-cycle must
-        // not delay the next slot)
-        free_streak = (n_solvers == 0) ? free_streak + 1 : 0;
-        free_rounds = (free_streak >= 4) ? FKS_FREE_ROUNDS : 0;
-        const bool all_done = named_barrier_and(bar_full, 32 * n_warps, after == AF_DONE && !want_solve);
+        __syncwarp();
+        }  // active
+#ifdef FKS_PHASE_TIMERS
+        textra[0] += 1;
+        if (solve_phase) textra[2] += 1;
+#endif
         FKS_TICK(9)
-        if (all_done) break;
-        if ((int)threadIdx.x == 32 * grp * wpg) {  // next read is at least two full barriers away
-            *g2_done = 0u;
-            *g2_late = 0u;
-        }
     }
 #ifdef FKS_PHASE_TIMERS
     if (lane == 0)
@@ -2375,6 +2379,10 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         for (int i = 0; i < 12; i++) atomicAdd(a.stats + 16 + i, (unsigned long long)tacc[i]);
         for (int i = 0; i < 4; i++) atomicAdd(a.stats + 28 + i, (unsigned long long)tqr[i]);
         for (int i = 0; i < 4; i++) atomicAdd(a.stats + 32 + i, (unsigned long long)textra[i]);
+        if (warp == 0) {
+            for (int i = 0; i < 4; i++) atomicAdd(a.stats + 36 + i, (unsigned long long)tcyc[i]);
+            for (int i = 0; i < 8; i++) atomicAdd(a.stats + 40 + i, (unsigned long long)tmax[i]);
+        }
     }
 #endif
     __syncwarp();
@@ -2404,7 +2412,7 @@ __device__ __noinline__ bool self_collision_bool(int wb, int X, double check_res
     const double* caps = ws + wl.caps;
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch_slot() + fr.a.sl.keys);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(context_scratch(wb) + fr.a.sl.keys);
     const double diag = 2.0 * 1.7320508075688772 * check_resolution * (1.0 + 1e-6) + 1e-9;  // cells at index 0 are two cells wide
     bool found = false;
     bool keys_ready = false;
@@ -2498,6 +2506,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) check_config
     const int lane = lane_id();
     const int wb = a.warps_off + (threadIdx.x >> 5) * a.wl.total * 8;
     double* ws = wsd(wb);
+    if (lane == 0) reinterpret_cast<WarpVars*>(ws + a.wl.vars)->ctx = (int)(threadIdx.x >> 5);  // scratch slot of this warp
+    __syncwarp();
     const double map_res = a.env.map_res;
     const unsigned long long warps_total = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.n_particles; i += warps_total) {
@@ -2526,7 +2536,7 @@ __global__ void __launch_bounds__(128) qr_solve_kernel(double* work, const unsig
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        f->a.wl = make_warp_layout(1, 0, cols, cols, 160);  // room for the state of a paused factorisation
+        f->a.wl = make_warp_layout(1, 0, cols, cols);
         f->a.warps_off = (int)((sizeof(Frame) + 15) & ~(size_t)15);
     }
     __syncthreads();
@@ -2538,8 +2548,7 @@ __global__ void __launch_bounds__(128) qr_solve_kernel(double* work, const unsig
     for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps_total) {
         if (lane == 0) *reinterpret_cast<unsigned*>(ws + fr.a.wl.flags) = 0u;
         __syncwarp();
-        bool done = colpiv_qr_solve(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw, false);
-        while (!done) done = colpiv_qr_solve(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw, true);  // tall systems pause
+        colpiv_qr_solve(wb, work + offsets[i], rows[i], rows[i], cols, fr.a.wl.raw);
         if (lane < cols) x_out[(size_t)i * cols + lane] = ws[fr.a.wl.raw + lane];
         if (lane == 0) flags_out[i] = *reinterpret_cast<const unsigned*>(ws + fr.a.wl.flags);
         __syncwarp();
@@ -2587,7 +2596,7 @@ size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stri
     const size_t warps_off = pts_off + (size_t)P * (sizeof(double2) + sizeof(PointZL));
     // shared-memory Jacobian store: whatever the CTA leaves free goes to it, up to every point of the robot (3 P rows)
     const WarpLayout w0 = make_warp_layout(L, J, D, stride, 0);
-    const size_t base = warps_off + (size_t)warps_per_block * w0.total * 8 + 16;
+    const size_t base = warps_off + (size_t)warps_per_block * w0.total * 8 + kSyncBytes;
     int extra = 0;
     if (smem_limit > base) {
         const long long spare = (long long)((smem_limit - base) / (size_t)warps_per_block / 8);
@@ -2598,55 +2607,27 @@ size_t simulate_smem_plan(LaunchArgs* args, int L, int J, int D, int P, int stri
         if (e < 0) e = 0;
         extra = (int)(e & ~1ll);
         // (the layout pads for alignment: step back until the CTA fits again)
-        while (extra > 0 && warps_off + (size_t)warps_per_block * make_warp_layout(L, J, D, stride, extra).total * 8 + 16 > smem_limit) extra -= 2;
+        while (extra > 0 && warps_off + (size_t)warps_per_block * make_warp_layout(L, J, D, stride, extra).total * 8 + kSyncBytes > smem_limit) extra -= 2;
     }
     args->wl = make_warp_layout(L, J, D, stride, extra);
     args->pts_off = (int)pts_off;
     args->warps_off = (int)warps_off;
     size_t off = warps_off + (size_t)warps_per_block * args->wl.total * 8;
-    args->sync_off = (int)off;  // one 16-byte word of CTA-level synchronisation state
-    off += 16;
+    args->sync_off = (int)off;  // CTA-level scheduling state (context pool)
+    off += kSyncBytes;
     return off;
 }
 
-template <int KIND>
-static const void* kernel_ptr_of(bool trace, int mode) {
-    if (trace) return (const void*)simulate_kernel<KIND, true, kModeAll>;
-    if (mode == kModeFree) return (const void*)simulate_kernel<KIND, false, kModeFree>;
-    if (mode == kModeContact) return (const void*)simulate_kernel<KIND, false, kModeContact>;
-    return (const void*)simulate_kernel<KIND, false, kModeAll>;
-}
-static const void* kernel_ptr(int kind, bool trace = false, int mode = kModeAll) {
+static const void* kernel_ptr(int kind, bool trace = false) {
     switch (kind) {
-        case FKS_ROBOT_SE2: return kernel_ptr_of<FKS_ROBOT_SE2>(trace, mode);
-        case FKS_ROBOT_SE3: return kernel_ptr_of<FKS_ROBOT_SE3>(trace, mode);
-        case FKS_ROBOT_LINKED: return kernel_ptr_of<FKS_ROBOT_LINKED>(trace, mode);
+        case FKS_ROBOT_SE2: return trace ? (const void*)simulate_kernel<FKS_ROBOT_SE2, true> : (const void*)simulate_kernel<FKS_ROBOT_SE2>;
+        case FKS_ROBOT_SE3: return trace ? (const void*)simulate_kernel<FKS_ROBOT_SE3, true> : (const void*)simulate_kernel<FKS_ROBOT_SE3>;
+        case FKS_ROBOT_LINKED: return trace ? (const void*)simulate_kernel<FKS_ROBOT_LINKED, true> : (const void*)simulate_kernel<FKS_ROBOT_LINKED>;
     }
     return nullptr;
 }
 
-size_t park_record_bytes(const WarpLayout& wl) { return (size_t)(3 * wl.S + (wl.stats - wl.target) + 2) * 8; }
-
-// Counting sort of the parked particles by key (the controller step of their first contact: the earlier, the more work is
-// left): order[base[key] + i] = arrival index.  The order inside a bucket does not matter (it only schedules).
-__global__ void park_order_kernel(unsigned* meta, const unsigned* key, unsigned* order) {
-    __shared__ unsigned base[kParkBuckets];
-    const unsigned count = meta[0];
-    if (threadIdx.x < kParkBuckets) {
-        unsigned b = 0u;
-        for (int i = 0; i < (int)threadIdx.x; i++) b += meta[1 + i];
-        base[threadIdx.x] = b;
-    }
-    __syncthreads();
-    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
-        const unsigned b = key[e];
-        order[base[b] + atomicAdd(meta + 1 + kParkBuckets + b, 1u)] = e;
-    }
-}
-int launch_park_order(const LaunchArgs& args, int grid, void* stream) {
-    park_order_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(args.park_meta, args.park_key, args.park_order);
-    return (int)cudaGetLastError();
-}
+size_t context_bytes(const WarpLayout& wl) { return (size_t)((wl.T + 2 * wl.L12 - wl.cfg) + wl.L12 + (wl.save2_end - wl.target)) * 8; }
 
 int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelInfo* out) {
     const void* fn = kernel_ptr(kind);
@@ -2667,10 +2648,10 @@ int simulate_kernel_info(int kind, size_t dyn_smem, int warps_per_block, KernelI
     return 0;
 }
 
-int launch_simulate(int kind, int mode, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
+int launch_simulate(int kind, const LaunchArgs& args, int grid, size_t dyn_smem, void* stream,
                     const void* l2_window_base, size_t l2_window_bytes) {
     const int block_threads = 32 * args.warps_per_block;
-    const void* fn = kernel_ptr(kind, args.trace != nullptr, mode);
+    const void* fn = kernel_ptr(kind, args.trace != nullptr);
     if (!fn) return (int)cudaErrorInvalidValue;
     {
         // the attribute is per function and per device, and simulators of the same robot kind share the function: set it for
@@ -2725,7 +2706,7 @@ int launch_check_config(int kind, const LaunchArgs& args, int grid, size_t dyn_s
 int launch_qr_solve(double* work, const unsigned long long* offsets, const int* rows, int cols, int n, double* x_out, unsigned* flags_out,
                     void* stream) {
     const int warps = 4;
-    const WarpLayout wl = make_warp_layout(1, 0, cols, cols, 160);
+    const WarpLayout wl = make_warp_layout(1, 0, cols, cols);
     const size_t smem = ((sizeof(Frame) + 15) & ~(size_t)15) + (size_t)warps * wl.total * 8;
     cudaError_t err = cudaFuncSetAttribute(qr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;

@@ -304,16 +304,11 @@ class GpuParticleContactSimulator:
         check(lib.fks_sim_enable_kernel_timing(self._h, int(bool(enable))))
 
     def kernel_times_ms(self):
-        """Device time of the kernels of the last batch call: [free flight, hand-over sort, contact] or [the single kernel]."""
+        """Device time of the simulate kernel of the last batch call (a one-element list once timing is enabled)."""
         out = (C.c_double * 4)()
         n = C.c_int(0)
         check(lib.fks_sim_kernel_times(self._h, out, C.byref(n)))
         return [float(out[i]) for i in range(n.value)]
-
-    def free_flight_statistics(self):
-        out = (C.c_uint64 * capi.NUM_STATS)()
-        check(lib.fks_sim_free_flight_statistics(self._h, out))
-        return {k: int(out[i]) for i, k in enumerate(capi.STAT_NAMES)}
 
     @property
     def launch_count(self):

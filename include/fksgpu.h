@@ -316,15 +316,11 @@ int fks_forward_simulate_traced(fks_sim* sim, const double* start, const double*
 int fks_get_statistics(fks_sim* sim, uint64_t* out);
 int fks_reset_statistics(fks_sim* sim);
 
-/* Measurement aids.  A batch call with contacts allowed runs a free-flight kernel (every particle up to its first colliding
- * microstep), a small hand-over sort, and a contact kernel (the parked particles to their end).
- * fks_sim_enable_kernel_timing: record CUDA events around them from now on; fks_sim_kernel_times: device milliseconds of the
- * kernels of the LAST call (out_ms[0] free flight, [1] hand-over sort, [2] contact; a single-kernel call fills [0] only) and
- * how many were timed; fks_sim_free_flight_statistics: the counters of the free-flight kernels alone (fks_get_statistics
- * minus these = the contact kernels). */
+/* Measurement aid: fks_sim_enable_kernel_timing records CUDA events around the simulate kernel from now on;
+ * fks_sim_kernel_times returns the device milliseconds of the kernel of the LAST batch call in out_ms[0] (and 1 in
+ * *n_kernels when it was timed).  It waits for that call. */
 int fks_sim_enable_kernel_timing(fks_sim* sim, int enable);
 int fks_sim_kernel_times(fks_sim* sim, double* out_ms, int* n_kernels);
-int fks_sim_free_flight_statistics(fks_sim* sim, uint64_t* out);
 
 /* number of kernel launches issued by this simulator so far (bench "gpu_launches") */
 uint64_t fks_sim_launch_count(const fks_sim* sim);

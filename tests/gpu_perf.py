@@ -40,15 +40,20 @@ def run(name, n, free=False, reps=3):
         capi.lib.fks_debug_phase_cycles(sim._h, ph)
         tot = float(sum(ph[:10])) or 1.0
         if sum(ph[:10]):
-            names = ["A apply", "group-1 barrier", "B measure", "-", "T trans", "full barrier", "C collect", "solver barrier", "D solve+estimate", "end barrier"]
-            print("    warp clocks: " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(names, ph)), flush=True)
+            names = ["A apply", "claim + load", "B measure", "census + park", "T transitions", "start barrier", "C collect", "swap barrier", "D solve + E estimate", "end of cycle"]
+            print("    warp clocks: " + ", ".join("%s %.1f%%" % (n, 100 * v / tot) for n, v in zip(names, ph) if n != "-"), flush=True)
             print("    per call: collect %.0f clk (n=%d), solve in shared memory %.0f clk (n=%d), solve in the global store %.0f clk (n=%d), estimate %.0f clk" % (
                 ph[10] / max(ph[11], 1), ph[11], ph[12] / max(ph[13], 1), ph[13], ph[14] / max(ph[15], 1), ph[15],
                 ph[19] / max(ph[11], 1)), flush=True)
             nw = 148 * 32  # counters are summed over all warps
-            sc = ph[16] / nw
-            print("    super-cycles per CTA %.0f (%.0f clk each), solver warps per super-cycle %.1f, group-1 extra rounds per warp %.0f" % (
-                sc, tot / nw / max(sc, 1), ph[17] / max(ph[16], 1), ph[18] / nw), flush=True)
+            cyc = ph[16] / nw
+            print("    cycles per CTA %.0f (%.0f clk each), of which solve cycles %.0f with %.1f solver warps each" % (
+                cyc, tot / nw / max(cyc, 1), ph[18] / nw, ph[17] / max(ph[18] / 32.0, 1) / 1.0), flush=True)
+            print("    cycle length (warp 0 of every CTA): round cycles %.0f clk (n=%d per CTA), solve cycles %.0f clk (n=%d per CTA)" % (
+                ph[20] / max(ph[21], 1), ph[21] / 148, ph[22] / max(ph[23], 1), ph[23] / 148), flush=True)
+            nr_, ns_ = max(ph[21], 1), max(ph[23], 1)
+            print("    slowest warp per cycle (mean over cycles): A %.0f, B %.0f, T %.0f per round cycle; swap %.0f per cycle; collect %.0f, solve %.0f, estimate %.0f per solve cycle" % (
+                ph[24] / nr_, ph[25] / nr_, ph[26] / nr_, ph[27] / (nr_ + ns_), ph[28] / ns_, ph[29] / ns_, ph[30] / ns_), flush=True)
     sim.close()
 
 
