@@ -585,7 +585,7 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     const DevRobot& h = robot->host;
     std::memset(&s->plan, 0, sizeof(s->plan));
     int wpb = kWarpsPerBlock;
-    if (const char* ev = std::getenv("FKS_WARPS_PER_BLOCK")) {  // developer knob: 1..16 warps per lock-step CTA
+    if (const char* ev = std::getenv("FKS_WARPS_PER_BLOCK")) {  // developer knob: warps per lock-step CTA, 1..kWarpsPerBlock
         const int v = std::atoi(ev);
         if (v >= 1 && v <= kWarpsPerBlock) wpb = v;
     }

@@ -23,8 +23,11 @@ constexpr int kMaxJoints = 16;
 constexpr int kMaxPairs = (kMaxLinks * (kMaxLinks - 1)) / 2;
 constexpr int kMaxSelfPartners = kMaxLinks - 1;
 constexpr int kPairChunks = (kMaxPairs + 31) / 32;
+// 24 warps per CTA: 80 registers per thread instead of the 64 that 32 warps leave (fewer spills in the solver) and a
+// bigger shared-memory block per warp; measured 3-9 % faster than 32 on the contact workloads, 2 % slower in free flight
+// (profiles/r2_kernel_experiments.md)
 #ifndef FKS_MAX_WARPS
-#define FKS_MAX_WARPS 32
+#define FKS_MAX_WARPS 24
 #endif
 constexpr int kWarpsPerBlock = FKS_MAX_WARPS;  // upper bound of warps per CTA (launch bounds); the CTA's warps run in lock step
 constexpr int kThreadsPerBlock = kWarpsPerBlock * 32;

@@ -39,7 +39,7 @@ namespace fksdev {
 #define FKS_SKIP_SINGLE_ESTIMATE 1
 #endif
 #ifndef FKS_MIN_BLOCKS
-#define FKS_MIN_BLOCKS 1  // lock-step CTAs (16 warps each) per SM the register allocation is planned for
+#define FKS_MIN_BLOCKS 1  // lock-step CTAs per SM the register allocation is planned for
 #endif
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -97,45 +97,6 @@ __device__ __noinline__ void trace_append(unsigned kind, unsigned step, unsigned
     for (int i = lane; i < a.trace_width; i += 32) v[i] = i < n ? values[i] : 0.0;
 }
 
-// named barriers over a subset of the CTA's warps (PTX barrier.sync / barrier.red with a thread count)
-__device__ __forceinline__ void named_barrier(int id, int threads) {
-    asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ bool named_barrier_or(int id, int threads, bool pred) {
-    unsigned out;
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(out)
-        : "r"(id), "r"(threads), "r"((unsigned)pred)
-        : "memory");
-    return out != 0u;
-}
-
-// count / conjunction of a predicate over the threads of a named barrier
-__device__ __forceinline__ int named_barrier_popc(int id, int threads, bool pred) {
-    unsigned out;
-    asm volatile(
-        "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.popc.u32 %0, %1, %2, q;\n\t}"
-        : "=r"(out)
-        : "r"(id), "r"(threads), "r"((unsigned)pred)
-        : "memory");
-    return (int)out;
-}
-__device__ __forceinline__ bool named_barrier_and(int id, int threads, bool pred) {
-    unsigned out;
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbarrier.red.and.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(out)
-        : "r"(id), "r"(threads), "r"((unsigned)pred)
-        : "memory");
-    return out != 0u;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FKS_FULL, v, o);
-    return v;
-}
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FKS_FULL, v, o));
