@@ -4,6 +4,7 @@
 // the device path cannot run.
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: named host ranges for Nsight Systems / ncu --nvtx, free without a tool attached
 
 #include <algorithm>
 #include <cmath>
@@ -114,6 +115,8 @@ struct fks_sim {
     unsigned long long *d_tape_off, *d_dec, *d_dec_off;
     char* d_results;
     size_t cap_starts, cap_targets, cap_tape, cap_tape_off, cap_results, cap_dec, cap_dec_off;
+    unsigned long long* d_trace_buf = nullptr;  // fks_forward_simulate_traced: [counter word | records], grown on demand
+    size_t cap_trace_buf = 0;
     size_t smem_limit;
     // context pool of the simulate kernel: global store of parked particle contexts and their scratch slots
     char* d_ctx_store;
@@ -136,6 +139,15 @@ struct fks_sim {
 };
 
 extern "C" {
+
+namespace {
+struct NvtxRange {  // one named range per C-ABI call and per stage inside it
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace
 
 int fks_abi_version(void) { return FKS_ABI_VERSION; }
 
@@ -652,6 +664,7 @@ void fks_sim_destroy(fks_sim* s) {
     cudaFree(s->d_tape_off);
     cudaFree(s->d_dec);
     cudaFree(s->d_dec_off);
+    cudaFree(s->d_trace_buf);
     cudaFree(s->d_ctx_store);
     cudaFree(s->d_results);
     if (s->last_done) cudaEventDestroy(s->last_done);
@@ -743,6 +756,7 @@ int fks_forward_simulate_async(fks_sim* s, const double* starts, const double* t
                          void* results) {
     int rc = check_batch(s, starts, targets, n, n_targets, noise_mode, tape ? tape->draws : nullptr, tape ? tape->offsets : nullptr, results);
     if (rc != FKS_OK || n == 0) return rc;
+    NvtxRange range("fks_forward_simulate");
     DeviceGuard guard(s->device);
     if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_forward_simulate: cudaSetDevice failed");
     const size_t stride = (size_t)s->robot->stride;
@@ -763,26 +777,34 @@ int fks_forward_simulate_async(fks_sim* s, const double* starts, const double* t
             if ((rc = ensure(&s->d_dec_off, &s->cap_dec_off, n + 1)) != FKS_OK) return rc;
         }
     }
-    FKS_CUDA(cudaMemcpyAsync(s->d_starts, starts, n * stride * 8, cudaMemcpyHostToDevice, s->stream));
-    FKS_CUDA(cudaMemcpyAsync(s->d_targets, targets, n_targets * stride * 8, cudaMemcpyHostToDevice, s->stream));
-    if (noise_mode == FKS_NOISE_INJECTED) {
-        if (n_draws) FKS_CUDA(cudaMemcpyAsync(s->d_tape, tape->draws, n_draws * 8, cudaMemcpyHostToDevice, s->stream));
-        FKS_CUDA(cudaMemcpyAsync(s->d_tape_off, tape->offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s->stream));
-        if (with_decisions) {
-            if (n_dec_words) FKS_CUDA(cudaMemcpyAsync(s->d_dec, tape->decisions, n_dec_words * 8, cudaMemcpyHostToDevice, s->stream));
-            FKS_CUDA(cudaMemcpyAsync(s->d_dec_off, tape->decision_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    {
+        NvtxRange h2d("fks: H2D starts / targets / tape");
+        FKS_CUDA(cudaMemcpyAsync(s->d_starts, starts, n * stride * 8, cudaMemcpyHostToDevice, s->stream));
+        FKS_CUDA(cudaMemcpyAsync(s->d_targets, targets, n_targets * stride * 8, cudaMemcpyHostToDevice, s->stream));
+        if (noise_mode == FKS_NOISE_INJECTED) {
+            if (n_draws) FKS_CUDA(cudaMemcpyAsync(s->d_tape, tape->draws, n_draws * 8, cudaMemcpyHostToDevice, s->stream));
+            FKS_CUDA(cudaMemcpyAsync(s->d_tape_off, tape->offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+            if (with_decisions) {
+                if (n_dec_words) FKS_CUDA(cudaMemcpyAsync(s->d_dec, tape->decisions, n_dec_words * 8, cudaMemcpyHostToDevice, s->stream));
+                FKS_CUDA(cudaMemcpyAsync(s->d_dec_off, tape->decision_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+            }
         }
     }
-    rc = simulate_on_stream(s, s->d_starts, s->d_targets, n, n_targets, allow_contacts, noise_mode, s->d_tape,
-                            (const uint64_t*)s->d_tape_off, with_decisions ? (const uint64_t*)s->d_dec : nullptr,
-                            with_decisions ? (const uint64_t*)s->d_dec_off : nullptr, first_particle_id, s->d_results, s->stream);
+    {
+        NvtxRange launch("fks: simulate kernel");
+        rc = simulate_on_stream(s, s->d_starts, s->d_targets, n, n_targets, allow_contacts, noise_mode, s->d_tape,
+                                (const uint64_t*)s->d_tape_off, with_decisions ? (const uint64_t*)s->d_dec : nullptr,
+                                with_decisions ? (const uint64_t*)s->d_dec_off : nullptr, first_particle_id, s->d_results, s->stream);
+    }
     if (rc != FKS_OK) return rc;
+    NvtxRange d2h("fks: D2H records");
     FKS_CUDA(cudaMemcpyAsync(results, s->d_results, n * rec, cudaMemcpyDeviceToHost, s->stream));
     return FKS_OK;
 }
 
 int fks_sim_synchronize(fks_sim* s) {
     if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_sim_synchronize: null simulator");
+    NvtxRange range("fks_sim_synchronize");
     DeviceGuard guard(s->device);
     if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_sim_synchronize: cudaSetDevice failed");
     FKS_CUDA(cudaStreamSynchronize(s->stream));
@@ -811,34 +833,30 @@ int fks_forward_simulate_traced(fks_sim* s, const double* start, const double* t
     DeviceGuard guard(s->device);
     if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_forward_simulate_traced: cudaSetDevice failed");
     const size_t rec = fks_sim_trace_stride(s);
-    char* d_trace = nullptr;
-    unsigned int* d_count = nullptr;
-    FKS_CUDA(cudaMalloc((void**)&d_trace, std::max<size_t>(trace_capacity, 1) * rec));
-    cudaError_t e = cudaMalloc((void**)&d_count, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, sizeof(unsigned int), s->stream);
+    NvtxRange range("fks_forward_simulate_traced");
+    // the trace buffer and its counter belong to the simulator and grow on demand (no allocation per call)
     int rc = FKS_OK;
-    if (e != cudaSuccess) {
-        rc = cuda_fail(e, "fks_forward_simulate_traced: allocation");
-    } else {
-        s->d_trace = d_trace;
-        s->d_trace_count = d_count;
-        s->trace_capacity = (unsigned int)trace_capacity;
-        rc = fks_forward_simulate(s, start, target, 1, 1, allow_contacts, noise_mode, tape, particle_id, result);
-        s->d_trace = nullptr;
-        s->d_trace_count = nullptr;
-        s->trace_capacity = 0;
+    if ((rc = ensure(&s->d_trace_buf, &s->cap_trace_buf, (std::max<size_t>(trace_capacity, 1) * rec + 7) / 8 + 1)) != FKS_OK) return rc;
+    char* d_trace = reinterpret_cast<char*>(s->d_trace_buf) + 8;
+    unsigned int* d_count = reinterpret_cast<unsigned int*>(s->d_trace_buf);
+    FKS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned int), s->stream));
+    s->d_trace = d_trace;
+    s->d_trace_count = d_count;
+    s->trace_capacity = (unsigned int)trace_capacity;
+    rc = fks_forward_simulate(s, start, target, 1, 1, allow_contacts, noise_mode, tape, particle_id, result);
+    s->d_trace = nullptr;
+    s->d_trace_count = nullptr;
+    s->trace_capacity = 0;
+    if (rc != FKS_OK) return rc;
+    unsigned int count = 0;
+    FKS_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, s->stream));
+    FKS_CUDA(cudaStreamSynchronize(s->stream));
+    if (trace_capacity && count) {
+        FKS_CUDA(cudaMemcpyAsync(trace_records, d_trace, std::min<size_t>(count, trace_capacity) * rec, cudaMemcpyDeviceToHost, s->stream));
+        FKS_CUDA(cudaStreamSynchronize(s->stream));
     }
-    if (rc == FKS_OK) {
-        unsigned int count = 0;
-        e = cudaMemcpy(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && trace_capacity)
-            e = cudaMemcpy(trace_records, d_trace, std::min<size_t>(count, trace_capacity) * rec, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = cuda_fail(e, "fks_forward_simulate_traced: copy back");
-        else *n_records = count;
-    }
-    cudaFree(d_trace);
-    cudaFree(d_count);
-    return rc;
+    *n_records = count;
+    return FKS_OK;
 }
 
 int fks_reverse_simulate(fks_sim* s, const double* starts, const double* targets, size_t n, size_t n_targets,

@@ -13,8 +13,8 @@
  *
  * The reference has no FFI; its boundary is the C++ virtual interface
  * simple_simulator_interface::SimulatorInterface (spcs.hpp:372) created by the factories in
- * fast_kinematic_simulator.hpp:18-22.  A C++ adapter (csrc/host/gpu_particle_contact_simulator.hpp)
- * implements that interface on top of the functions below; INTEGRATION.md shows the binding.
+ * fast_kinematic_simulator.hpp:18-22.  A C++ adapter (include/fksgpu_simulator.hpp) mirrors that interface on top of
+ * the functions below (include/fksgpu_glue.hpp derives it from the reference's own types); INTEGRATION.md shows the binding.
  *
  * Conventions
  *  - plain C, opaque handles, int status return (0 = FKS_OK), no exceptions cross the boundary;

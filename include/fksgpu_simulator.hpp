@@ -7,9 +7,9 @@
 //   MakeGpu{SE2,SE3,Linked}Simulator                fast_kinematic_simulator.hpp:18-22 (same argument order)
 //   GetDefaultSolverParameters                      fast_kinematic_simulator.hpp:13-16
 // but carries no Eigen / ROS / arc_utilities types: configurations are the flat layouts of the C ABI
-// (SE2: x, y, theta; SE3: row-major 3x4 [R|t]; linked: one value per active joint).  INTEGRATION.md shows the
-// ~30-line glue that converts the reference's own types (Eigen::Matrix<double,3,1>, Eigen::Isometry3d,
-// std::vector<SimpleJointModel>) and derives this class from simple_simulator_interface::SimulatorInterface.
+// (SE2: x, y, theta; SE3: row-major 3x4 [R|t]; linked: one value per active joint).  include/fksgpu_glue.hpp holds the
+// glue that converts the reference's own types (Eigen::Matrix<double,3,1>, Eigen::Isometry3d, sdf_tools grids) behind
+// FKSGPU_WITH_EIGEN / FKSGPU_WITH_SDF_TOOLS; INTEGRATION.md shows how a maintainer wires it into the factories.
 //
 // Errors: the reference asserts (asserts are live in its build, CMakeLists.txt:66).  Here argument errors and
 // device errors throw std::runtime_error with the library's message; conditions the reference would abort on
@@ -118,8 +118,53 @@ struct ConfigTraits<std::vector<double>> {
     static std::vector<double> Unflatten(const double* in, int stride) { return std::vector<double>(in, in + stride); }
 };
 
+// Clean-room shim of the part of simple_simulator_interface::SimulatorInterface<Configuration, RNG, ConfigAlloc> this
+// path sits behind (upstream header, absent from the reference tree; the overrides at spcs.hpp:488-512, :788-843 and :1398
+// give the signatures).  The robot argument of the reference calls (`const std::shared_ptr<BaseRobotType>& immutable_robot`)
+// is the robot the simulator was created with here -- the reference clones it per particle and never mutates it (:826) --
+// and the display callback takes an opaque pointer instead of visualization_msgs::MarkerArray.  include/fksgpu_glue.hpp
+// adapts both to the reference's own types when they are available.
 template <typename Configuration>
-class GpuParticleContactSimulator {
+class SimulatorInterface {
+public:
+    typedef SimulationResult<Configuration> Result;
+    typedef std::function<void(const void*)> DisplayFn;
+    virtual ~SimulatorInterface() {}
+    virtual std::vector<Result> ForwardSimulateRobots(const std::vector<Configuration>& start_positions,
+                                                      const std::vector<Configuration>& target_positions, bool allow_contacts,
+                                                      const DisplayFn& display_fn = nullptr) = 0;                      // :788
+    virtual std::vector<Result> ReverseSimulateRobots(const std::vector<Configuration>& start_positions,
+                                                      const std::vector<Configuration>& target_positions, bool allow_contacts,
+                                                      const DisplayFn& display_fn = nullptr) = 0;                      // :806
+    virtual Result ForwardSimulateRobot(const Configuration& start, const Configuration& target, bool allow_contacts) = 0;  // :824
+    virtual Result ForwardSimulateRobot(const Configuration& start, const Configuration& target, bool allow_contacts,
+                                        ForwardSimulationStepTrace<Configuration>& trace, bool enable_tracing) = 0;     // :824
+    virtual bool CheckConfigCollision(const Configuration& config, double inflation_ratio) = 0;                         // :1398
+    virtual std::map<std::string, double> GetStatistics() = 0;                                                          // :488
+    virtual void ResetStatistics() = 0;                                                                                 // :502
+    virtual int32_t GetDebugLevel() const = 0;                                                                          // :446
+    virtual int32_t SetDebugLevel(int32_t debug_level) = 0;                                                             // :451
+};
+
+// A recorded run of the reference (or of the CPU oracle) for the parity mode: the truncated-normal draws each particle
+// consumed and, optionally, the decisions of its contact solves (fks_noise_tape in fksgpu.h).
+struct NoiseTape {
+    std::vector<double> draws;
+    std::vector<uint64_t> offsets;           // [n + 1]
+    std::vector<uint64_t> decisions;         // records of 2 + n_dof words, may be empty
+    std::vector<uint64_t> decision_offsets;  // [n + 1] when decisions are given
+    fks_noise_tape View() const {
+        fks_noise_tape t;
+        t.draws = draws.data();
+        t.offsets = offsets.data();
+        t.decisions = decisions.empty() ? nullptr : decisions.data();
+        t.decision_offsets = decision_offsets.empty() ? nullptr : decision_offsets.data();
+        return t;
+    }
+};
+
+template <typename Configuration>
+class GpuParticleContactSimulator : public SimulatorInterface<Configuration> {
 public:
     typedef SimulationResult<Configuration> Result;
 
@@ -137,6 +182,7 @@ public:
         stride_ = fks_robot_config_stride(robot_);
         record_ = fks_sim_result_stride(sim_);
         dof_ = robot.n_dof;
+        debug_level_ = debug_level;
     }
     // same, in an environment that already lives on the device (shared, must outlive the simulator)
     GpuParticleContactSimulator(const std::shared_ptr<DeviceEnvironment>& environment, const fks_robot_desc& robot,
@@ -154,6 +200,7 @@ public:
         stride_ = fks_robot_config_stride(robot_);
         record_ = fks_sim_result_stride(sim_);
         dof_ = robot.n_dof;
+        debug_level_ = debug_level;
     }
     ~GpuParticleContactSimulator() { Release(); }
     GpuParticleContactSimulator(const GpuParticleContactSimulator&) = delete;
@@ -162,25 +209,25 @@ public:
     // spcs.hpp:788: one result per start; target_positions.size() must be 1 or start_positions.size() (assert :790-793)
     std::vector<Result> ForwardSimulateRobots(const std::vector<Configuration>& start_positions,
                                               const std::vector<Configuration>& target_positions, bool allow_contacts,
-                                              const std::function<void(const void*)>& display_fn = nullptr) {
+                                              const std::function<void(const void*)>& display_fn = nullptr) override {
         (void)display_fn;  // RViz markers: not on the hot path (spcs.hpp:1725-1736 only fires at debug_level >= 2)
         return Simulate(start_positions, target_positions, allow_contacts, false);
     }
     // spcs.hpp:806 (ReverseSimulateMutableRobot forwards to the forward path, :838-841)
     std::vector<Result> ReverseSimulateRobots(const std::vector<Configuration>& start_positions,
                                               const std::vector<Configuration>& target_positions, bool allow_contacts,
-                                              const std::function<void(const void*)>& display_fn = nullptr) {
+                                              const std::function<void(const void*)>& display_fn = nullptr) override {
         (void)display_fn;
         return Simulate(start_positions, target_positions, allow_contacts, true);
     }
     // spcs.hpp:824: single particle
-    Result ForwardSimulateRobot(const Configuration& start, const Configuration& target, bool allow_contacts) {
+    Result ForwardSimulateRobot(const Configuration& start, const Configuration& target, bool allow_contacts) override {
         return ForwardSimulateRobots(std::vector<Configuration>(1, start), std::vector<Configuration>(1, target), allow_contacts)[0];
     }
 
     // spcs.hpp:824 with the trace arguments: single particle, trace filled when enable_tracing is set
     Result ForwardSimulateRobot(const Configuration& start, const Configuration& target, bool allow_contacts,
-                                ForwardSimulationStepTrace<Configuration>& trace, bool enable_tracing) {
+                                ForwardSimulationStepTrace<Configuration>& trace, bool enable_tracing) override {
         if (!enable_tracing) return ForwardSimulateRobot(start, target, allow_contacts);
         std::vector<double> s0((size_t)stride_), t0((size_t)stride_);
         ConfigTraits<Configuration>::Flatten(start, s0.data(), stride_);
@@ -215,7 +262,7 @@ public:
     }
 
     // spcs.hpp:1398: planner-side static query (environment inflated by inflation_ratio cells, self collisions)
-    bool CheckConfigCollision(const Configuration& config, double inflation_ratio) {
+    bool CheckConfigCollision(const Configuration& config, double inflation_ratio) override {
         std::vector<double> flat((size_t)stride_);
         ConfigTraits<Configuration>::Flatten(config, flat.data(), stride_);
         uint8_t out = 0;
@@ -231,7 +278,7 @@ public:
     }
 
     // spcs.hpp:488-500, same keys
-    std::map<std::string, double> GetStatistics() {
+    std::map<std::string, double> GetStatistics() override {
         uint64_t s[FKS_NUM_STATS];
         Check(fks_get_statistics(sim_, s));
         std::map<std::string, double> out;
@@ -245,11 +292,29 @@ public:
         out["recovered_unsuccessful_resolves"] = (double)s[FKS_STAT_RECOVERED_UNSUCCESSFUL_RESOLVES];
         return out;
     }
-    void ResetStatistics() { Check(fks_reset_statistics(sim_)); }  // spcs.hpp:502-512
+    void ResetStatistics() override { Check(fks_reset_statistics(sim_)); }  // spcs.hpp:502-512
+    int32_t GetDebugLevel() const override { return debug_level_; }               // spcs.hpp:446-449
+    int32_t SetDebugLevel(int32_t debug_level) override {                         // spcs.hpp:451-455 (messages only; no device effect)
+        debug_level_ = debug_level;
+        return debug_level_;
+    }
 
     // noise: Philox keyed by (prng_seed, first_particle_id + index); the id offset advances per call so that
     // successive calls draw fresh noise, as the reference's per-thread generators do
     void SetNextParticleId(uint64_t id) { next_particle_id_ = id; }
+    // FKS_NOISE_PHILOX (default) or FKS_NOISE_NONE for the calls that follow
+    void SetNoiseMode(int noise_mode) {
+        if (noise_mode != FKS_NOISE_PHILOX && noise_mode != FKS_NOISE_NONE)
+            throw std::invalid_argument("fksgpu: SetNoiseMode takes FKS_NOISE_PHILOX or FKS_NOISE_NONE; a tape goes through SetNoiseTape");
+        noise_mode_ = noise_mode;
+        tape_.reset();
+    }
+    // parity mode: the NEXT batch call consumes this recorded run (one entry per start position) instead of drawing noise
+    void SetNoiseTape(const std::shared_ptr<const NoiseTape>& tape) {
+        if (!tape || tape->offsets.size() < 2) throw std::invalid_argument("fksgpu: empty noise tape");
+        tape_ = tape;
+        noise_mode_ = FKS_NOISE_INJECTED;
+    }
     int ConfigStride() const { return stride_; }
     const char* KernelInfo() { return fks_sim_kernel_info(sim_); }
 
@@ -262,9 +327,17 @@ private:
         for (size_t i = 0; i < n; i++) ConfigTraits<Configuration>::Flatten(starts[i], hs.data() + i * (size_t)stride_, stride_);
         for (size_t i = 0; i < targets.size(); i++) ConfigTraits<Configuration>::Flatten(targets[i], ht.data() + i * (size_t)stride_, stride_);
         std::vector<unsigned char> rec(n * record_);
+        fks_noise_tape view;
+        const fks_noise_tape* tape = nullptr;
+        if (noise_mode_ == FKS_NOISE_INJECTED) {
+            if (!tape_ || tape_->offsets.size() != n + 1) throw std::invalid_argument("fksgpu: the noise tape does not match the batch");
+            view = tape_->View();
+            tape = &view;
+        }
         Check((reverse ? fks_reverse_simulate : fks_forward_simulate)(sim_, hs.data(), ht.data(), n, targets.size(), allow_contacts ? 1 : 0,
-                                                                     FKS_NOISE_PHILOX, nullptr, next_particle_id_, rec.data()));
+                                                                     noise_mode_, tape, next_particle_id_, rec.data()));
         next_particle_id_ += n;
+        if (noise_mode_ == FKS_NOISE_INJECTED) SetNoiseMode(FKS_NOISE_PHILOX);  // a tape describes one batch
         std::vector<Result> out(n);
         for (size_t i = 0; i < n; i++) out[i] = Unpack(rec.data() + i * record_, targets.size() == 1 ? targets[0] : targets[i]);
         return out;
@@ -297,6 +370,73 @@ private:
     fks_robot* robot_;
     fks_sim* sim_;
     int stride_ = 0, dof_ = 0;
+    size_t record_ = 0;
+    uint64_t next_particle_id_ = 0;
+    int noise_mode_ = FKS_NOISE_PHILOX;
+    int32_t debug_level_ = 0;
+    std::shared_ptr<const NoiseTape> tape_;
+};
+
+// The same batch calls over several GPUs of one box (fks_multi_* in fksgpu.h): contiguous particle shards, environment and
+// robot replicated per device, records independent of the device count (Philox noise is keyed by the global particle id).
+template <typename Configuration>
+class MultiGpuParticleContactSimulator {
+public:
+    typedef SimulationResult<Configuration> Result;
+    // devices empty: devices 0 .. n_devices-1
+    MultiGpuParticleContactSimulator(const std::vector<int32_t>& devices, int32_t n_devices, const fks_env_desc& environment,
+                                     const fks_robot_desc& robot, const fks_solver_params& solver_config,
+                                     double simulation_controller_frequency, uint64_t prng_seed, int32_t debug_level)
+        : sim_(nullptr) {
+        Check(fks_multi_sim_create(devices.empty() ? nullptr : devices.data(), devices.empty() ? n_devices : (int32_t)devices.size(),
+                                   &environment, &robot, &solver_config, simulation_controller_frequency, prng_seed, debug_level, &sim_));
+        stride_ = robot.kind == FKS_ROBOT_SE2 ? 3 : (robot.kind == FKS_ROBOT_SE3 ? 12 : robot.n_dof);
+        record_ = fks_multi_sim_result_stride(sim_);
+    }
+    ~MultiGpuParticleContactSimulator() { fks_multi_sim_destroy(sim_); }
+    MultiGpuParticleContactSimulator(const MultiGpuParticleContactSimulator&) = delete;
+    MultiGpuParticleContactSimulator& operator=(const MultiGpuParticleContactSimulator&) = delete;
+    int DeviceCount() const { return fks_multi_sim_device_count(sim_); }
+
+    // spcs.hpp:788 over all devices
+    std::vector<Result> ForwardSimulateRobots(const std::vector<Configuration>& starts, const std::vector<Configuration>& targets,
+                                              bool allow_contacts) {
+        const size_t n = starts.size();
+        if (!(targets.size() == 1 || targets.size() == n)) throw std::invalid_argument("fksgpu: need 1 target or one per start");
+        std::vector<double> hs(n * (size_t)stride_), ht(targets.size() * (size_t)stride_);
+        for (size_t i = 0; i < n; i++) ConfigTraits<Configuration>::Flatten(starts[i], hs.data() + i * (size_t)stride_, stride_);
+        for (size_t i = 0; i < targets.size(); i++) ConfigTraits<Configuration>::Flatten(targets[i], ht.data() + i * (size_t)stride_, stride_);
+        std::vector<unsigned char> rec(n * record_);
+        Check(fks_multi_forward_simulate(sim_, hs.data(), ht.data(), n, targets.size(), allow_contacts ? 1 : 0, FKS_NOISE_PHILOX, nullptr,
+                                         next_particle_id_, rec.data()));
+        next_particle_id_ += n;
+        std::vector<Result> out(n);
+        for (size_t i = 0; i < n; i++) {
+            const unsigned char* r = rec.data() + i * record_;
+            fks_result_tail tail;
+            std::memcpy(&tail, r + sizeof(double) * (size_t)stride_, sizeof(tail));
+            out[i].result_config = ConfigTraits<Configuration>::Unflatten(reinterpret_cast<const double*>(r), stride_);
+            out[i].actual_target = targets.size() == 1 ? targets[0] : targets[i];
+            out[i].did_contact = (tail.flags & FKS_FLAG_DID_CONTACT) != 0;
+            out[i].outcome_is_nominal = true;
+            out[i].flags = tail.flags;
+            out[i].n_microsteps = tail.n_microsteps;
+            out[i].n_resolver_iterations = tail.n_resolver_iters;
+            out[i].n_steps = tail.n_steps;
+        }
+        return out;
+    }
+    std::vector<uint64_t> GetStatisticCounters() {
+        std::vector<uint64_t> s(FKS_NUM_STATS);
+        Check(fks_multi_get_statistics(sim_, s.data()));
+        return s;
+    }
+    void ResetStatistics() { Check(fks_multi_reset_statistics(sim_)); }
+    void SetNextParticleId(uint64_t id) { next_particle_id_ = id; }
+
+private:
+    fks_multi_sim* sim_;
+    int stride_ = 0;
     size_t record_ = 0;
     uint64_t next_particle_id_ = 0;
 };
