@@ -95,7 +95,7 @@ int main() {
                 joints[j].axis[0] = 0.0; joints[j].axis[1] = 1.0; joints[j].axis[2] = 0.0;
                 joints[j].lower_limit = -2.5; joints[j].upper_limit = 2.5; joints[j].distance_weight = 1.0;
             }
-            std::vector<fks_axis_params> axes(J, fksgpu::AxisParams(2.0, 0.0, 0.0, 0.0, 1.0, 0.1, 0.005));
+            std::vector<fks_axis_params> axes(J, fksgpu::AxisParams(3.0, 0.0, 0.0, 0.0, 1.0, 0.1, 0.005));
             std::vector<uint8_t> allowed((size_t)L * L, 1);  // self collisions are not the subject here
             fks_robot_desc robot;
             std::memset(&robot, 0, sizeof(robot));
@@ -104,7 +104,7 @@ int main() {
             Identity12(robot.base_transform, 0.013, 0.007, 0.021);
             robot.joints = joints.data(); robot.allowed_self_collision = allowed.data();
             robot.position_distance_weight = 1.0; robot.rotation_distance_weight = 1.0;
-            bad += RunScenario("linked arm", FKS_ROBOT_LINKED, env.Description(), robot, Config{0.2, 0.5, 0.4}, Config{0.6, 0.9, 0.7}, 0.9);
+            bad += RunScenario("linked arm", FKS_ROBOT_LINKED, env.Description(), robot, Config{0.2, 0.5, 0.4}, Config{0.6, 1.3, 1.0}, 0.9);
         }
         // ---- 2. SE(3) peg against a block -----------------------------------------------------------------------------
         {
@@ -119,7 +119,7 @@ int main() {
                         plink.push_back(0);
                     }
             std::vector<fks_axis_params> axes;
-            for (int i = 0; i < 6; i++) axes.push_back(fksgpu::AxisParams(1.0, 0.0, 0.0, 0.0, i < 3 ? 1.0 : 0.5, 0.1, 0.01));
+            for (int i = 0; i < 6; i++) axes.push_back(fksgpu::AxisParams(3.0, 0.0, 0.0, 0.0, i < 3 ? 1.0 : 0.5, 0.1, 0.01));
             fks_robot_desc robot;
             std::memset(&robot, 0, sizeof(robot));
             robot.kind = FKS_ROBOT_SE3; robot.n_links = 1; robot.n_joints = 0; robot.n_dof = 6; robot.n_points = (int64_t)plink.size();

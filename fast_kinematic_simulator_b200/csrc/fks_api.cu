@@ -108,6 +108,7 @@ struct fks_sim {
     KernelInfo kinfo;
     LaunchArgs plan;  // layouts and shared-memory offsets (simulate_smem_plan)
     char* d_scratch;
+    char* d_jscratch = nullptr;
     unsigned long long* d_stats;
     unsigned int* d_counter;
     // staging for the host-buffer entry point (grown on demand)
@@ -624,7 +625,8 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     s->grid_max = prop.multiProcessorCount * s->kinfo.max_blocks_per_sm;
     s->num_sms = prop.multiProcessorCount;
     s->pool = std::min(2 * wpb, kMaxPool);
-    const size_t scratch_bytes = (size_t)s->grid_max * s->pool * s->plan.sl.total;  // one slot per context
+    const size_t scratch_bytes = (size_t)s->grid_max * s->pool * s->plan.sl.total;  // one small slot per context
+    const size_t jscratch_bytes = (size_t)s->grid_max * wpb * s->plan.sl.jtotal;    // one tall-system slot per warp
     s->plan.pool = s->pool;
     s->plan.ctx_stride = (int)context_bytes(s->plan.wl);
     const size_t ctx_bytes = (size_t)s->grid_max * s->pool * (size_t)s->plan.ctx_stride;
@@ -632,6 +634,7 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     if ((err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (err = cudaEventCreateWithFlags(&s->last_done, cudaEventDisableTiming)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_scratch, scratch_bytes)) != cudaSuccess ||
+        (err = cudaMalloc((void**)&s->d_jscratch, jscratch_bytes)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_ctx_store, ctx_bytes)) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_stats, 128 * sizeof(unsigned long long))) != cudaSuccess ||
         (err = cudaMalloc((void**)&s->d_counter, 4 * sizeof(unsigned int))) != cudaSuccess ||
@@ -642,9 +645,9 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     char buf[512];
     std::snprintf(buf, sizeof(buf),
                   "simulate_kernel<kind=%d>: %d regs/thread, %zu B dynamic smem/CTA, %d B local/thread, %d threads/CTA, "
-                  "%d CTAs/SM x %d SMs (persistent grid %d), scratch %llu B/context, L2 window %zu B",
+                  "%d CTAs/SM x %d SMs (persistent grid %d), scratch %llu B/warp, L2 window %zu B",
                   h.kind, s->kinfo.regs, s->dyn_smem, s->kinfo.local_bytes, 32 * wpb, s->kinfo.max_blocks_per_sm,
-                  prop.multiProcessorCount, s->grid_max, (unsigned long long)s->plan.sl.total, env->l2_window_bytes);
+                  prop.multiProcessorCount, s->grid_max, (unsigned long long)s->plan.sl.jtotal, env->l2_window_bytes);
     s->info = buf;
     *out = s;
     return FKS_OK;
@@ -656,6 +659,7 @@ void fks_sim_destroy(fks_sim* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->has_last) cudaEventSynchronize(s->last_done);
     cudaFree(s->d_scratch);
+    cudaFree(s->d_jscratch);
     cudaFree(s->d_stats);
     cudaFree(s->d_counter);
     cudaFree(s->d_starts);
@@ -700,6 +704,7 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
     a.stats = s->d_stats;
     a.counter = s->d_counter;
     a.scratch = s->d_scratch;
+    a.jscratch = s->d_jscratch;
     a.n_particles = n;
     a.n_targets = n_targets;
     a.seed = s->seed;
@@ -897,13 +902,14 @@ int fks_check_config_collision(fks_sim* s, const double* configs, size_t n, doub
     a.pzl = s->robot->d_pzl;
     a.starts = s->d_starts;
     a.scratch = s->d_scratch;
+    a.jscratch = s->d_jscratch;
     a.ctx_store = s->d_ctx_store;
     a.n_particles = n;
     a.cfg_stride = s->robot->stride;
     const size_t per_sm = (n + (size_t)s->num_sms - 1) / (size_t)s->num_sms;
     const int wpb = (int)std::max<size_t>(1, std::min<size_t>((size_t)s->plan.warps_per_block, per_sm));
     a.warps_per_block = wpb;
-    a.pool = wpb;  // one context (= one scratch slot) per warp
+    a.pool = wpb;  // (check_config keeps no context pool; scratch slots are per warp)
     a.sync_off = a.warps_off + wpb * a.wl.total * 8;
     const size_t dyn_smem = (size_t)a.sync_off + kSyncBytes;
     const int grid = (int)std::min<size_t>((size_t)s->grid_max, (n + (size_t)wpb - 1) / (size_t)wpb);

@@ -113,8 +113,7 @@ struct WarpVars {
     // the current / previous kinematic state, the last collision bits, and whether the next thing it needs is a contact solve
     int after, op, op_in, op_out, op_u, op_tn, op_derive, measure, cur, prev, want_solve;
     unsigned cc;
-    int ctx;        // index of this context in the CTA's pool (fixed; selects its global scratch slot)
-    int pend_rows;  // rows of a stacked system that was collected but is too tall for the small store: it waits for a TALL cycle
+    int ctx;        // index of this context in the CTA's pool (fixed: its slot of the global context store)
 };
 constexpr int kWarpVarsDoubles = (int)((sizeof(WarpVars) + 7) / 8);
 
@@ -204,17 +203,21 @@ inline __host__ __device__ WarpLayout make_warp_layout(int L, int J, int D, int 
     return w;
 }
 
-// ---- global scratch (bytes), one slot per particle CONTEXT --------------------------------------
+// ---- global scratch (bytes): a small slot per particle context and a big one per warp -----------------------------------
 // the global store of a stacked Jacobian too tall for shared memory (collected in one solve phase, factored in a later
 // one -- possibly by another warp) and the self-collision corrections (found by a collision check, consumed by the next
 // solve phase)
 struct ScratchLayout {
-    unsigned long long jstore;    // (D+1) * ldj doubles, then P u64 (candidate list of collect_corrections)
+    // per particle CONTEXT (written by the collision check of a round, read by the collect of the following solve, possibly
+    // on another warp):
     unsigned long long selfcorr;  // 3*P doubles
     unsigned long long selfwork;  // small dense solve workspace
     unsigned long long keys;      // P packed 64-bit cell keys
     unsigned long long sflag;     // P bytes
-    unsigned long long total;
+    unsigned long long total;     // bytes of a context's slot
+    // per WARP (written and consumed inside one solve task):
+    unsigned long long jstore;    // offset 0 of the warp's slot: (D+1) * ldj doubles, then P u64 (candidate list of collect_corrections)
+    unsigned long long jtotal;    // bytes of a warp's slot
     int ldj;
     int _pad;
 };
@@ -227,12 +230,13 @@ inline __host__ __device__ ScratchLayout make_scratch_layout(int D, int P) {
     s.ldj = ((3 * P + 3) / 4) * 4;
     s._pad = 0;
     unsigned long long o = 0;
-    s.jstore = o; o += (unsigned long long)(D + 1) * s.ldj * 8 + (unsigned long long)P * 8;
     s.selfcorr = o; o += (unsigned long long)3 * P * 8;
     s.selfwork = o; o += (unsigned long long)kSelfWorkDoubles * 8;
     s.keys = o; o += (unsigned long long)P * 8;
     s.sflag = o; o += (((unsigned long long)P + 7) / 8) * 8;
     s.total = ((o + 127) / 128) * 128;
+    s.jstore = 0;
+    s.jtotal = ((((unsigned long long)(D + 1) * s.ldj * 8 + (unsigned long long)P * 8) + 127) / 128) * 128;
     return s;
 }
 
@@ -262,7 +266,8 @@ struct LaunchArgs {
     char* results;
     unsigned long long* stats;
     unsigned int* counter;
-    char* scratch;                   // global scratch, one slot per context (pool per CTA)
+    char* scratch;                   // global scratch, one slot per context of every CTA's pool (self-collision lists)
+    char* jscratch;                  // global store of stacked systems too tall for shared memory, one slot per warp
     // Context pool: every CTA keeps `pool` particles in flight for its warps_per_block warps (fks_kernels.cu, simulate_kernel).
     // A context that no warp has loaded lives in ctx_store (ctx_stride bytes each, pool per CTA).
     char* ctx_store;

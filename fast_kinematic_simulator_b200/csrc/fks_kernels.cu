@@ -68,11 +68,18 @@ __device__ __forceinline__ T wv_add(T* field, T inc) {
     *field = v;
     return v;
 }
-// global scratch slot of the particle context this warp has loaded
+// global scratch slot of the particle context this warp has loaded (self-collision lists: written by the collision check of
+// a round, read by the collect of the following solve, which another warp may run)
 __device__ __forceinline__ char* context_scratch(int wb) {
     const LaunchArgs& a = frame().a;
     const int ctx = reinterpret_cast<const WarpVars*>(wsd(wb) + a.wl.vars)->ctx;
     return a.scratch + ((size_t)blockIdx.x * a.pool + ctx) * a.sl.total;
+}
+// global slot of this WARP for a stacked system too tall for shared memory: written and consumed inside one solve task, so it
+// belongs to the warp -- 148 x 24 slots whose touched lines stay in L2, instead of one per context
+__device__ __forceinline__ double* warp_jstore() {
+    const LaunchArgs& a = frame().a;
+    return reinterpret_cast<double*>(a.jscratch + ((size_t)blockIdx.x * a.warps_per_block + (threadIdx.x >> 5)) * a.sl.jtotal);
 }
 
 // ForwardSimulationStepTrace (spcs:1583-1617, :1703, :1714, :1778), flat: one record per assignment / push_back of the
@@ -1083,7 +1090,7 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
     const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + P);
     const char* cslot = context_scratch(wb);
-    double* Ag = reinterpret_cast<double*>(context_scratch(wb) + fr.a.sl.jstore);
+    double* Ag = warp_jstore();
     const unsigned char* sflag = reinterpret_cast<const unsigned char*>(cslot + fr.a.sl.sflag);
     const double* selfcorr = reinterpret_cast<const double*>(cslot + fr.a.sl.selfcorr);
     // candidate list: {point index | bit 31 = needs the environment estimate, raw cell value}; the first kCandShared
@@ -1268,7 +1275,7 @@ __device__ __forceinline__ void spill_system(int wb, int cols) {
     const WarpLayout& wl = fr.a.wl;
     const int lane = lane_id();
     const double* As = wsd(wb) + wl.jsm;
-    double* Ag = reinterpret_cast<double*>(context_scratch(wb) + fr.a.sl.jstore);
+    double* Ag = warp_jstore();
     const int lds = wl.jsm_ld, cap_s = (wl.jsm_ld / 3) * 3, ldg = fr.a.sl.ldj;
     for (int c = 0; c <= cols; c++)
         for (int r = lane; r < cap_s; r += 32) Ag[(size_t)c * ldg + r] = As[c * lds + r];
@@ -1282,7 +1289,7 @@ __device__ __forceinline__ void place_tall_system(int wb, int rows, int cols, do
     const WarpLayout& wl = fr.a.wl;
     const int lane = lane_id();
     double* As = wsd(wb) + wl.jsm;
-    double* Ag = reinterpret_cast<double*>(context_scratch(wb) + fr.a.sl.jstore);
+    double* Ag = warp_jstore();
     const int ldg = fr.a.sl.ldj, ldb = wl.jsm_big_ld;
     *store = Ag;
     *store_ld = ldg;
@@ -1648,14 +1655,6 @@ __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned
 #ifndef FKS_SOLVE_BATCH_EIGHTHS
 #define FKS_SOLVE_BATCH_EIGHTHS 8
 #endif
-// ... and to a TALL cycle (the deferred solves of systems too tall for the small shared-memory store).  FKS_DEFER_TALL = 0
-// factors them in the solve cycle that collected them (the whole batch then waits for them).
-#ifndef FKS_TALL_BATCH_EIGHTHS
-#define FKS_TALL_BATCH_EIGHTHS 4
-#endif
-#ifndef FKS_DEFER_TALL
-#define FKS_DEFER_TALL 0
-#endif
 namespace {
 enum { OP_NONE = 0, OP_KIN = 1, OP_APPLY = 2 };
 enum { M_NONE = 0, M_MOTION = 1, M_CHECK = 2 };
@@ -1672,7 +1671,7 @@ enum {
     AF_NOCONTACT_KIN,   // step-start configuration restored -> the particle ends
     AF_DONE             // no particles left
 };
-enum { NEED_EMPTY = 0, NEED_ROUND = 1, NEED_SOLVE = 2, NEED_DEAD = 3, NEED_TALL = 4 };  // what a context of the pool waits for
+enum { NEED_EMPTY = 0, NEED_ROUND = 1, NEED_SOLVE = 2, NEED_DEAD = 3 };  // what a context of the pool waits for
 
 // a context's three ranges (fks_device_types.h) between the warp's shared block and its slot of the global context store
 __device__ __forceinline__ void context_copy(double* ws, double* g, const WarpLayout& wl, bool to_global) {
@@ -1813,19 +1812,16 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         const int n_lo = need[lane], n_hi = need[32 + lane];  // lane c / c + 32 looks at context c / c + 32 (NEED_DEAD beyond the pool)
         const int h = lane < n_warps ? (int)holds[lane] : -1; // lane w looks at warp w
         const int ns = __popc(__ballot_sync(FKS_FULL, n_lo == NEED_SOLVE)) + __popc(__ballot_sync(FKS_FULL, n_hi == NEED_SOLVE));
-        const int nt = __popc(__ballot_sync(FKS_FULL, n_lo == NEED_TALL)) + __popc(__ballot_sync(FKS_FULL, n_hi == NEED_TALL));
         const int nr = __popc(__ballot_sync(FKS_FULL, n_lo == NEED_ROUND)) + __popc(__ballot_sync(FKS_FULL, n_hi == NEED_ROUND));
         const unsigned e_lo = __ballot_sync(FKS_FULL, n_lo == NEED_EMPTY), e_hi = __ballot_sync(FKS_FULL, n_hi == NEED_EMPTY);
         const bool can_admit = (e_lo | e_hi) != 0u && *exhausted == 0u;
-        if (ns + nt + nr == 0 && !can_admit) break;  // every particle of this CTA has ended and there is none left to fetch
-        // ---- 2. phase: a batch of solves (or of deferred tall solves) as soon as it is big enough, or when the rounds run out
-        //         of takers; else a round ----------------------------------------------------------------------------------
+        if (ns + nr == 0 && !can_admit) break;  // every particle of this CTA has ended and there is none left to fetch
+        // ---- 2. phase: a batch of solves as soon as it is big enough, or when the rounds run out of takers; else a round -----
         const int round_supply = nr + (can_admit ? __popc(e_lo) + __popc(e_hi) : 0);
         int want = NEED_ROUND;
         if (ns > 0 && 8 * ns >= FKS_SOLVE_BATCH_EIGHTHS * n_warps) want = NEED_SOLVE;
-        else if (nt > 0 && 8 * nt >= FKS_TALL_BATCH_EIGHTHS * n_warps) want = NEED_TALL;
-        else if (2 * round_supply < n_warps && (ns > round_supply || nt > round_supply)) want = ns >= nt ? NEED_SOLVE : NEED_TALL;
-        else if (round_supply == 0) want = ns >= nt ? NEED_SOLVE : NEED_TALL;
+        else if (2 * round_supply < n_warps && ns > round_supply) want = NEED_SOLVE;
+        else if (round_supply == 0) want = NEED_SOLVE;
         const bool solve_phase = want != NEED_ROUND;
 #ifdef FKS_PHASE_TIMERS
         last_kind = solve_phase ? 1 : 0;
@@ -1884,7 +1880,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         if (active) {
         int after = wv->after, op = wv->op, op_in = wv->op_in, op_out = wv->op_out, op_u = wv->op_u, op_tn = wv->op_tn,
             op_derive = wv->op_derive, measure = wv->measure, cur = wv->cur, prev = wv->prev;
-        bool want_solve = wv->want_solve != 0, tall_pending = false;
+        bool want_solve = wv->want_solve != 0;
         unsigned cc = wv->cc;
         double m_result = wv->m_result;
         __syncwarp();
@@ -2243,7 +2239,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
         }  // rounds
         } else {
         // =========================== SOLVE: phase C, collect corrections (spcs:1627) ====================
-        // (TALL: the corrections were collected in an earlier solve cycle and wait in the context's global store)
             int rows = 0;
 #ifdef FKS_PHASE_TIMERS
             const long long tc0 = clock64();
@@ -2251,23 +2246,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #endif
             double* jstore = ws + wl.jsm;
             int jld = wl.jsm_ld;
-            bool deferred = false;
-            if (want == NEED_TALL) {
-                rows = wv->pend_rows;
+            rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
+            if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
+            if (rows > (wl.jsm_ld / 3) * 3) {  // too tall for the small store: the bigger one, or the warp's global slot
+                spill_system(wb, D);
                 place_tall_system(wb, rows, D, &jstore, &jld);
-            } else {
-                rows = collect_corrections<KIND>(wb, prev, cur, (cc & 2u) != 0u);
-                if (lane == 0) add_stat(wb, FKS_STAT_TOTAL_CORRECTED_POINTS, (unsigned long long)(rows / 3));
-                if (rows > (wl.jsm_ld / 3) * 3) {
-                    spill_system(wb, D);
-                    if (FKS_DEFER_TALL) {
-                        deferred = true;
-                        if (lane == 0) wv->pend_rows = rows;
-                        __syncwarp();
-                    } else {
-                        place_tall_system(wb, rows, D, &jstore, &jld);
-                    }
-                }
             }
 #ifdef FKS_PHASE_TIMERS
             tacc[10] += clock64() - tc0;
@@ -2275,7 +2258,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
 #endif
             FKS_MAXTICK(4, tc0)
             FKS_TICK(6)
-            if (!deferred) {
+            {
             // ======================= phase D: stacked-Jacobian solve (spcs:1629,1990-1998) ==============
 #ifdef FKS_PHASE_TIMERS
             const long long tq0 = clock64();
@@ -2311,8 +2294,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             measure = M_CHECK;
             after = AF_RESOLVE_CHECK;
             want_solve = false;
-            }  // !deferred
-            tall_pending = deferred;
+            }
             FKS_TICK(8)
         }
         // the context's control state goes back to its block, its need into the census
@@ -2323,7 +2305,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
             wv->want_solve = want_solve ? 1 : 0;
             wv->cc = cc;
             wv->m_result = m_result;
-            need[ctx] = tall_pending ? NEED_TALL : (want_solve ? NEED_SOLVE : (after == AF_DONE ? NEED_DEAD : NEED_ROUND));
+            need[ctx] = want_solve ? NEED_SOLVE : (after == AF_DONE ? NEED_DEAD : NEED_ROUND);
             if (after == AF_DONE) *exhausted = 1u;
         }
         __syncwarp();

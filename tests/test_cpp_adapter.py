@@ -44,4 +44,4 @@ def test_glue_templates_against_mock_reference_types():
 def test_adapter_on_gpu(name):
     r = subprocess.run([build(name)], capture_output=True, text=True)
     print(r.stdout)
-    assert r.returncode == 0 and "ok" in r.stdout and "FAILED" not in r.stdout
+    assert r.returncode == 0 and "ok" in r.stdout and "FAILED" not in r.stdout, r.stdout + r.stderr
