@@ -116,6 +116,8 @@ struct fks_sim {
     unsigned long long *d_tape_off, *d_dec, *d_dec_off;
     char* d_results;
     size_t cap_starts, cap_targets, cap_tape, cap_tape_off, cap_results, cap_dec, cap_dec_off;
+    unsigned int* d_part = nullptr;  // fks_end_states_partition: totals + per-block counts
+    size_t cap_part = 0;
     unsigned long long* d_trace_buf = nullptr;  // fks_forward_simulate_traced: [counter word | records], grown on demand
     size_t cap_trace_buf = 0;
     size_t smem_limit;
@@ -669,6 +671,7 @@ void fks_sim_destroy(fks_sim* s) {
     cudaFree(s->d_dec);
     cudaFree(s->d_dec_off);
     cudaFree(s->d_trace_buf);
+    cudaFree(s->d_part);
     cudaFree(s->d_ctx_store);
     cudaFree(s->d_results);
     if (s->last_done) cudaEventDestroy(s->last_done);
@@ -986,6 +989,47 @@ int fks_debug_phase_cycles(fks_sim* s, uint64_t* out16) {
 }
 
 const char* fks_sim_kernel_info(fks_sim* s) { return s ? s->info.c_str() : ""; }
+
+// ---------------------------------------------------------------------------------------------
+// first consumer of a batch on the device (fksgpu.h)
+// ---------------------------------------------------------------------------------------------
+int fks_end_states_partition(fks_sim* s, const void* d_results, size_t n, uint32_t* d_order, uint64_t* counts, void* cuda_stream) {
+    if (!s || !counts) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_end_states_partition: null argument");
+    counts[0] = counts[1] = 0;
+    if (n == 0) return FKS_OK;
+    if (!d_results || !d_order || n > 0xffffffffull) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_end_states_partition: bad buffer or count");
+    NvtxRange range("fks_end_states_partition");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_end_states_partition: cudaSetDevice failed");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    int rc;
+    const size_t n_blocks = (n + 1023) / 1024;
+    if ((rc = ensure(&s->d_part, &s->cap_part, n_blocks + 4)) != FKS_OK) return rc;  // [2 x u64 totals | block counts]
+    unsigned long long* totals = reinterpret_cast<unsigned long long*>(s->d_part);
+    rc = launch_partition((const char*)d_results, fks_sim_result_stride(s), s->robot->stride, n, s->d_part + 4, totals, d_order, stream);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "fks_end_states_partition: launch");
+    s->launches += 3;
+    unsigned long long host[2] = {0, 0};
+    FKS_CUDA(cudaMemcpyAsync(host, totals, sizeof(host), cudaMemcpyDeviceToHost, stream));
+    FKS_CUDA(cudaStreamSynchronize(stream));
+    counts[0] = host[0];
+    counts[1] = host[1];
+    return FKS_OK;
+}
+
+int fks_end_states_pairwise_distance(fks_sim* s, const void* d_results, const uint32_t* d_subset, size_t m, double* d_out, void* cuda_stream) {
+    if (!s) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_end_states_pairwise_distance: null simulator");
+    if (m == 0) return FKS_OK;
+    if (!d_results || !d_out || m > 65535) return fail(FKS_ERR_INVALID_ARGUMENT, "fks_end_states_pairwise_distance: bad buffer, or more than 65535 records");
+    NvtxRange range("fks_end_states_pairwise_distance");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(FKS_ERR_CUDA, "fks_end_states_pairwise_distance: cudaSetDevice failed");
+    const int rc = launch_pairwise_distance(s->robot->host.kind, s->robot->d_robot, (const char*)d_results, fks_sim_result_stride(s),
+                                            s->robot->stride, d_subset, (unsigned)m, d_out, cuda_stream);
+    if (rc != 0) return cuda_fail((cudaError_t)rc, "fks_end_states_pairwise_distance: launch");
+    s->launches += 1;
+    return FKS_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // test entry: the device's stacked-Jacobian solver on caller-provided systems (fksgpu.h)

@@ -284,6 +284,41 @@ __device__ __noinline__ void twist_between(const double* a, const double* b, dou
     twist[5] = wz;
 }
 
+// robot->ComputeConfigurationDistanceTo(target) (the call at spcs:898; the robot classes are upstream, so this follows the
+// oracle's restatement `Robot::distance_to`): SE2 / SE3 weigh translation and rotation angle, the linked robot takes the
+// weighted joint-space norm with continuous joints wrapped.
+template <int KIND>
+__device__ __forceinline__ double config_distance(const DevRobot& rb, const double* cur, const double* target) {
+    if (KIND == FKS_ROBOT_SE2) {
+        const double dx = fabs(target[0] - cur[0]), dy = fabs(target[1] - cur[1]);
+        const double dr = fabs(wrap_angle(target[2] - cur[2]));
+        return (sqrt(dx * dx + dy * dy) * rb.pos_w) + (dr * rb.rot_w);
+    } else if (KIND == FKS_ROBOT_SE3) {
+        double c12[12], tg[12], ci[12], Dm[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            c12[i] = cur[i];
+            tg[i] = target[i];
+        }
+        const double dx = tg[3] - c12[3], dy = tg[7] - c12[7], dz = tg[11] - c12[11];
+        iso_inverse(c12, ci);
+        iso_mul(ci, tg, Dm);
+        const double cs = fmin(fmax(0.5 * (Dm[0] + Dm[5] + Dm[10] - 1.0), -1.0), 1.0);
+        return (sqrt(dx * dx + dy * dy + dz * dz) * rb.pos_w) + (acos(cs) * rb.rot_w);
+    } else {
+        double sacc = 0.0;
+        for (int j = 0; j < rb.J; j++) {
+            const DevJoint& jd = rb.joints[j];
+            if (jd.active < 0) continue;
+            double dj = target[jd.active] - cur[jd.active];
+            if (jd.type == FKS_JOINT_CONTINUOUS) dj = wrap_angle(dj);
+            const double wd = dj * jd.weight;
+            sacc += wd * wd;
+        }
+        return sqrt(sacc);
+    }
+}
+
 // TruncatedNormalUncertainVelocityActuator::GetControlValue (unc:70-75 noiseless, :77-90 noisy)
 __device__ __forceinline__ double actuate(int wb, const DevAxis& ax, double u, bool noisy, double tn) {
     if (isnan(u) || isinf(u)) raise_flag(wb, FKS_FLAG_WOULD_ASSERT_NAN);  // assert unc:72-73
@@ -2165,37 +2200,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
                         if (lane == 0) add_stat(wb, FKS_STAT_RECOVERED_UNSUCCESSFUL_RESOLVES, 1ull);
                     }
                     if (!ends && sp.shortcut_distance > 0.0) {  // ComputeConfigurationDistanceTo (spcs:898); never < 0
-                        const double* c2 = ws + wl.cfg + cur * S;
-                        const double* target = ws + wl.target;
-                        double dist;
-                        if (KIND == FKS_ROBOT_SE2) {
-                            const double dx = fabs(target[0] - c2[0]), dy = fabs(target[1] - c2[1]);
-                            const double dr = fabs(wrap_angle(target[2] - c2[2]));
-                            dist = (sqrt(dx * dx + dy * dy) * rb.pos_w) + (dr * rb.rot_w);
-                        } else if (KIND == FKS_ROBOT_SE3) {
-                            double c12[12], tg[12], ci[12], Dm[12];
-#pragma unroll
-                            for (int i = 0; i < 12; i++) {
-                                c12[i] = c2[i];
-                                tg[i] = target[i];
-                            }
-                            const double dx = tg[3] - c12[3], dy = tg[7] - c12[7], dz = tg[11] - c12[11];
-                            iso_inverse(c12, ci);
-                            iso_mul(ci, tg, Dm);
-                            const double cs = fmin(fmax(0.5 * (Dm[0] + Dm[5] + Dm[10] - 1.0), -1.0), 1.0);
-                            dist = (sqrt(dx * dx + dy * dy + dz * dz) * rb.pos_w) + (acos(cs) * rb.rot_w);
-                        } else {
-                            double sacc = 0.0;
-                            for (int j = 0; j < rb.J; j++) {
-                                const DevJoint& jd = rb.joints[j];
-                                if (jd.active < 0) continue;
-                                double dj = target[jd.active] - c2[jd.active];
-                                if (jd.type == FKS_JOINT_CONTINUOUS) dj = wrap_angle(dj);
-                                const double wd = dj * jd.weight;
-                                sacc += wd * wd;
-                            }
-                            dist = sqrt(sacc);
-                        }
+                        const double dist = config_distance<KIND>(rb, ws + wl.cfg + cur * S, ws + wl.target);
                         if (dist < sp.shortcut_distance) {
                             wv->flags |= FKS_FLAG_ENDED_BY_SHORTCUT;
                             ends = true;
@@ -2655,6 +2660,117 @@ int launch_qr_solve(double* work, const unsigned long long* offsets, const int* 
     if (err != cudaSuccess) return (int)err;
     const int grid = (n + warps - 1) / warps < 4096 ? (n + warps - 1) / warps : 4096;
     qr_solve_kernel<<<grid, 32 * warps, smem, (cudaStream_t)stream>>>(work, offsets, rows, cols, n, x_out, flags_out);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// the first consumer of a batch, on the device.  The planner (uncertainty_planning_core.cpp:97-99) splits the
+// returned particles by did_contact and groups them by configuration distance; with these two kernels the end-state records
+// stay in HBM between ForwardSimulateRobots and that step.  Records are cfg_stride doubles + fks_result_tail.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPartitionBlock = 1024;
+
+__device__ __forceinline__ bool record_in_contact(const char* results, size_t rec_stride, int cfg_stride, size_t i) {
+    return (reinterpret_cast<const fks_result_tail*>(results + i * rec_stride + (size_t)cfg_stride * 8)->flags & FKS_FLAG_DID_CONTACT) != 0u;
+}
+// pass 1: particles in contact per block of 1024 records
+__global__ void __launch_bounds__(kPartitionBlock) partition_count_kernel(const char* results, size_t rec_stride, int cfg_stride, size_t n,
+                                                                          unsigned* block_counts) {
+    const size_t i = (size_t)blockIdx.x * kPartitionBlock + threadIdx.x;
+    const int c = __syncthreads_count(i < n && record_in_contact(results, rec_stride, cfg_stride, i));
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned)c;
+}
+// pass 2 (one block): exclusive scan of the block counts in place; totals[0] = particles without contact, totals[1] = with
+__global__ void __launch_bounds__(kPartitionBlock) partition_scan_kernel(unsigned* block_counts, unsigned n_blocks, size_t n,
+                                                                         unsigned long long* totals) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (unsigned base = 0; base < n_blocks; base += kPartitionBlock) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned v = i < n_blocks ? block_counts[i] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(FKS_FULL, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = warp_sums[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(FKS_FULL, w, o);
+                if (threadIdx.x >= o) w += t;
+            }
+            warp_sums[threadIdx.x] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned before = carry + ((threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0u) + (incl - v);
+        if (i < n_blocks) block_counts[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        totals[1] = carry;
+        totals[0] = (unsigned long long)n - carry;
+    }
+}
+// pass 3: ids without contact first, ids in contact after them, ascending inside each part
+__global__ void __launch_bounds__(kPartitionBlock) partition_scatter_kernel(const char* results, size_t rec_stride, int cfg_stride, size_t n,
+                                                                            const unsigned* block_offsets, const unsigned long long* totals,
+                                                                            unsigned* order) {
+    __shared__ unsigned warp_counts[32];
+    const size_t i = (size_t)blockIdx.x * kPartitionBlock + threadIdx.x;
+    const bool valid = i < n, contact = valid && record_in_contact(results, rec_stride, cfg_stride, i);
+    const unsigned ballot = __ballot_sync(FKS_FULL, contact);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) warp_counts[warp] = (unsigned)__popc(ballot);
+    __syncthreads();
+    unsigned before_in_block = (unsigned)__popc(ballot & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; w++) before_in_block += warp_counts[w];
+    if (!valid) return;
+    const size_t contact_before = (size_t)block_offsets[blockIdx.x] + before_in_block;  // ids in contact below i
+    if (contact) order[(size_t)totals[0] + contact_before] = (unsigned)i;
+    else order[i - contact_before] = (unsigned)i;
+}
+
+// out[a * m + b] = distance from the configuration of record subset[a] to that of record subset[b] (subset == nullptr: identity)
+template <int KIND>
+__global__ void __launch_bounds__(256) pairwise_distance_kernel(const DevRobot* robot, const char* results, size_t rec_stride, int cfg_stride,
+                                                                const unsigned* subset, unsigned m, double* out) {
+    __shared__ double from[kMaxDof < 12 ? 12 : kMaxDof];
+    const unsigned a = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ia = subset ? subset[a] : a;
+    if ((int)threadIdx.x < cfg_stride) from[threadIdx.x] = reinterpret_cast<const double*>(results + ia * rec_stride)[threadIdx.x];
+    __syncthreads();
+    if (b >= m) return;
+    const size_t ib = subset ? subset[b] : b;
+    out[(size_t)a * m + b] = config_distance<KIND>(*robot, from, reinterpret_cast<const double*>(results + ib * rec_stride));
+}
+
+int launch_partition(const char* results, size_t rec_stride, int cfg_stride, size_t n, unsigned* block_counts, unsigned long long* totals,
+                     unsigned* order, void* stream) {
+    const unsigned n_blocks = (unsigned)((n + kPartitionBlock - 1) / kPartitionBlock);
+    cudaStream_t st = (cudaStream_t)stream;
+    partition_count_kernel<<<n_blocks, kPartitionBlock, 0, st>>>(results, rec_stride, cfg_stride, n, block_counts);
+    partition_scan_kernel<<<1, kPartitionBlock, 0, st>>>(block_counts, n_blocks, n, totals);
+    partition_scatter_kernel<<<n_blocks, kPartitionBlock, 0, st>>>(results, rec_stride, cfg_stride, n, block_counts, totals, order);
+    return (int)cudaGetLastError();
+}
+int launch_pairwise_distance(int kind, const DevRobot* robot, const char* results, size_t rec_stride, int cfg_stride, const unsigned* subset,
+                             unsigned m, double* out, void* stream) {
+    const dim3 grid((m + 255) / 256, m);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kind) {
+        case FKS_ROBOT_SE2: pairwise_distance_kernel<FKS_ROBOT_SE2><<<grid, 256, 0, st>>>(robot, results, rec_stride, cfg_stride, subset, m, out); break;
+        case FKS_ROBOT_SE3: pairwise_distance_kernel<FKS_ROBOT_SE3><<<grid, 256, 0, st>>>(robot, results, rec_stride, cfg_stride, subset, m, out); break;
+        case FKS_ROBOT_LINKED: pairwise_distance_kernel<FKS_ROBOT_LINKED><<<grid, 256, 0, st>>>(robot, results, rec_stride, cfg_stride, subset, m, out); break;
+        default: return (int)cudaErrorInvalidValue;
+    }
     return (int)cudaGetLastError();
 }
 

@@ -211,6 +211,12 @@ def make_tape(draws, offsets, decisions=None, decision_offsets=None):
     return t, keep
 
 
+def _dev_ptr(x):
+    if x is None:
+        return None
+    return x.data_ptr() if hasattr(x, "data_ptr") else int(x)
+
+
 class GpuParticleContactSimulator:
     """The GPU sibling of SimpleParticleContactSimulator for the batch calls."""
 
@@ -259,6 +265,19 @@ class GpuParticleContactSimulator:
         check(lib.fks_forward_simulate_device(self._h, ptr(d_starts), ptr(d_targets), int(n), int(n_targets),
                                               int(bool(allow_contacts)), int(noise_mode), ptr(d_tape), ptr(d_tape_offsets),
                                               int(first_particle_id), ptr(d_results), int(stream) if stream else None))
+
+    # -- first consumer of a batch on the device (the planner's use of the results, uncertainty_planning_core.cpp:97-99)
+    def end_states_partition(self, d_results, n, d_order, stream=0):
+        """d_order (n x uint32 on the device) = ids without contact (ascending), then ids with contact (ascending);
+        returns (n_without_contact, n_with_contact)."""
+        counts = (C.c_uint64 * 2)()
+        check(lib.fks_end_states_partition(self._h, _dev_ptr(d_results), int(n), _dev_ptr(d_order), counts, int(stream) if stream else None))
+        return int(counts[0]), int(counts[1])
+
+    def end_states_pairwise_distance(self, d_results, m, d_out, d_subset=None, stream=0):
+        """d_out[a * m + b] = ComputeConfigurationDistanceTo (spcs.hpp:898) between records d_subset[a] and d_subset[b]."""
+        check(lib.fks_end_states_pairwise_distance(self._h, _dev_ptr(d_results), _dev_ptr(d_subset), int(m), _dev_ptr(d_out),
+                                                   int(stream) if stream else None))
 
     def trace_dtype(self):
         width = (lib.fks_sim_trace_stride(self._h) - 16) // 8

@@ -396,6 +396,25 @@ int fks_env_build_timings(const fks_env* env, double* out_ms, int n);
 int fks_env_download(const fks_env* env, fks_built_env** out);
 
 /* -------------------------------------------------------------------------------------------
+ * First consumer of a batch, on the device.  The planner that holds the simulator
+ * (uncertainty_planning_core.cpp:97-99) splits the returned particles by did_contact and groups them by configuration
+ * distance; with these two calls the end-state records of fks_forward_simulate_device stay in HBM for that step.
+ *   fks_end_states_partition          d_order[0 .. counts[0]) = ids of the particles WITHOUT contact, ascending;
+ *                                     d_order[counts[0] .. n) = ids of the particles WITH contact, ascending
+ *                                     (SimulationResult::did_contact, spcs.hpp:918).  counts is a HOST array of 2; the call
+ *                                     returns after the stream has finished these kernels.
+ *   fks_end_states_pairwise_distance  d_out[a * m + b] = robot.ComputeConfigurationDistanceTo (the call at spcs.hpp:898) from
+ *                                     record d_subset[a] to record d_subset[b]; d_subset == NULL takes records 0 .. m-1.
+ *                                     SE2 / SE3: position_distance_weight * |dt| + rotation_distance_weight * angle;
+ *                                     linked: weighted joint-space norm, continuous joints wrapped.  Asynchronous on the stream.
+ * d_results: device records as written by fks_forward_simulate_device (fks_sim_result_stride bytes each).
+ * ----------------------------------------------------------------------------------------- */
+int fks_end_states_partition(fks_sim* sim, const void* d_results, size_t n_particles, uint32_t* d_order, uint64_t* counts,
+                             void* cuda_stream);
+int fks_end_states_pairwise_distance(fks_sim* sim, const void* d_results, const uint32_t* d_subset, size_t m, double* d_out,
+                                     void* cuda_stream);
+
+/* -------------------------------------------------------------------------------------------
  * Test entry: the device's stacked-Jacobian solver (ComputeResolverCorrectionStepStackedJacobian, spcs.hpp:1990-1998 =
  * J.colPivHouseholderQr().solve(c)) on caller-provided systems, one warp each.  System i has rows[i] rows and `cols`
  * unknowns and is stored at systems + offsets[i] as cols + 1 columns of rows[i] doubles (column major, right-hand side

@@ -1619,6 +1619,28 @@ void oracle_check_config_collision(const oracle_sim* o, const double* configs, s
     for (int64_t i = 0; i < (int64_t)n; i++) out[i] = o->s.check_config_collision(configs + (size_t)i * stride, inflation_ratio) ? 1 : 0;
 }
 
+// SURVEY 8(f)-3, the first consumer of a batch (uncertainty_planning_core.cpp:97-99): particles split by did_contact
+// (ascending ids inside each part, no-contact part first) and their pairwise configuration distances
+// (robot->ComputeConfigurationDistanceTo, the call at spcs:898; RESTATEMENT of the upstream robot classes like distance_to).
+void oracle_end_states_partition(const uint32_t* flags, size_t n, uint32_t* order, uint64_t* counts2) {
+    size_t k = 0;
+    for (size_t i = 0; i < n; i++)
+        if (!(flags[i] & FKS_FLAG_DID_CONTACT)) order[k++] = (uint32_t)i;
+    counts2[0] = k;
+    for (size_t i = 0; i < n; i++)
+        if (flags[i] & FKS_FLAG_DID_CONTACT) order[k++] = (uint32_t)i;
+    counts2[1] = n - counts2[0];
+}
+void oracle_pairwise_config_distance(const oracle_sim* o, const double* configs, size_t n, double* out) {
+    const int stride = o->s.proto.cfg_stride();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        Robot robot = o->s.proto;
+        robot.set_position(configs + (size_t)i * stride, nullptr);
+        for (size_t j = 0; j < n; j++) out[(size_t)i * n + j] = robot.distance_to(configs + j * stride);
+    }
+}
+
 uint64_t oracle_tape_total(const oracle_sim* o) {
     uint64_t t = 0;
     for (auto& v : o->s.recorded) t += v.size();

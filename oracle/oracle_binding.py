@@ -44,6 +44,10 @@ def load():
                                             C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     lib.oracle_check_config_collision.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
     lib.oracle_check_config_collision.restype = None
+    lib.oracle_end_states_partition.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.oracle_end_states_partition.restype = None
+    lib.oracle_pairwise_config_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.oracle_pairwise_config_distance.restype = None
     lib.oracle_tape_total.argtypes = [C.c_void_p]
     lib.oracle_tape_total.restype = C.c_uint64
     lib.oracle_copy_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -237,6 +241,13 @@ class OracleSimulator:
         lib().oracle_check_config_collision(self._h, configs.ctypes.data, configs.shape[0], float(inflation_ratio), out.ctypes.data)
         return out.astype(bool)
 
+    def pairwise_config_distance(self, configs):
+        """ComputeConfigurationDistanceTo (spcs.hpp:898) between every pair of configurations -> (n, n)."""
+        configs = _f64(configs).reshape(-1, self.stride)
+        out = np.zeros((configs.shape[0], configs.shape[0]))
+        lib().oracle_pairwise_config_distance(self._h, configs.ctypes.data, configs.shape[0], out.ctypes.data)
+        return out
+
     def statistics(self):
         out = np.zeros(11, dtype=np.uint64)
         lib().oracle_get_statistics(self._h, out.ctypes.data)
@@ -320,6 +331,15 @@ def qr_device_model(A, b, opt_bits=3):
     out = np.zeros(4)
     lib().oracle_qr_device_model(Acm.ctypes.data, b.ctypes.data, A.shape[0], A.shape[1], int(opt_bits), x.ctypes.data, out.ctypes.data)
     return x, int(out[0]), int(out[2]), float(out[3])
+
+
+def end_states_partition(flags):
+    """Particles split by did_contact: (order, n_without_contact, n_with_contact); ascending ids inside each part."""
+    flags = np.ascontiguousarray(flags, dtype=np.uint32)
+    order = np.zeros(flags.shape[0], dtype=np.uint32)
+    counts = np.zeros(2, dtype=np.uint64)
+    lib().oracle_end_states_partition(flags.ctypes.data, flags.shape[0], order.ctypes.data, counts.ctypes.data)
+    return order, int(counts[0]), int(counts[1])
 
 
 def max_condition_of_last_call(oracle, n):
