@@ -124,6 +124,7 @@ struct fks_sim {
     // context pool of the simulate kernel: global store of parked particle contexts and their scratch slots
     char* d_ctx_store;
     int pool;
+    int pool_eighths = 16;
     // device time of the simulate kernel of the last batch call (fks_sim_kernel_times), recorded only after
     // fks_sim_enable_kernel_timing
     cudaEvent_t tev[2];
@@ -626,7 +627,9 @@ int fks_sim_create(const fks_env* env, const fks_robot* robot, const fks_solver_
     if (err != cudaSuccess) { delete s; return cuda_fail(err, "cudaGetDeviceProperties"); }
     s->grid_max = prop.multiProcessorCount * s->kinfo.max_blocks_per_sm;
     s->num_sms = prop.multiProcessorCount;
-    s->pool = std::min(2 * wpb, kMaxPool);
+    s->pool_eighths = 16;  // contexts per warp, in eighths (2 per warp)
+    if (const char* ev = std::getenv("FKS_POOL_EIGHTHS")) s->pool_eighths = std::max(8, std::atoi(ev));  // developer knob
+    s->pool = std::min((s->pool_eighths * wpb + 7) / 8, kMaxPool);
     const size_t scratch_bytes = (size_t)s->grid_max * s->pool * s->plan.sl.total;  // one small slot per context
     const size_t jscratch_bytes = (size_t)s->grid_max * wpb * s->plan.sl.jtotal;    // one tall-system slot per warp
     s->plan.pool = s->pool;
@@ -732,7 +735,7 @@ static int simulate_on_stream(fks_sim* s, const double* d_starts, const double* 
     FKS_CUDA(cudaMemsetAsync(s->d_counter, 0, 4 * sizeof(unsigned int), stream));
     const void* l2_base = s->env->l2_window_bytes ? s->env->d_sdf : nullptr;
     a.ctx_store = s->d_ctx_store;
-    a.pool = std::min(2 * wpb, s->pool);
+    a.pool = std::max(wpb, std::min((s->pool_eighths * wpb + 7) / 8, s->pool));
     if (s->timing) FKS_CUDA(cudaEventRecord(s->tev[0], stream));
     const int rc = launch_simulate(s->robot->host.kind, a, grid, dyn_smem, stream, l2_base, s->env->l2_window_bytes);
     if (rc != 0) return cuda_fail((cudaError_t)rc, "simulate kernel launch");
