@@ -157,23 +157,39 @@ def se3_highres(n_particles=65536, seed=1003, n_cuboids=256, cube=10.1, res=0.02
         oid += 1
     centres = np.array(centres)
     exts = np.array(exts)
+    boxes = obstacles[8:]
     prng = np.random.Generator(np.random.MT19937(seed))
     starts = np.empty((n_particles, 12))
     targets = np.empty((n_particles, 12))
     i = 0
     while i < n_particles:
-        c = prng.uniform(-h + 0.6, h - 0.6, 3)
-        # keep the start clear of every cuboid's bounding sphere + peg radius (free space)
-        if np.any(np.linalg.norm(centres - c, axis=1) < exts + 0.33):
-            continue
         rv = prng.normal(0.0, 0.5, 3)
-        d = prng.normal(0.0, 1.0, 3)
-        d = 0.3 * d / np.linalg.norm(d)
+        if i % 2 == 0:
+            # free flight: anywhere clear of every cuboid's bounding sphere + peg radius, 0.3 m in a random direction
+            c = prng.uniform(-h + 0.6, h - 0.6, 3)
+            if np.any(np.linalg.norm(centres - c, axis=1) < exts + 0.33):
+                continue
+            d = prng.normal(0.0, 1.0, 3)
+            d = 0.3 * d / np.linalg.norm(d)
+        else:
+            # approach: in front of a face of a random cuboid (clear of all the others), 0.3 m straight at the face --
+            # the peg ends up pressed against it, so half of the batch resolves contacts against the HBM-resident SDF
+            k = int(prng.integers(0, len(boxes)))
+            T, ext = np.asarray(boxes[k][0]).reshape(3, 4), np.asarray(boxes[k][1])
+            a, sgn = int(prng.integers(0, 3)), (1.0 if prng.random() < 0.5 else -1.0)
+            normal = sgn * T[:, a]
+            lateral = sum(prng.uniform(-0.5, 0.5) * ext[b] * T[:, b] for b in range(3) if b != a)
+            c = T[:, 3] + normal * (ext[a] + 0.31 + prng.uniform(0.02, 0.12)) + lateral
+            others = np.arange(len(boxes)) != k
+            if np.any(np.abs(c) > h - 0.6) or np.any(np.linalg.norm(centres[others] - c, axis=1) < exts[others] + 0.33):
+                continue
+            d = -0.3 * normal
         starts[i] = _se3_config(c, rv)
         targets[i] = _se3_config(c + d, rv)
         i += 1
     return Workload("se3_highres", capi.ROBOT_SE3, obstacles, res, _se3_robot(), starts, targets,
-                    "SE(3) peg (P=396) among %d random cuboids, %.2f m cube at res %.3f (HBM-resident SDF)" % (n_cuboids, cube, res))
+                    "SE(3) peg (P=396) among %d random cuboids, %.2f m cube at res %.3f (HBM-resident SDF); every second particle is "
+                    "driven 0.3 m straight at a cuboid face, the others 0.3 m in a random direction through free space" % (n_cuboids, cube, res))
 
 
 # ------------------------------------------------------------------------------------------------

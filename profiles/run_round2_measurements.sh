@@ -21,5 +21,9 @@ B2="$B --workload se3_narrow_passage --particles 16384"
 $B2 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:simulate_kernel -s 1 -c 1 -f -o $O/prof_r2_se3_narrow $B2 > $O/ncu_full_r2_se3.log 2>&1; echo full2_rc=$?
 B4="$B --workload se3_highres"
 $B4 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:simulate_kernel -s 1 -c 1 -f -o $O/prof_r2_se3_highres $B4 > $O/ncu_full_r2_highres.log 2>&1; echo full4_rc=$?
+# config 4 with the link-level culling of check_env on (default) and off: DRAM bytes and duration of the simulate kernel
+for c in 1 0; do
+  FKS_CULL=$c $B4 > /dev/null 2>&1 && FKS_CULL=$c ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sectors.sum --clock-control none -k regex:simulate_kernel -s 1 -c 1 --csv --log-file $O/dram_r2_highres_cull$c.csv $B4 > /dev/null 2>&1; echo cull${c}_rc=$?
+done
 python tests/gpu_perf.py > $O/gpu_perf_r2.log 2>&1
 echo done
