@@ -988,6 +988,9 @@ int fks_debug_phase_cycles(fks_sim* s, uint64_t* out16) {
     DeviceGuard guard(s->device);
     FKS_CUDA(cudaDeviceSynchronize());
     FKS_CUDA(cudaMemcpy(out16, s->d_stats + 16, 48 * sizeof(uint64_t), cudaMemcpyDeviceToHost));  // 48 values
+    launch_dbg_copy(s->d_stats + 64, nullptr);  // (timers build: 64 more developer counters behind them)
+    FKS_CUDA(cudaDeviceSynchronize());
+    FKS_CUDA(cudaMemcpy(out16 + 48, s->d_stats + 64, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return FKS_OK;
 }
 

@@ -317,6 +317,7 @@ int launch_partition(const char* results, size_t rec_stride, int cfg_stride, siz
                      unsigned* order, void* stream);
 int launch_pairwise_distance(int kind, const DevRobot* robot, const char* results, size_t rec_stride, int cfg_stride, const unsigned* subset,
                              unsigned m, double* out, void* stream);
+int launch_dbg_copy(unsigned long long* out, void* stream);  // developer counters of the FKS_PHASE_TIMERS build
 int launch_fp64_peak(double* out, int grid, int iters, void* stream);
 int launch_gather(const float* data, unsigned long long n_mask, float* out, int grid, int iters, void* stream);
 

@@ -627,9 +627,13 @@ __device__ __noinline__ bool check_env(int wb, int X, int use_cull, double colli
     unsigned links = (!use_cull || !e.cull || (double)oob < thr) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, thr > 0.0 ? thr : 0.0);
     // walk the runs of consecutive active links (one contiguous point range each), kBatch x 32 points -- kBatch
     // independent gathers per lane -- at a time
+    // ... the DISTAL run first: the answer is a disjunction over the points, so the order is free, and a serial chain touches
+    // things with its far end more often than with its base -- a colliding configuration is then settled on the first run
+    bool first_run = true;
     while (links) {
-        const int first = __ffs(links) - 1;
-        const int len = __ffs(~(links >> first)) - 1;
+        const int last = 31 - __clz(links);                     // highest active link
+        const int len = __clz(~(links << (31 - last)));         // length of the run of active links that ends there
+        const int first = last - len + 1;
         links &= ~(((len >= 32) ? 0xffffffffu : ((1u << len) - 1u)) << first);
         const int end = rb.link_begin[first + len];
         for (int pos = rb.link_begin[first]; pos < end; pos += 32 * kBatch) {
@@ -663,6 +667,12 @@ __device__ __noinline__ bool check_env(int wb, int X, int use_cull, double colli
                 nlist += __popc(m);
             }
         }
+        if (first_run && links != 0u && nlist > 0) {  // near-surface points on the distal run: look at them before walking on
+            __syncwarp();
+            if (check_env_second_tier(wb, X, list, nlist, thr)) return true;
+            nlist = 0;
+        }
+        first_run = false;
     }
     __syncwarp();
     return nlist > 0 && check_env_second_tier(wb, X, list, nlist, thr);
@@ -836,6 +846,72 @@ __device__ __forceinline__ void scan_link_cell(const SelfCtx& sc, const double* 
     }
 }
 
+// cell key of a link point: LocationToExtendedGridIndex (spcs:1173-1181) DIVIDES by the map resolution and truncates toward
+// zero; the three coordinates are packed 21 bits each (cells of one robot pose never differ by 2^21)
+__device__ __forceinline__ unsigned long long self_cell_key(const DevEnv& e, const double* T, double x, double y, double z) {
+    double wx, wy, wz;
+    apply_T(T, x, y, z, wx, wy, wz);
+    const double gx = e.inv_origin[0] * wx + e.inv_origin[1] * wy + e.inv_origin[2] * wz + e.inv_origin[3];
+    const double gy = e.inv_origin[4] * wx + e.inv_origin[5] * wy + e.inv_origin[6] * wz + e.inv_origin[7];
+    const double gz = e.inv_origin[8] * wx + e.inv_origin[9] * wy + e.inv_origin[10] * wz + e.inv_origin[11];
+    const long long kx = (long long)(gx / e.map_res), ky = (long long)(gy / e.map_res), kz = (long long)(gz / e.map_res);
+    return ((unsigned long long)kx & 0x1FFFFFull) | (((unsigned long long)ky & 0x1FFFFFull) << 21) | (((unsigned long long)kz & 0x1FFFFFull) << 42);
+}
+
+// 10 bits per axis of a cell key: equal keys stay equal
+__device__ __forceinline__ unsigned fold_cell_key(unsigned long long k) {
+    return (unsigned)(k & 0x3FFull) | ((unsigned)((k >> 21) & 0x3FFull) << 10) | ((unsigned)((k >> 42) & 0x3FFull) << 20);
+}
+// Middle phase between the capsule test and the exact pass: do two links of a candidate pair have points in ONE cell at all?
+// Keys in registers, compared through shuffles -- no scratch memory, a few thousand clocks -- on a 30-bit fold of the exact
+// pass's key (10 bits per axis: equal keys stay equal, so a miss here is a miss there; a false hit only costs the exact pass).
+// The capsule bound has to allow for cells that are two cells wide, so most of its candidates share no cell: without this
+// phase 1.5 % of the arm's collision checks ran the 30 k-clock exact pass for 1 % of them to find anything, and the slowest
+// warp of a lock-step round was, every third round, one of those (profiles/r2_kernel_experiments.md).
+__device__ __noinline__ bool self_pairs_share_a_cell(int wb, int Xcur, unsigned cp0, unsigned cp1, unsigned cp2, unsigned cp3) {
+    const Frame& fr = frame();
+    const DevRobot& rb = fr.rb;
+    const DevEnv& e = fr.a.env;
+    const int lane = lane_id();
+    const double* Tcur = wsd(wb) + fr.a.wl.T + Xcur * fr.a.wl.L12;
+    const double2* pxy = reinterpret_cast<const double2*>(smem_raw + fr.a.pts_off);
+    const PointZL* pzl = reinterpret_cast<const PointZL*>(pxy + fr.a.P);
+    const unsigned cps[kPairChunks] = {cp0, cp1, cp2, cp3};
+#pragma unroll 1
+    for (int ch = 0; ch < kPairChunks; ch++) {
+        unsigned m = cps[ch];
+        while (m) {
+            const int q = ch * 32 + (__ffs(m) - 1);
+            m &= m - 1u;
+            const int la = rb.pair_a[q], lb = rb.pair_b[q];
+            const int a0 = rb.link_begin[la], a1 = rb.link_begin[la + 1], b0 = rb.link_begin[lb], b1 = rb.link_begin[lb + 1];
+            // 64 points of link a in two registers per lane; the points of link b, 32 at a time, are passed around once
+#pragma unroll 1
+            for (int ab = a0; ab < a1; ab += 64) {
+                unsigned ka0 = 0x80000000u, ka1 = 0x80000000u;  // no point: equal to no key of the other link
+                const int pa0 = ab + lane, pa1 = ab + 32 + lane;
+                if (pa0 < a1) ka0 = fold_cell_key(self_cell_key(e, Tcur + 12 * la, pxy[pa0].x, pxy[pa0].y, pzl[pa0].z));
+                if (pa1 < a1) ka1 = fold_cell_key(self_cell_key(e, Tcur + 12 * la, pxy[pa1].x, pxy[pa1].y, pzl[pa1].z));
+#pragma unroll 1
+                for (int bb = b0; bb < b1; bb += 32) {
+                    const int pb = bb + lane;
+                    unsigned kb = 0xC0000000u;
+                    if (pb < b1) kb = fold_cell_key(self_cell_key(e, Tcur + 12 * lb, pxy[pb].x, pxy[pb].y, pzl[pb].z));
+                    const int nb = min(32, b1 - bb);
+                    bool hit = false;
+#pragma unroll 4
+                    for (int s2 = 0; s2 < nb; s2++) {
+                        const unsigned k = __shfl_sync(FKS_FULL, kb, s2);
+                        hit = hit | (ka0 == k) | (ka1 == k);
+                    }
+                    if (__any_sync(FKS_FULL, hit)) return true;
+                }
+            }
+        }
+    }
+    return false;
+}
+
 __device__ __noinline__ bool self_collisions_exact(int wb, int Xprev, int Xcur, unsigned cp0, unsigned cp1, unsigned cp2, unsigned cp3) {
     const Frame& fr = frame();
     const DevRobot& rb = fr.rb;
@@ -875,14 +951,7 @@ __device__ __noinline__ bool self_collisions_exact(int wb, int Xprev, int Xcur, 
         const int l = pzl[p].link;
         unsigned long long key = 0ull;
         if ((cand >> l) & 1u) {
-            double wx, wy, wz;
-            apply_T(Tcur + 12 * l, pxy[p].x, pxy[p].y, pzl[p].z, wx, wy, wz);
-            const double gx = e.inv_origin[0] * wx + e.inv_origin[1] * wy + e.inv_origin[2] * wz + e.inv_origin[3];
-            const double gy = e.inv_origin[4] * wx + e.inv_origin[5] * wy + e.inv_origin[6] * wz + e.inv_origin[7];
-            const double gz = e.inv_origin[8] * wx + e.inv_origin[9] * wy + e.inv_origin[10] * wz + e.inv_origin[11];
-            const long long kx = (long long)(gx / e.map_res), ky = (long long)(gy / e.map_res), kz = (long long)(gz / e.map_res);
-            key = ((unsigned long long)kx & 0x1FFFFFull) | (((unsigned long long)ky & 0x1FFFFFull) << 21) |
-                  (((unsigned long long)kz & 0x1FFFFFull) << 42);
+            key = self_cell_key(e, Tcur + 12 * l, pxy[p].x, pxy[p].y, pzl[p].z);
         }
         sc.keys[p] = key;
         sc.sflag[p] = 0;
@@ -1087,14 +1156,36 @@ __device__ __forceinline__ bool collect_self(int wb, int Xprev, int Xcur) {
         anyc = anyc || (m != 0u);
     }
     if (!anyc) return false;
+    if (!self_pairs_share_a_cell(wb, Xcur, cp[0], cp[1], cp[2], cp[3])) return false;
     return self_collisions_exact(wb, Xprev, Xcur, cp[0], cp[1], cp[2], cp[3]);
 }
 
 // CheckCollision (spcs:1418-1436): bit 0 = in collision, bit 1 = self-collision map non-empty
+#ifdef FKS_PHASE_TIMERS
+__device__ unsigned long long g_dbg[64];  // developer counters: [0..15] histogram of check_env clocks (bins of 2048), [16..31] of collect_self, 32.. sums
+#endif
 template <int KIND>
 __device__ __forceinline__ unsigned check_collision(int wb, int Xprev, int Xcur, int use_cull) {
+#ifdef FKS_PHASE_TIMERS
+    const long long t0 = clock64();
+#endif
     const bool envc = check_env(wb, Xcur, use_cull, 0.0);
+#ifdef FKS_PHASE_TIMERS
+    const long long t1 = clock64();
+#endif
     const bool has_self = (KIND == FKS_ROBOT_LINKED) ? collect_self(wb, Xprev, Xcur) : false;
+#ifdef FKS_PHASE_TIMERS
+    if (lane_id() == 0) {
+        const long long t2 = clock64();
+        atomicAdd(&g_dbg[min((int)((t1 - t0) >> 11), 15)], 1ull);
+        atomicAdd(&g_dbg[16 + min((int)((t2 - t1) >> 11), 15)], 1ull);
+        atomicAdd(&g_dbg[32], (unsigned long long)(t1 - t0));
+        atomicAdd(&g_dbg[33], (unsigned long long)(t2 - t1));
+        atomicAdd(&g_dbg[34 + (envc ? 1 : 0)], 1ull);
+        atomicAdd(&g_dbg[36 + (envc ? 1 : 0)], (unsigned long long)(t1 - t0));
+        atomicAdd(&g_dbg[38 + (has_self ? 1 : 0)], 1ull);
+    }
+#endif
     return ((envc || has_self) ? 1u : 0u) | (has_self ? 2u : 0u);
 }
 
@@ -1152,7 +1243,7 @@ __device__ __noinline__ int collect_corrections(int wb, int Xprev, int Xcur, boo
     // ---- pass 1 -----------------------------------------------------------------------------------
     int ncand = 0;
     unsigned links = (fr.a.cull_mode != 1 || !e.cull || has_self) ? ((1u << rb.L) - 1u) : active_links(e, rb, G, 2.0 * res);
-    while (links) {
+    while (links) {  // ascending: the rows of the stacked system are in (link, point) order (spcs:1893-1929)
         const int first = __ffs(links) - 1;
         const int len = __ffs(~(links >> first)) - 1;
         links &= ~(((len >= 32) ? 0xffffffffu : ((1u << len) - 1u)) << first);
@@ -2783,6 +2874,23 @@ int launch_pairwise_distance(int kind, const DevRobot* robot, const char* result
     return (int)cudaGetLastError();
 }
 
+#ifdef FKS_PHASE_TIMERS
+__global__ void dbg_copy_kernel(unsigned long long* out) {
+    if (threadIdx.x < 64) {
+        out[threadIdx.x] = g_dbg[threadIdx.x];
+        g_dbg[threadIdx.x] = 0ull;
+    }
+}
+#endif
+int launch_dbg_copy(unsigned long long* out, void* stream) {
+#ifdef FKS_PHASE_TIMERS
+    dbg_copy_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(out);
+#else
+    (void)out;
+    (void)stream;
+#endif
+    return (int)cudaGetLastError();
+}
 int launch_fp64_peak(double* out, int grid, int iters, void* stream) {
     fp64_peak_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, iters);
     return (int)cudaGetLastError();

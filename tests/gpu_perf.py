@@ -35,7 +35,7 @@ def run(name, n, free=False, reps=3):
         s["total_microsteps"] / best * 1e3, int(((rec["flags"] & 2) != 0).sum()), int((rec["flags"] & 1).sum())), flush=True)
     import ctypes as C
     if hasattr(capi.lib, "fks_debug_phase_cycles"):
-        ph = (C.c_uint64 * 48)()
+        ph = (C.c_uint64 * 112)()
         capi.lib.fks_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
         capi.lib.fks_debug_phase_cycles(sim._h, ph)
         tot = float(sum(ph[:10])) or 1.0
@@ -54,6 +54,12 @@ def run(name, n, free=False, reps=3):
             nr_, ns_ = max(ph[21], 1), max(ph[23], 1)
             print("    slowest warp per cycle (mean over cycles): A %.0f, B %.0f, T %.0f per round cycle; swap %.0f per cycle; collect %.0f, solve %.0f, estimate %.0f per solve cycle" % (
                 ph[24] / nr_, ph[25] / nr_, ph[26] / nr_, ph[27] / (nr_ + ns_), ph[28] / ns_, ph[29] / ns_, ph[30] / ns_), flush=True)
+            d = ph[48:]
+            if sum(d[:16]):
+                print("    check_env clocks, bins of 2048: " + " ".join(str(int(v)) for v in d[0:16]), flush=True)
+                print("    collect_self clocks, bins of 2048: " + " ".join(str(int(v)) for v in d[16:32]), flush=True)
+                print("    check_env mean %.0f clk, collect_self mean %.0f clk; check_env no-collision %d calls mean %.0f clk, collision %d calls mean %.0f clk; self: %d without / %d with" % (
+                    d[32] / max(sum(d[:16]), 1), d[33] / max(sum(d[:16]), 1), d[34], d[36] / max(d[34], 1), d[35], d[37] / max(d[35], 1), d[38], d[39]), flush=True)
     sim.close()
 
 
