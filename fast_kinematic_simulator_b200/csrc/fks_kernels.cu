@@ -1472,6 +1472,11 @@ __device__ __forceinline__ double quad_sum(unsigned mask, double p) {
 // the solver's row loops stay rolled: 30 KB less code for the warps of a SOLVE cycle to fetch, 2-5 % faster on the contact
 // workloads than nvcc's default unrolling (profiles/r2_kernel_experiments.md)
 #define FKS_QR_INNER_LOOP _Pragma("unroll 1")
+// ... but the loads of FKS_QR_BATCH rows go out together: a system in the global store pays an L2 round trip per load
+// otherwise (solve from the global store 126 k -> 82 k clocks at 4; 2 measured as fast as 4 and 8 end to end, with less code); the sums stay in row order
+#ifndef FKS_QR_BATCH
+#define FKS_QR_BATCH 2
+#endif
 template <int SLOTS>  // columns per quad: 1 for up to 8 columns (every robot of the reference), 2 for up to 16
 __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows, int cols, int x_off) {
     const Frame& fr = frame();
@@ -1653,8 +1658,20 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
             const bool reflect = !last_row && tau != 0.0;
             if (reflect) {
                 double pd = 0.0;
+                int r = r0;
                 FKS_QR_INNER_LOOP
-                for (int r = r0; r < rows; r += 4) pd = add_rn(pd, mul_rn(piv[r], mine[r]));
+                for (; r + 4 * (FKS_QR_BATCH - 1) < rows; r += 4 * FKS_QR_BATCH) {
+                    double av[FKS_QR_BATCH], bv2[FKS_QR_BATCH];
+#pragma unroll
+                    for (int u = 0; u < FKS_QR_BATCH; u++) {
+                        av[u] = piv[r + 4 * u];
+                        bv2[u] = mine[r + 4 * u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < FKS_QR_BATCH; u++) pd = add_rn(pd, mul_rn(av[u], bv2[u]));
+                }
+                FKS_QR_INNER_LOOP
+                for (; r < rows; r += 4) pd = add_rn(pd, mul_rn(piv[r], mine[r]));
                 tmp = add_rn(quad_sum(quad, pd), ak);
                 ak = sub_rn(ak, mul_rn(tau, tmp));
             } else if (last_row) {
@@ -1663,8 +1680,31 @@ __device__ __noinline__ void colpiv_qr_lanes(int wb, double* A, int ld, int rows
             __syncwarp(quad);  // every lane of the quad has read the old mine[k]
             if (i == 0) mine[k] = ak;
             double p1 = 0.0, p2 = 0.0;
+            int r = r0;
             FKS_QR_INNER_LOOP
-            for (int r = r0; r < rows; r += 4) {
+            for (; r + 4 * (FKS_QR_BATCH - 1) < rows; r += 4 * FKS_QR_BATCH) {
+                double v[FKS_QR_BATCH];
+#pragma unroll
+                for (int u = 0; u < FKS_QR_BATCH; u++) v[u] = mine[r + 4 * u];
+                if (reflect) {
+                    double av[FKS_QR_BATCH];
+#pragma unroll
+                    for (int u = 0; u < FKS_QR_BATCH; u++) av[u] = piv[r + 4 * u];
+#pragma unroll
+                    for (int u = 0; u < FKS_QR_BATCH; u++) {
+                        v[u] = sub_rn(v[u], mul_rn(mul_rn(tau, av[u]), tmp));
+                        mine[r + 4 * u] = v[u];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < FKS_QR_BATCH; u++) {
+                    const double sq = mul_rn(v[u], v[u]);
+                    p1 = add_rn(p1, sq);
+                    if (u > 0 || r >= k + 2) p2 = add_rn(p2, sq);  // r + 4 >= k + 2 always (r >= k + 1)
+                }
+            }
+            FKS_QR_INNER_LOOP
+            for (; r < rows; r += 4) {
                 double v = mine[r];
                 if (reflect) {
                     v = sub_rn(v, mul_rn(mul_rn(tau, piv[r]), tmp));
