@@ -119,7 +119,7 @@ def bench_md():
              "`r2_kernel_experiments.md`).\n" % (r["bound"], r["achieved"], r["peak"], r["unit"], r["frac"], rh["achieved"], rh["peak"], rh["frac"],
                                                  r["traffic"], r["algorithmic_bytes_per_launch"], r64["achieved"], r64["peak"], r64["frac"]))
     L.append("Full JSON of the default run:\n\n```json\n%s\n```\n" % json.dumps(main))
-    for name, title in (("bench_r2_2gpu.json", "Two GPUs"), ("bench_r2_8gpu.json", "Eight GPUs")):
+    for name, title in (("bench_r2_2gpu.json", "Two GPUs"), ("bench_r2_4gpu.json", "Four GPUs"), ("bench_r2_8gpu.json", "Eight GPUs")):
         d = load(name)
         if d:
             c5 = d.get("config5") or {}
