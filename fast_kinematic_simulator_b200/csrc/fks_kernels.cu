@@ -1848,11 +1848,17 @@ enum {
 };
 enum { NEED_EMPTY = 0, NEED_ROUND = 1, NEED_SOLVE = 2, NEED_DEAD = 3 };  // what a context of the pool waits for
 
+#ifndef FKS_COPY_UNROLL
+#define FKS_COPY_UNROLL 4
+#endif
 // a context's three ranges (fks_device_types.h) between the warp's shared block and its slot of the global context store
 __device__ __forceinline__ void context_copy(double* ws, double* g, const WarpLayout& wl, bool to_global) {
     const int lane = lane_id();
     const int n0 = wl.T + 2 * wl.L12 - wl.cfg, n1 = wl.L12, n2 = wl.save2_end - wl.target;
     // (cache-global loads / stores: the slot is written and read by different warps of the CTA, the L1 is not coherent)
+    // Measured and NOT adopted (profiles/r2_kernel_experiments.md): explicit batches of 4 / 8 loads in flight, one fused
+    // park + load pass, a __noinline__ copy -- each made the whole kernel 3-13 % slower, free flight included: the extra
+    // live registers in this function cost more than the shorter copy wins.
     if (to_global) {
         for (int e = lane; e < n0; e += 32) __stcg(g + e, ws[wl.cfg + e]);
         for (int e = lane; e < n1; e += 32) __stcg(g + n0 + e, ws[wl.G + e]);
@@ -1960,7 +1966,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock, FKS_MIN_BLOCKS) simulate_ker
     __shared__ unsigned cyc_max[8];     // per cycle: longest A, B, T, swap, collect, solve, estimate of any warp
     long long tmax[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (threadIdx.x < 8) cyc_max[threadIdx.x] = 0u;
-#define FKS_MAXTICK(i, since) { if (lane == 0) atomicMax(&cyc_max[i], (unsigned)(clock64() - (since))); }
+#define FKS_MAXTICK(i, since) { if (lane == 0) { const unsigned dt_ = (unsigned)(clock64() - (since)); atomicMax(&cyc_max[i], dt_); if ((i) == 0 || (i) == 2 || (i) == 3) atomicAdd(&g_dbg[((i) == 0 ? 40 : ((i) == 2 ? 48 : 56)) + min((int)(dt_ >> 11), 7)], 1ull); } }
 #else
 #define FKS_TICK(i)
 #define FKS_MAXTICK(i, since)

@@ -58,6 +58,7 @@ def run(name, n, free=False, reps=3):
             if sum(d[:16]):
                 print("    check_env clocks, bins of 2048: " + " ".join(str(int(v)) for v in d[0:16]), flush=True)
                 print("    collect_self clocks, bins of 2048: " + " ".join(str(int(v)) for v in d[16:32]), flush=True)
+                print("    A / T / swap clocks, bins of 2048: " + " ".join(str(int(v)) for v in d[40:48]) + " / " + " ".join(str(int(v)) for v in d[48:56]) + " / " + " ".join(str(int(v)) for v in d[56:64]), flush=True)
                 print("    check_env mean %.0f clk, collect_self mean %.0f clk; check_env no-collision %d calls mean %.0f clk, collision %d calls mean %.0f clk; self: %d without / %d with" % (
                     d[32] / max(sum(d[:16]), 1), d[33] / max(sum(d[:16]), 1), d[34], d[36] / max(d[34], 1), d[35], d[37] / max(d[35], 1), d[38], d[39]), flush=True)
     sim.close()
