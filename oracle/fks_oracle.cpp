@@ -534,8 +534,7 @@ struct Robot {
 
     // TruncatedNormalUncertainVelocityActuator::GetControlValue (unc:70-75 / 77-90).
     // `tn` = output of noise_distribution_(rng); nullptr = noiseless overload.
-    inline double actuate(int axis, double u, const double* tn, bool* nan_seen) const {
-        const fks_axis_params& a = mdl->axes[(size_t)axis];
+    static inline double actuate_axis(const fks_axis_params& a, double u, const double* tn, bool* nan_seen) {
         if (std::isnan(u) || std::isinf(u)) *nan_seen = true;  // assert unc:72-73
         const double vl = std::abs(a.velocity_limit);
         const double real_u = clamp_value(u, -vl, vl);
@@ -545,6 +544,9 @@ struct Robot {
         const double bound = std::max(pb, mb);
         const double real_noise = (*tn) * bound;
         return real_u + real_noise;
+    }
+    inline double actuate(int axis, double u, const double* tn, bool* nan_seen) const {
+        return actuate_axis(mdl->axes[(size_t)axis], u, tn, nan_seen);
     }
 
     // ApplyControlInput(input[, rng]) (tnuva:152-177 SE2, :348-382 SE3, :538-596 linked)
@@ -1734,6 +1736,21 @@ void oracle_pid_run(double kp, double ki, double kd, double iclamp, const double
     Pid p;
     p.init(kp, ki, kd, iclamp);
     for (int i = 0; i < n; i++) out[i] = p.feedback(errors[i], timesteps[i]);
+}
+// the oracle's actuator (Robot::actuate_axis) on n (control, draw) pairs: noiseless and noisy value per pair -- pinned
+// against the reference's own simple_uncertainty_models.hpp (oracle/_ref/unc_ref) by tests/test_oracle_actuator.py
+void oracle_actuate_run(double velocity_limit, double proportional_noise, double minimum_noise, const double* controls,
+                        const double* draws, int n, double* out_quiet, double* out_noisy) {
+    fks_axis_params a;
+    std::memset(&a, 0, sizeof(a));
+    a.velocity_limit = velocity_limit;
+    a.proportional_noise = proportional_noise;
+    a.minimum_noise = minimum_noise;
+    bool nan_seen = false;
+    for (int i = 0; i < n; i++) {
+        out_quiet[i] = Robot::actuate_axis(a, controls[i], nullptr, &nan_seen);
+        out_noisy[i] = Robot::actuate_axis(a, controls[i], draws + i, &nan_seen);
+    }
 }
 void oracle_exp_twist(const double* twist, double* out12) {
     const Iso T = exp_twist(twist);

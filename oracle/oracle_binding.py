@@ -11,6 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfks_oracle.so")
 PID_REF = os.path.join(_HERE, "_ref", "pid_ref")
+UNC_REF = os.path.join(_HERE, "_ref", "unc_ref")
 
 ORACLE_NOISE_MT19937 = 3
 SENS_NAMES = ("cell_boundary", "est_threshold", "est_zero", "rank_cut", "pivot_tie", "nmicro", "normal_tie",
@@ -44,6 +45,8 @@ def load():
                                             C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     lib.oracle_check_config_collision.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
     lib.oracle_check_config_collision.restype = None
+    lib.oracle_actuate_run.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.oracle_actuate_run.restype = None
     lib.oracle_end_states_partition.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.oracle_end_states_partition.restype = None
     lib.oracle_pairwise_config_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -353,6 +356,27 @@ def sensitivity_of_last_call(oracle, n):
     sens = np.zeros(n, dtype=np.uint32)
     lib().oracle_copy_sensitivity(oracle._h, sens.ctypes.data)
     return sens
+
+
+def actuator_reference(velocity_limit, acceleration_limit, proportional_noise, minimum_noise, percent_variance, controls, draws):
+    """Run the REFERENCE's own TruncatedNormalUncertainVelocityActuator (oracle/_ref/unc_ref, simple_uncertainty_models.hpp
+    compiled against the stand-in of arc_utilities in oracle/shim) with injected draws.
+    -> (noiseless values, noisy values, (mean, stddev, lower, upper) handed to its noise distribution)."""
+    lines = ["%r %r %r %r %r %d" % (float(velocity_limit), float(acceleration_limit), float(proportional_noise), float(minimum_noise),
+                                    float(percent_variance), len(controls))]
+    lines += ["%r %r" % (float(c), float(d)) for c, d in zip(controls, draws)]
+    out = subprocess.run([UNC_REF], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split()
+    vals = np.array([float(x) for x in out[:2 * len(controls)]]).reshape(-1, 2)
+    return vals[:, 0], vals[:, 1], tuple(float(x) for x in out[2 * len(controls):])
+
+
+def actuator_oracle(velocity_limit, proportional_noise, minimum_noise, controls, draws):
+    """The oracle's actuator arithmetic (Robot::actuate_axis) on the same pairs -> (noiseless, noisy)."""
+    controls, draws = _f64(controls), _f64(draws)
+    quiet, noisy = np.zeros(len(controls)), np.zeros(len(controls))
+    lib().oracle_actuate_run(float(velocity_limit), float(proportional_noise), float(minimum_noise), controls.ctypes.data,
+                             draws.ctypes.data, len(controls), quiet.ctypes.data, noisy.ctypes.data)
+    return quiet, noisy
 
 
 def pid_reference(kp, ki, kd, iclamp, errors, timesteps):

@@ -4,6 +4,8 @@ vectors, which come from the REFERENCE's own header through oracle/_ref/pid_ref)
     python tests/golden/make_golden.py
 
 * pid_golden.json        -- outputs of the reference's SimplePIDController (bit-exact pin of the PID restatement)
+* actuator_golden.json   -- outputs of the reference's TruncatedNormalUncertainVelocityActuator with injected draws
+                            (simple_uncertainty_models.hpp through oracle/_ref/unc_ref: bit-exact pin of the actuator restatement)
 * env_golden.npz         -- BuildCompleteEnvironment of two small obstacle sets (tests/env_cases.py: thin_plates, rotated_boxes)
                             by the oracle: occupancy, float SDF, surface-normal table (host and device builder are held to it)
 * trace_golden.npz       -- step traces (ForwardSimulationStepTrace, flat) of single particles by the oracle, Philox noise
@@ -25,6 +27,21 @@ sys.path.insert(0, ROOT)
 
 from fast_kinematic_simulator_b200 import capi, workloads as W  # noqa: E402
 from oracle import oracle_binding as OB  # noqa: E402
+
+
+def actuator():
+    rng = np.random.default_rng(2025)
+    cases = []
+    for _ in range(24):
+        params = [float(rng.uniform(-2.0, 2.0)), 0.3, float(rng.uniform(-0.5, 0.5)), float(rng.uniform(-0.1, 0.1)),
+                  float(rng.choice([0.5, -0.5, 0.0, 1.7, 0.25]))]
+        controls = [float(x) for x in rng.normal(0.0, 1.5, 28)] + [0.0, params[0], -params[0], 10.0 * params[0]]
+        draws = [float(x) for x in rng.uniform(-1.0, 1.0, 28)] + [1.0, -1.0, 0.0, 0.5]
+        quiet, noisy, dist = OB.actuator_reference(*params, controls, draws)
+        cases.append(dict(params=params, controls=controls, draws=draws, quiet=[float(x) for x in quiet],
+                          noisy=[float(x) for x in noisy], distribution=list(dist)))
+    json.dump(dict(source="reference simple_uncertainty_models.hpp via oracle/_ref/unc_ref (arc_utilities stand-in: oracle/shim)", cases=cases),
+              open(os.path.join(HERE, "actuator_golden.json"), "w"))
 
 
 def pid():
@@ -102,6 +119,7 @@ def traces():
 
 if __name__ == "__main__":
     pid()
+    actuator()
     forward()
     environments()
     traces()
