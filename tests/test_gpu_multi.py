@@ -75,3 +75,63 @@ def test_device_resident_results_are_all_gathered_on_every_device():
     for d in range(g):
         rec = dr[d].cpu().numpy().view(m.dtype)
         assert np.array_equal(rec, single.records), d
+
+
+# ---- one process per GPU: fast_kinematic_simulator_b200/distributed.py over NCCL (the torchrun deployment) ---------------
+def _nccl_worker(rank, world, port, n, q):
+    import os
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from fast_kinematic_simulator_b200 import capi, workloads as W
+    from fast_kinematic_simulator_b200.distributed import ShardedForwardSimulator, reduce_statistics
+
+    w = W.arm_table(n)
+    sim = w.make_simulator(device=rank)
+
+    def shard(starts, targets, first_id):
+        return sim.forward_simulate_robots(starts, targets, True, capi.NOISE_PHILOX, first_particle_id=first_id).records
+
+    sh = ShardedForwardSimulator(shard, sim.result_stride, torch.device("cuda", rank))
+    out = sh.forward_simulate_robots(w.starts, w.targets)
+    s = sim.get_statistics()
+    stats = reduce_statistics([s[k] for k in capi.STAT_NAMES], torch.device("cuda", rank))
+    if rank == 0:
+        q.put((out.cpu().numpy().tobytes(), stats.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_process_per_gpu_over_nccl_matches_one_gpu():
+    """ShardedForwardSimulator (ragged contiguous shards, all_gather_into_tensor over NCCL, all-reduced counters) on two
+    ranks == one GPU, byte for byte."""
+    import os
+
+    import torch.multiprocessing as mp
+
+    n, world = 1001, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    raw, stats = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    w = W.arm_table(n)
+    sim = w.make_simulator()
+    ref = sim.forward_simulate_robots(w.starts, w.targets, True, capi.NOISE_PHILOX)
+    assert raw == ref.records.tobytes()
+    s = sim.get_statistics()
+    assert stats == [s[k] for k in capi.STAT_NAMES]
