@@ -81,3 +81,23 @@ def test_tiny_batches_spread_over_sms():
     for n in (1, 2, 31, 33, 127):
         part = sim.forward_simulate_robots(w.starts[:n], w.targets, True, capi.NOISE_PHILOX)
         assert np.array_equal(part.records, full.records[:n])
+
+
+def test_arm_table_full_size_against_the_oracle():
+    """BASELINE config 3 at its full size -- 65 536 arm particles in contact -- in injection mode: the oracle's draws, its
+    solver decisions and the solutions of its ill-conditioned solves (condition estimate > 100) on the tapes.  Every flag
+    and counter of EVERY particle and the statistics must be the oracle's; 99.9 % of the configurations must be within the
+    1e-9 of the north star (measured: 65 515 of 65 536), at most 0.02 % beyond 1e-6 (measured: 3; a chain of hundreds of
+    condition-100 solves carries 1e-16 that far now and then), none beyond 1e-2 (measured maximum 1.6e-4)."""
+    n = 65536
+    w = W.arm_table(n)
+    rep, gpu, ref, sens = parity.run_parity(w, n, decision_cond_limit=100.0)
+    print(parity.describe(rep, sens))
+    err = rep["cfg_err"]
+    print("beyond 1e-9 / 1e-7 / 1e-6 / max:", int((err > 1e-9).sum()), int((err > 1e-7).sum()), int((err > 1e-6).sum()), float(err.max()))
+    assert rep["n_desync"] == 0
+    assert rep["discrete_ok"].all(), int((~rep["discrete_ok"]).sum())
+    assert rep["gpu_stats"] == rep["oracle_stats"]
+    assert (err > 1e-9).sum() <= 0.001 * n
+    assert (err > 1e-6).sum() <= 0.0002 * n
+    assert err.max() < 1e-2
