@@ -101,3 +101,15 @@ def test_arm_table_full_size_against_the_oracle():
     assert (err > 1e-9).sum() <= 0.001 * n
     assert (err > 1e-6).sum() <= 0.0002 * n
     assert err.max() < 1e-2
+
+
+def test_se3_highres_parity_in_the_full_size_environment():
+    """BASELINE config 4: the 511^3 SDF (534 MB, HBM-resident, no L2 window), 2 048 of its particles -- every second one driven
+    at a cuboid face -- in injection mode against the oracle in the same environment."""
+    n = 2048
+    w = W.se3_highres(n_particles=n)
+    rep, gpu, ref, sens = parity.run_parity(w, n)
+    print(parity.describe(rep, sens))
+    assert len(rep["bad_insensitive"]) == 0 and rep["n_desync"] == 0
+    assert rep["n_match"] >= 0.999 * n, rep["n_match"]
+    assert 0.2 < gpu.did_contact.mean() < 0.8 and int(gpu.n_resolver_iters.sum()) > 10 * n
