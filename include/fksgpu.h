@@ -273,7 +273,12 @@ int fks_forward_simulate_async(fks_sim* sim, const double* starts, const double*
 int fks_sim_synchronize(fks_sim* sim);
 
 /* Same with DEVICE buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream).
- * d_tape_draws / d_tape_offsets may be NULL unless noise_mode == FKS_NOISE_INJECTED. */
+ * d_tape_draws / d_tape_offsets may be NULL unless noise_mode == FKS_NOISE_INJECTED.
+ * Streams: a simulator owns ONE particle counter, context store and scratch, so its batch calls never overlap -- each launch
+ * records an event and the next launch of the same simulator, on whatever stream (a caller's or the simulator's own, which
+ * the host-buffer calls use), waits for it.  Calls on different streams are therefore safe and ordered by issue; for
+ * batches that should run concurrently use one simulator per stream.  Like the reference (spcs.hpp:846-850) a simulator
+ * serves one caller thread at a time. */
 int fks_forward_simulate_device(fks_sim* sim, const double* d_starts, const double* d_targets,
                                 size_t n_particles, size_t n_targets, int allow_contacts,
                                 int noise_mode, const double* d_tape_draws,
