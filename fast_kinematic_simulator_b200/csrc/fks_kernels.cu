@@ -1789,7 +1789,7 @@ __device__ __noinline__ void fill_noise(int wb, unsigned long long pid, unsigned
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// The kernel: a persistent grid, ONE CTA of up to 32 warps per SM; a warp works on one particle at a time.
+// The kernel: a persistent grid, ONE CTA of up to kWarpsPerBlock (24) warps per SM; a warp works on one particle at a time.
 //
 // The nested loops of the reference (controller step -> microstep -> resolver iteration) are flattened into a per-PARTICLE
 // state machine with two kinds of phases:
