@@ -1146,6 +1146,27 @@ __device__ __forceinline__ bool collect_self(int wb, int Xprev, int Xcur) {
                 const double d2 = segment_distance_sq(caps + 6 * a, caps + 6 * a + 3, caps + 6 * b, caps + 6 * b + 3);
                 const double reach = rb.cap_radius[a] + rb.cap_radius[b] + diag;
                 hit = d2 <= reach * reach;
+                // Only the cells at index 0 of an axis are two cells wide (they span -res .. +res of the grid coordinate): beyond
+                // the ordinary cell diagonal the two links can share a cell only if BOTH reach that slab on the same axis.
+                const double narrow = rb.cap_radius[a] + rb.cap_radius[b] + 0.5 * diag;
+                if (hit && d2 > narrow * narrow) {
+                    const DevEnv& e = fr.a.env;
+                    bool both = false;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        bool reaches[2];
+#pragma unroll
+                        for (int side = 0; side < 2; side++) {
+                            const double* c = caps + 6 * (side ? b : a);
+                            const double g0 = e.inv_origin[4 * k] * c[0] + e.inv_origin[4 * k + 1] * c[1] + e.inv_origin[4 * k + 2] * c[2] + e.inv_origin[4 * k + 3];
+                            const double g1 = e.inv_origin[4 * k] * c[3] + e.inv_origin[4 * k + 1] * c[4] + e.inv_origin[4 * k + 2] * c[5] + e.inv_origin[4 * k + 3];
+                            const double nearest = (g0 < 0.0) != (g1 < 0.0) ? 0.0 : fmin(fabs(g0), fabs(g1));
+                            reaches[side] = nearest - rb.cap_radius[side ? b : a] <= e.map_res * (1.0 + 1e-6) + 1e-9;
+                        }
+                        both = both || (reaches[0] && reaches[1]);
+                    }
+                    hit = both;
+                }
             }
         }
         const unsigned m = __ballot_sync(FKS_FULL, hit);
